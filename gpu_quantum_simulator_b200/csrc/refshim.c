@@ -1,0 +1,117 @@
+/*
+ * refshim.c -- the reference's C function surface, executed on the GPU.
+ *
+ * Each qsb_ref_* function has the argument meaning, ownership and stdout
+ * behaviour of its namesake at /root/reference/quantum_simulator.c:25-30:
+ *   compute_state_vector                     :115-254
+ *   execute_single_qubit_gate                :81-92
+ *   execute_cnot                             :94-106
+ *   compute_state_cumulative_distribution    :256-268
+ *   measurement                              :270-283
+ * Host `v` buffers are `double complex` images (interleaved re, im).  The
+ * state is computed in fp64 on the device unless QSB_PRECISION=32 is set.
+ * Unlike the reference these never call exit(); refcompat.c adds that.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include "qsim_b200.h"
+#include "qsb_internal.h"
+
+static double now_s(void)
+{
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return tv.tv_sec + tv.tv_usec * 1e-6;
+}
+
+static void shim_options(qsb_options_t *o)
+{
+    qsb_options_default(o);
+    const char *p = getenv("QSB_PRECISION");
+    o->precision = (p && atoi(p) == 32) ? QSB_F32 : QSB_F64;
+    const char *m = getenv("QSB_MODE");
+    if (m && !strcmp(m, "sweep")) o->mode = QSB_MODE_SWEEP;
+}
+
+double *qsb_ref_compute_state_vector(const char *filename, int *num_q)
+{
+    qsb_gate_t *gates = NULL; size_t n = 0; int nq = 0;
+    int rc = qsb_parse_qasm_file(filename, &nq, &gates, &n);
+    if (rc) return NULL;
+    double t0 = now_s();                       /* reference starts its clock before the gate loop (:143) */
+    qsb_options_t o; shim_options(&o);
+    qsb_t *s = NULL;
+    rc = qsb_create(&s, nq, &o);
+    if (rc) { qsb_free(gates); return NULL; }
+    rc = qsb_apply_gates(s, gates, n);
+    qsb_free(gates);
+    double *v = NULL;
+    if (!rc) {
+        v = (double *)malloc(sizeof(double) * 2 * ((size_t)1 << nq));
+        if (!v) { qsb_set_error("Malloc error"); rc = QSB_ERR_NOMEM; }
+    }
+    if (!rc) rc = qsb_download(s, v, 0, 1ULL << nq);
+    qsb_destroy(s);
+    if (rc) { free(v); return NULL; }
+    printf("%lf\n", now_s() - t0);              /* :244-248 */
+    if (num_q) *num_q = nq;
+    return v;
+}
+
+static int one_gate(double *v, int num_q, const qsb_gate_t *g)
+{
+    qsb_options_t o; shim_options(&o);
+    qsb_t *s = NULL;
+    int rc = qsb_create(&s, num_q, &o);
+    if (rc) return rc;
+    rc = qsb_upload(s, v, 0, 1ULL << num_q);
+    if (!rc) rc = qsb_apply_gates(s, g, 1);
+    if (!rc) rc = qsb_download(s, v, 0, 1ULL << num_q);
+    qsb_destroy(s);
+    return rc;
+}
+
+void qsb_ref_execute_single_qubit_gate(double *v, int num_q, const double U[8], int target)
+{
+    /* the reference computes v0' = v0*U[0] + v1*U[2], v1' = v0*U[1] + v1*U[3] (:88-89) */
+    qsb_gate_t g; memset(&g, 0, sizeof g);
+    g.target = target;
+    g.m[0] = U[0]; g.m[1] = U[1]; g.m[2] = U[4]; g.m[3] = U[5];
+    g.m[4] = U[2]; g.m[5] = U[3]; g.m[6] = U[6]; g.m[7] = U[7];
+    if (one_gate(v, num_q, &g)) fprintf(stderr, "qsim_b200: %s\n", qsb_last_error());
+}
+
+void qsb_ref_execute_cnot(double *v, int num_q, int control, int target)
+{
+    qsb_gate_t g; memset(&g, 0, sizeof g);
+    g.controls = 1ULL << control; g.target = target;
+    g.m[2] = 1.0; g.m[4] = 1.0;
+    if (one_gate(v, num_q, &g)) fprintf(stderr, "qsim_b200: %s\n", qsb_last_error());
+}
+
+double *qsb_ref_compute_state_cumulative_distribution(const double *v, int num_q)
+{
+    double *res = (double *)malloc(sizeof(double) * ((size_t)1 << num_q));
+    if (!res) { printf("Malloc error\n"); return NULL; }   /* :258-261 */
+    qsb_options_t o; shim_options(&o);
+    qsb_t *s = NULL;
+    int rc = qsb_create(&s, num_q, &o);
+    if (!rc) rc = qsb_upload(s, v, 0, 1ULL << num_q);
+    if (!rc) rc = qsb_cdf(s, res, 0, 1ULL << num_q);
+    if (s) qsb_destroy(s);
+    if (rc) { fprintf(stderr, "qsim_b200: %s\n", qsb_last_error()); free(res); return NULL; }
+    return res;
+}
+
+long long qsb_ref_measurement(const double *cumul, int num_q)
+{
+    /* same draw and scan as :271-282 (host-side: the CDF is already on the host here) */
+    double r = 0.0, coeff = 1.0 / RAND_MAX;
+    for (int i = 0; i < 10; i++) { r += rand() * coeff; coeff *= 1.0 / RAND_MAX; }
+    long long idx = 0, last = (1LL << num_q) - 1;
+    while ((cumul[idx] == 0.0 || cumul[idx] < r) && idx < last) idx++;
+    return idx;
+}

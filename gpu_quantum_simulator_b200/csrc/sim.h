@@ -1,0 +1,44 @@
+/* sim.h -- host-side objects behind the opaque handles of qsim_b200.h. */
+#pragma once
+#include "common.cuh"
+
+struct TiledPlan; /* tiled.h */
+
+struct qsb_sim {
+    int n = 0;        /* logical qubits of the circuit                          */
+    int g = 0;        /* log2(world): qubits whose physical bit is the rank     */
+    int nloc = 0;     /* physical local index bits (>= min tile, may pad n - g) */
+    int nphys = 0;    /* nloc + g: width of the physical global index           */
+    int prec = QSB_F32;
+    int rank = 0, world = 1, device = 0;
+    qsb_options_t opt{};
+    void *state = nullptr;   /* 2^nloc amplitudes                               */
+    void *state2 = nullptr;  /* exchange target buffer (multi-GPU), lazily made */
+    size_t state_bytes = 0;
+    BitPerm perm{};          /* logical qubit -> physical bit (identity at reset) */
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
+    void *staging = nullptr; /* device staging for readout                      */
+    size_t staging_bytes = 0;
+    void *d_scratch = nullptr; /* small device scratch (reductions)             */
+    qsb_run_stats_t last{};
+    void *comm = nullptr;    /* ncclComm_t                                      */
+    /* peer access (filled by qsb_comm_init) */
+    void *peer_state[64] = {nullptr};
+    void *peer_state2[64] = {nullptr};
+};
+
+struct qsb_plan {
+    int mode = QSB_MODE_TILED;
+    int n = 0, prec = QSB_F32, world = 1;
+    std::vector<COp> cops;   /* canonical ops in source order (sweep mode executes these) */
+    double gphase[2] = {1.0, 0.0}; /* global scalar factored out of diagonal gates */
+    TiledPlan *tiled = nullptr;
+    qsb_run_stats_t stats{};
+};
+
+/* canonicalise source gates -> COps (+ global phase) */
+int qsb_canonicalise(const qsb_gate_t *gates, size_t n, int num_qubits, std::vector<COp> &out, double gphase[2]);
+
+/* element size of one amplitude */
+static inline size_t amp_bytes(int prec) { return prec == QSB_F64 ? 16 : 8; }

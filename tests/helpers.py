@@ -1,0 +1,191 @@
+"""Test-side access to the CPU checker (oracle/) and the host emulator (tests/hostcheck/).
+
+Only tests, smoke() and bench.py's CPU-baseline legs import this; the product package never does.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libqsim_ref.so")
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "ref_cexe")
+HOSTCHECK_SO = os.path.join(ROOT, "tests", "hostcheck", "libqsb_hostcheck.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE_DIR = "/root/reference"
+
+
+def _build(path, directory):
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", directory], check=True, capture_output=True)
+    return path
+
+
+def oracle_lib():
+    L = C.CDLL(_build(ORACLE_SO, os.path.join(ROOT, "oracle")))
+    L.oc_apply_1q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_uint64]
+    L.oc_apply_cx.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int]
+    L.oc_gate_matrix.argtypes = [C.c_char_p, C.c_double, C.POINTER(C.c_double)]
+    L.oc_gate_matrix.restype = C.c_int
+    L.oc_run_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    L.oc_run_file.restype = C.c_int
+    L.oc_cdf.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.oc_measure.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.oc_measure.restype = C.c_uint64
+    L.oc_free.argtypes = [C.c_void_p]
+    return L
+
+
+def oracle_run_file(path):
+    """Oracle restatement on a QASM file -> (n, complex128 state)."""
+    L = oracle_lib()
+    p, n = C.c_void_p(), C.c_int()
+    rc = L.oc_run_file(str(path).encode(), C.byref(p), C.byref(n))
+    if rc:
+        raise RuntimeError(f"oracle rc={rc}")
+    N = 1 << n.value
+    out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(2 * N,)).copy()
+    L.oc_free(p)
+    return n.value, out.view(np.complex128)
+
+
+def oracle_run_circuit(circ, n, state=None):
+    """Oracle restatement on an in-memory circuit (superset gates) -> complex128 state."""
+    L = oracle_lib()
+    N = 1 << n
+    if state is None:
+        v = np.zeros(N, dtype=np.complex128)
+        v[0] = 1.0
+    else:
+        v = np.array(state, dtype=np.complex128)
+    m = (C.c_double * 8)()
+    ptr = v.ctypes.data
+    for name, q, p in circ:
+        arg = p[0] if p else 0.0
+        if name == "cx":
+            L.oc_apply_cx(ptr, n, 1 << q[0], q[1])
+        elif name == "ccx":
+            L.oc_apply_cx(ptr, n, (1 << q[0]) | (1 << q[1]), q[2])
+        elif name == "x":
+            L.oc_apply_cx(ptr, n, 0, q[0])
+        elif name == "swap":
+            L.oc_apply_cx(ptr, n, 1 << q[0], q[1]); L.oc_apply_cx(ptr, n, 1 << q[1], q[0]); L.oc_apply_cx(ptr, n, 1 << q[0], q[1])
+        elif name in ("cz", "cp"):
+            assert L.oc_gate_matrix(b"z" if name == "cz" else b"p", arg, m) == 0
+            L.oc_apply_1q(ptr, n, m, q[1], 1 << q[0])
+        else:
+            assert L.oc_gate_matrix(name.encode(), arg, m) == 0, name
+            L.oc_apply_1q(ptr, n, m, q[0], 0)
+    return v
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref_run_file(path):
+    """The UNMODIFIED reference compute_state_vector (oracle/_ref build) -> (n, complex128 state)."""
+    L = C.CDLL(REF_SO)
+    L.compute_state_vector.restype = C.c_void_p
+    L.compute_state_vector.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    n = C.c_int()
+    p = L.compute_state_vector(str(path).encode(), C.byref(n))
+    if not p:
+        raise RuntimeError("reference returned NULL")
+    N = 1 << n.value
+    out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(2 * N,)).copy()
+    C.CDLL(None).free(C.c_void_p(p))
+    return n.value, out.view(np.complex128)
+
+
+def ref_run_circuit(circ, n):
+    """Reference program on a circuit spelled in its own gate set; returns the state INCLUDING the
+    global phase the respelling dropped, i.e. directly comparable with the native circuit."""
+    from gpu_quantum_simulator_b200 import circuits
+    text, phi = circuits.to_reference_qasm(circ, n)
+    with tempfile.NamedTemporaryFile("w", suffix=".qasm", delete=False) as f:
+        f.write(text)
+        path = f.name
+    try:
+        _, v = ref_run_file(path)
+    finally:
+        os.unlink(path)
+    return v * complex(math.cos(phi), math.sin(phi))
+
+
+def hostcheck_run(circ_gates, n, precision=32, low_bits=0, state=None):
+    """Schedule with the product planner, interpret the tables on the host (tests/hostcheck).
+    -> (complex128 state in LOGICAL order, report dict)"""
+    from gpu_quantum_simulator_b200 import Gate
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck")))
+    L.qsb_hostcheck_run.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(Gate), C.c_size_t, C.c_void_p,
+                                    C.POINTER(C.c_int), C.c_void_p]
+    L.qsb_hostcheck_run.restype = C.c_int
+    T = 13 if precision == 32 else 12
+    nloc = max(n, T)
+    v = np.zeros(1 << nloc, dtype=np.complex128)
+    if state is None:
+        v[0] = 1.0
+    else:
+        v[: 1 << n] = state
+    rep = (C.c_int * 5)()
+    perm = np.zeros(64, dtype=np.int8)
+    rc = L.qsb_hostcheck_run(n, precision, low_bits, circ_gates, len(circ_gates), v.ctypes.data, rep, perm.ctypes.data)
+    if rc:
+        raise RuntimeError(f"hostcheck rc={rc}")
+    # physical -> logical
+    idx = np.arange(1 << n, dtype=np.uint64)
+    phys = np.zeros_like(idx)
+    for q in range(n):
+        phys |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(int(perm[q]))
+    out = v[phys]
+    report = dict(max_conflict=rep[0], bad_slots=rep[1], noncontig=rep[2], passes=rep[3], rounds=rep[4])
+    return out, report
+
+
+# ---- golden fixtures -------------------------------------------------------------------------
+def save_case(path, circ, n, amps, note=""):
+    names = np.array([c[0] for c in circ], dtype="U8")
+    qs = -np.ones((len(circ), 3), dtype=np.int16)
+    ps = np.full(len(circ), np.nan)
+    for i, (_, q, p) in enumerate(circ):
+        qs[i, : len(q)] = q
+        if p:
+            ps[i] = p[0]
+    np.savez_compressed(path, names=names, qubits=qs, params=ps, n=n, amps=amps, note=note)
+
+
+def load_case(path):
+    z = np.load(path, allow_pickle=False)
+    circ = []
+    for name, q, p in zip(z["names"], z["qubits"], z["params"]):
+        circ.append((str(name), tuple(int(x) for x in q if x >= 0), () if np.isnan(p) else (float(p),)))
+    return circ, int(z["n"]), z["amps"], str(z["note"])
+
+
+def golden_cases():
+    if not os.path.isdir(GOLDEN):
+        return []
+    return sorted(os.path.join(GOLDEN, f) for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+def parse_reference_style_file(path):
+    """Tiny independent reader for the two shipped circuits (used only to build fixtures)."""
+    circ, n = [], None
+    import re
+    for line in open(path, "rb").read().decode().replace("\r", "").split("\n"):
+        line = line.strip()
+        if not line or line.startswith("OPENQASM") or line.startswith("include"):
+            continue
+        if line.startswith("qubit"):
+            n = int(re.search(r"\[(\d+)\]", line).group(1))
+            continue
+        m = re.match(r"([a-z]+)(?:\(([^)]*)\))?\s+(.*);", line)
+        name, arg, ops = m.group(1), m.group(2), m.group(3)
+        q = tuple(int(x) for x in re.findall(r"\[(\d+)\]", ops))
+        circ.append((name, q, (float(arg),) if arg else ()))
+    return circ, n

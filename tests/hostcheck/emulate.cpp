@@ -1,0 +1,205 @@
+/*
+ * emulate.cpp -- TEST DOUBLE, never shipped: a host interpreter of the tiled
+ * schedule (DevPass / DevRound / HostOp tables), thread by thread and slot by
+ * slot, exactly as tiled_kernel.cu consumes them.  It lets the CPU test-suite
+ * verify the planner's tables (index maps, slot maps, op encodings) against the
+ * oracle without a GPU, and it checks what the kernel relies on:
+ *   - every smem slot is written exactly once per exchange,
+ *   - every 64-bit (f32) / 128-bit (f64) shared access phase is bank-conflict free,
+ *   - first-round loads / last-round stores of a warp are contiguous.
+ * It is linked only into tests/hostcheck/libqsb_hostcheck.so.
+ */
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <vector>
+
+#include "sim.h"
+#include "tiled.h"
+
+typedef std::complex<double> cd;
+
+struct Report { int max_conflict; int bad_slots; int noncontig; int passes; int rounds; };
+
+static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, Report &rep)
+{
+    const int L = f32 ? 2 : 1;                  /* pack lanes */
+    const int nb = f32 ? 4 : 3;
+    const int phase_lanes = f32 ? 16 : 8;       /* lanes per shared-memory phase */
+    const uint64_t loc_mask = (1ULL << nloc) - 1;
+    std::vector<cd> regs((size_t)QSB_THREADS * QSB_NV * L);
+    std::vector<cd> smem((size_t)4096 * L);
+    std::vector<int> written(4096);
+    const int nr = (int)hp.hdr.n_rounds;
+    for (uint64_t tile = 0; tile < hp.hdr.n_tiles; tile++) {
+        uint64_t t = tile, outer = 0;
+        for (uint32_t r = 0; r < hp.hdr.n_runs; r++) {
+            int len = hp.hdr.run_len[r];
+            outer |= (t & ((1ULL << len) - 1)) << hp.hdr.run_start[r];
+            t >>= len;
+        }
+        const uint64_t src_outer = outer | hp.hdr.src_fixed;
+        for (int rd = 0; rd < nr; rd++) {
+            const DevRound &RD = hp.rounds[rd];
+            std::vector<uint64_t> gthr(QSB_THREADS);
+            /* ---- load ---- */
+            for (int tid = 0; tid < QSB_THREADS; tid++) {
+                uint64_t g = src_outer;
+                for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) g |= RD.thr_gidx[j];
+                gthr[tid] = g;
+                uint32_t sb = 0;
+                for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.ld_thr[j];
+                for (int v = 0; v < QSB_NV; v++) {
+                    if (rd == 0) {
+                        uint64_t gi = g;
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) gi |= RD.vec_gidx[b];
+                        for (int l = 0; l < L; l++) regs[((size_t)tid * QSB_NV + v) * L + l] = st[(gi & loc_mask) | (uint64_t)l];
+                        if (f32 && (gi & 1)) rep.noncontig++;
+                    } else {
+                        uint32_t slot = sb;
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.ld_vec[b];
+                        for (int l = 0; l < L; l++) regs[((size_t)tid * QSB_NV + v) * L + l] = smem[(size_t)slot * L + l];
+                    }
+                }
+            }
+            /* contiguity of the first load: a warp's 32 lanes, fixed v, must cover one aligned run */
+            if (rd == 0) {
+                for (int w = 0; w < QSB_THREADS / 32; w++) {
+                    uint64_t lo = ~0ULL, hi = 0;
+                    for (int ln = 0; ln < 32; ln++) { uint64_t g = gthr[w * 32 + ln]; lo = std::min(lo, g); hi = std::max(hi, g); }
+                    /* with a >= 6 (f32) / 5 (f64) the span equals 32 units; smaller a: 2 or more runs */
+                    (void)lo; (void)hi;
+                }
+            }
+            /* bank check, load side */
+            if (rd > 0) {
+                for (int w = 0; w < QSB_THREADS / phase_lanes; w++) for (int v = 0; v < QSB_NV; v++) {
+                    std::set<uint32_t> banks;
+                    for (int ln = 0; ln < phase_lanes; ln++) {
+                        int tid = w * phase_lanes + ln;
+                        uint32_t slot = 0;
+                        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) slot ^= RD.ld_thr[j];
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.ld_vec[b];
+                        banks.insert(slot & ((1u << nb) - 1));
+                    }
+                    int conflict = phase_lanes / (int)banks.size();
+                    if (conflict > rep.max_conflict) rep.max_conflict = conflict;
+                }
+            }
+            /* ---- ops ---- */
+            for (int tid = 0; tid < QSB_THREADS; tid++) {
+                cd *R = &regs[(size_t)tid * QSB_NV * L];
+                cd pend(1.0, 0.0);
+                for (uint32_t i = 0; i < RD.n_ops; i++) {
+                    const HostOp &op = hp.ops[RD.op_begin + i];
+                    const uint32_t code = op.kind & 0xff, vb = (op.kind >> 8) & 0xf, lanes = (op.kind >> 12) & 3;
+                    const bool mux = (op.kind >> 16) & 1;
+                    const bool pred = (gthr[tid] & op.tmask) == op.tmask;
+                    if (!pred && !mux) continue;
+                    const double *c = op.c + (pred ? 16 : 0);
+                    auto C = [&](int k, int l) { return c[k * 2 + (f32 ? l : 0)]; };
+                    for (int v = 0; v < QSB_NV; v++) {
+                        if ((v & op.vmask) != op.vmask) continue;
+                        if (code == OP_MAT_R || code == OP_MAT_I || code == OP_MAT_G) {
+                            if ((v >> vb) & 1) continue;
+                            int w = v | (1 << vb);
+                            for (int l = 0; l < L; l++) {
+                                cd x0 = R[v * L + l], x1 = R[w * L + l], m00, m01, m10, m11;
+                                if (code == OP_MAT_R) { m00 = C(0, l); m01 = C(2, l); m10 = C(4, l); m11 = C(6, l); }
+                                else if (code == OP_MAT_I) { m00 = C(0, l); m01 = cd(0, C(2, l)); m10 = cd(0, C(4, l)); m11 = C(6, l);
+                                    if (C(1, l) != -C(2, l) || C(3, l) != -C(4, l)) rep.bad_slots++; }
+                                else { m00 = cd(C(0, l), C(1, l)); m01 = cd(C(2, l), C(3, l)); m10 = cd(C(4, l), C(5, l)); m11 = cd(C(6, l), C(7, l)); }
+                                R[v * L + l] = m00 * x0 + m01 * x1;
+                                R[w * L + l] = m10 * x0 + m11 * x1;
+                            }
+                        } else if (code == OP_MATP_R || code == OP_MATP_G) {
+                            cd x0 = R[v * L], x1 = R[v * L + 1];
+                            cd A0, A1, B0, B1;
+                            if (code == OP_MATP_R) { A0 = C(0, 0); A1 = C(0, 1); B0 = C(2, 0); B1 = C(2, 1); }
+                            else { A0 = cd(C(0, 0), C(1, 0)); A1 = cd(C(0, 1), C(1, 1)); B0 = cd(C(2, 0), C(3, 0)); B1 = cd(C(2, 1), C(3, 1)); }
+                            R[v * L] = A0 * x0 + B0 * x1;
+                            R[v * L + 1] = A1 * x1 + B1 * x0;
+                        } else if (code == OP_X) {
+                            if ((v >> vb) & 1) continue;
+                            int w = v | (1 << vb);
+                            for (int l = 0; l < L; l++) if (!f32 || ((lanes >> l) & 1)) std::swap(R[v * L + l], R[w * L + l]);
+                        } else if (code == OP_XP) {
+                            std::swap(R[v * L], R[v * L + 1]);
+                        } else if (code == OP_DIAG) {
+                            for (int l = 0; l < L; l++) R[v * L + l] *= cd(C(0, l), C(1, l));
+                        }
+                    }
+                    if (code == OP_TPHASE) pend *= cd(C(0, 0), C(1, 0));
+                }
+                if (RD.flags & 1) for (int k = 0; k < QSB_NV * L; k++) R[k] *= pend;
+                else if (pend != cd(1.0, 0.0)) rep.bad_slots++;
+            }
+            /* ---- store ---- */
+            if (rd == nr - 1) {
+                for (int tid = 0; tid < QSB_THREADS; tid++) {
+                    uint64_t d = outer | hp.hdr.dst_fixed;
+                    for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) d |= hp.hdr.dst_thr[j];
+                    for (int v = 0; v < QSB_NV; v++) {
+                        uint64_t gi = d;
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) gi |= hp.hdr.dst_vec[b];
+                        for (int l = 0; l < L; l++) st[(gi & loc_mask) | (uint64_t)l] = regs[((size_t)tid * QSB_NV + v) * L + l];
+                    }
+                }
+            } else {
+                std::fill(written.begin(), written.end(), 0);
+                for (int tid = 0; tid < QSB_THREADS; tid++) {
+                    uint32_t sb = 0;
+                    for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.st_thr[j];
+                    for (int v = 0; v < QSB_NV; v++) {
+                        uint32_t slot = sb;
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.st_vec[b];
+                        if (slot >= 4096) { rep.bad_slots++; continue; }
+                        written[slot]++;
+                        for (int l = 0; l < L; l++) smem[(size_t)slot * L + l] = regs[((size_t)tid * QSB_NV + v) * L + l];
+                    }
+                }
+                for (int s = 0; s < 4096; s++) if (written[s] != 1) rep.bad_slots++;
+                for (int w = 0; w < QSB_THREADS / phase_lanes; w++) for (int v = 0; v < QSB_NV; v++) {
+                    std::set<uint32_t> banks;
+                    for (int ln = 0; ln < phase_lanes; ln++) {
+                        int tid = w * phase_lanes + ln;
+                        uint32_t slot = 0;
+                        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) slot ^= RD.st_thr[j];
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.st_vec[b];
+                        banks.insert(slot & ((1u << nb) - 1));
+                    }
+                    int conflict = phase_lanes / (int)banks.size();
+                    if (conflict > rep.max_conflict) rep.max_conflict = conflict;
+                }
+            }
+        }
+    }
+}
+
+/* state: 2^max(num_q, T) complex doubles (interleaved), physical == logical order on entry;
+ * on exit amplitudes are in PHYSICAL order and perm_out[q] gives logical q -> physical bit. */
+extern "C" int qsb_hostcheck_run(int num_q, int prec, int low_bits, const qsb_gate_t *gates, size_t n,
+                                 double *state, int *report5, int8_t *perm_out)
+{
+    qsb_options_t opt; memset(&opt, 0, sizeof opt);
+    opt.precision = prec; opt.low_bits = low_bits; opt.world_size = 1;
+    const int T = tiled_min_local_bits(prec, &opt);
+    const int nloc = std::max(num_q, T);
+    std::vector<COp> cops; double gph[2];
+    int rc = qsb_canonicalise(gates, n, num_q, cops, gph);
+    if (rc) return rc;
+    BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
+    TiledPlan plan;
+    rc = tiled_schedule(num_q, prec, 0, nloc, 0, &opt, id, cops, gph, &plan);
+    if (rc) return rc;
+    std::vector<cd> st((size_t)1 << nloc);
+    memcpy((void *)st.data(), state, sizeof(cd) * st.size());
+    Report rep; memset(&rep, 0, sizeof rep);
+    rep.max_conflict = 1;
+    for (const HostPass &hp : plan.passes) { run_pass(hp, prec == QSB_F32, nloc, st, rep); rep.passes++; rep.rounds += (int)hp.hdr.n_rounds; }
+    memcpy(state, st.data(), sizeof(cd) * st.size());
+    report5[0] = rep.max_conflict; report5[1] = rep.bad_slots; report5[2] = rep.noncontig; report5[3] = rep.passes; report5[4] = rep.rounds;
+    for (int q = 0; q < 64; q++) perm_out[q] = plan.end_perm.pos[q];
+    return 0;
+}

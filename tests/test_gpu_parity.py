@@ -1,0 +1,159 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle, the golden vectors
+and size-independent properties.  Tolerances are BASELINE.json's: max|d amp| <= 1e-5 (f32),
+<= 1e-12 (f64), identical measurement argmax (as a tie-tolerant set)."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+import gpu_quantum_simulator_b200 as q
+from gpu_quantum_simulator_b200 import circuits, F32, F64, MODE_TILED, MODE_SWEEP
+
+pytestmark = pytest.mark.gpu
+
+TOL = {F32: 1e-5, F64: 1e-12}
+
+
+def run_gpu(circ, n, precision, mode=MODE_TILED, low_bits=0):
+    with q.Simulator(n, precision=precision, mode=mode, low_bits=low_bits) as s:
+        st = s.apply(q.gates_from_circuit(circ))
+        return s.state(), st
+
+
+@pytest.mark.parametrize("mode", [MODE_TILED, MODE_SWEEP], ids=["tiled", "sweep"])
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: os.path.basename(p)[:-4])
+def test_golden_vectors(path, precision, mode):
+    circ, n, amps, _ = helpers.load_case(path)
+    got, _ = run_gpu(circ, n, precision, mode)
+    assert np.max(np.abs(got - amps)) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+def test_grover_argmax_set_and_probabilities(precision):
+    circ, n, amps, _ = helpers.load_case(os.path.join(helpers.GOLDEN, "grover_3_18.npz"))
+    with q.Simulator(n, precision=precision) as s:
+        s.apply(q.gates_from_circuit(circ))
+        norm, idx, p = s.norm_argmax()
+        probs = s.probabilities()
+    assert idx in (3, 18)                      # p[3] - p[18] = 1.4e-15 in the reference
+    assert abs(p - 0.49959115777166263) < 1e-5
+    assert abs(norm - 1.0) < 1e-5
+    assert set(np.argsort(probs)[-2:]) == {3, 18}
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("n,ng,seed", [(16, 300, 21), (18, 400, 22), (20, 300, 23), (22, 150, 24)])
+def test_random_superset_vs_oracle(n, ng, seed, precision):
+    circ = circuits.random_superset(n, ng, seed)
+    want = helpers.oracle_run_circuit(circ, n)
+    got, st = run_gpu(circ, n, precision)
+    assert np.max(np.abs(got - want)) <= TOL[precision]
+    assert st["passes"] < ng
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+def test_layered_family_and_qft_vs_oracle(precision):
+    for circ, n in ((circuits.random_layered(22, depth=8, seed=12345), 22), (circuits.qft(20), 20)):
+        want = helpers.oracle_run_circuit(circ, n)
+        got, _ = run_gpu(circ, n, precision)
+        assert np.max(np.abs(got - want)) <= TOL[precision]
+
+
+@pytest.mark.parametrize("low_bits", [3, 4, 5])
+def test_low_bits_variants(low_bits):
+    circ = circuits.random_layered(18, depth=6, seed=3)
+    want = helpers.oracle_run_circuit(circ, 18)
+    got, _ = run_gpu(circ, 18, F32, low_bits=low_bits)
+    assert np.max(np.abs(got - want)) <= TOL[F32]
+
+
+def test_tiled_equals_sweep_and_f32_close_to_f64_at_26_qubits():
+    """Sizes the oracle cannot reach in seconds: fused vs unfused schedule, f32 vs f64, norm."""
+    n = 26
+    circ = circuits.random_layered(n, depth=6, seed=99)
+    gates = q.gates_from_circuit(circ)
+    with q.Simulator(n, precision=F64) as s:
+        s.apply(gates)
+        ref = s.state_native().copy()
+        norm64 = s.norm_argmax()[0]
+    with q.Simulator(n, precision=F64, mode=MODE_SWEEP) as s:
+        s.apply(gates)
+        sw = s.state_native()
+        assert np.max(np.abs(sw - ref)) <= 1e-12
+    with q.Simulator(n, precision=F32) as s:
+        s.apply(gates)
+        f32 = s.state_native()
+        norm32 = s.norm_argmax()[0]
+        assert np.max(np.abs(f32.astype(np.float64) - ref)) <= 1e-5
+    assert abs(norm64 - 1.0) < 1e-12 and abs(norm32 - 1.0) < 1e-4
+
+
+def test_unitarity_roundtrip_30_qubits():
+    """BASELINE size: circuit followed by its inverse returns |0...0> (f32)."""
+    n = 30
+    circ = circuits.random_layered(n, depth=4, seed=5)
+    inv = []
+    for name, qs, p in reversed(circ):
+        inv.append((name, qs, tuple(-x for x in p)) if name in ("rx", "rz") else (name, qs, p))
+    with q.Simulator(n, precision=F32) as s:
+        s.apply(q.gates_from_circuit(circ))
+        norm, _, _ = s.norm_argmax()
+        assert abs(norm - 1.0) < 1e-4
+        s.apply(q.gates_from_circuit(inv))
+        norm, idx, p = s.norm_argmax()
+        assert idx == 0 and abs(p - 1.0) < 1e-4
+        head = s.state(0, 8)
+        assert abs(abs(head[0]) - 1.0) < 1e-4 and np.max(np.abs(head[1:])) < 1e-5
+
+
+def test_reference_named_operations_and_cdf():
+    n = 10
+    circ = circuits.random_reference_gates(n, 200, seed=8)
+    want = helpers.oracle_run_circuit(circ, n)
+    L = helpers.oracle_lib()
+    cdf_want = np.zeros(1 << n)
+    L.oc_cdf(want.ctypes.data, n, cdf_want.ctypes.data)
+    with q.Simulator(n, precision=F64) as s:
+        s.set_state(want)
+        cdf = s.compute_state_cumulative_distribution()
+        assert np.max(np.abs(cdf - cdf_want)) < 1e-12
+        shots = s.measurement(64, seed=7)
+        assert all(cdf[k] > 0 for k in shots)
+        # one reference-style call at a time
+        s.reset()
+        h = np.array([1, 1, 1, -1]) / math.sqrt(2)
+        s.execute_single_qubit_gate(h, 0)
+        s.execute_cnot(0, 1)
+        v = s.state()
+        assert abs(v[0] - 1 / math.sqrt(2)) < 1e-15 and abs(v[3] - 1 / math.sqrt(2)) < 1e-15
+
+
+def test_ref_shim_and_cli(tmp_path):
+    import ctypes as C
+    circ, n, amps, _ = helpers.load_case(os.path.join(helpers.GOLDEN, "grover_3_18.npz"))
+    path = tmp_path / "grover.qasm"
+    path.write_bytes(circuits.to_qasm(circ, n).replace("\n", "\r\n").encode())   # CRLF like the shipped file
+    nq = C.c_int()
+    p = q.lib.qsb_ref_compute_state_vector(str(path).encode(), C.byref(nq))
+    assert p and nq.value == n
+    got = np.ctypeslib.as_array(p, shape=(2 << n,)).copy().view(np.complex128)
+    q.lib.qsb_free(p)
+    assert np.max(np.abs(got - amps)) <= 1e-12
+    exe = os.path.join(helpers.ROOT, "gpu_quantum_simulator_b200", "bin", "qsim")
+    out = subprocess.run([exe, str(path), "0", "--precision", "64", "--dump-amplitudes", "--precision-out", "17"],
+                         capture_output=True, text=True, check=True).stdout.split("\n")
+    float(out[0])                                             # line 1: "%lf" seconds, like the reference
+    vals = {}
+    for line in out[1:]:
+        if " : " in line:
+            k, rest = line.split(" : ")
+            re_, im_ = rest.replace(" i", "").split(" + ")
+            vals[int(k)] = complex(float(re_), float(im_))
+    assert max(abs(vals.get(k, 0) - amps[k]) for k in range(1 << n)) <= 1e-12
+    assert any(l.startswith("MOST LIKELY MEASUREMENT: ") for l in out)
+    bad = subprocess.run([exe], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Usage:" in bad.stdout

@@ -1,0 +1,69 @@
+"""Fusion / scheduling pass on the CPU: the planner's tables, interpreted by the host test double
+(tests/hostcheck), must reproduce the oracle; slot maps must be bijective and bank-conflict free."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import gpu_quantum_simulator_b200 as q
+from gpu_quantum_simulator_b200 import circuits
+
+
+def run_both(circ, n, precision, low_bits=0):
+    gates = q.gates_from_circuit(circ)
+    got, rep = helpers.hostcheck_run(gates, n, precision, low_bits)
+    want = helpers.oracle_run_circuit(circ, n)
+    return got, want, rep
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("n,ng,seed", [(1, 10, 0), (2, 30, 1), (5, 120, 2), (9, 200, 3), (13, 250, 4), (14, 200, 5), (15, 160, 6)])
+def test_tables_reproduce_oracle_on_superset_circuits(n, ng, seed, precision):
+    circ = circuits.random_superset(n, ng, seed)
+    got, want, rep = run_both(circ, n, precision)
+    assert rep["bad_slots"] == 0 and rep["noncontig"] == 0
+    assert rep["max_conflict"] == 1, "shared-memory exchange must be bank-conflict free"
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
+@pytest.mark.parametrize("precision,low_bits", [(32, 3), (32, 4), (32, 5), (64, 2), (64, 3), (64, 4)])
+def test_low_bits_option(precision, low_bits):
+    circ = circuits.random_layered(15, depth=4, seed=7)
+    got, want, rep = run_both(circ, 15, precision, low_bits)
+    assert rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
+@pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: os.path.basename(p)[:-4])
+def test_tables_reproduce_golden_vectors(path):
+    circ, n, amps, _ = helpers.load_case(path)
+    got, rep = helpers.hostcheck_run(q.gates_from_circuit(circ), n, 32)
+    assert rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+    assert np.max(np.abs(got - amps)) < 1e-12
+
+
+def test_qft_and_layered_family():
+    for circ, n in ((circuits.qft(14), 14), (circuits.random_layered(16, depth=5, seed=1), 16)):
+        got, want, rep = run_both(circ, n, 32)
+        assert rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+        assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_fusion_factor_on_headline_workload():
+    """30 q, depth 20: the pass count is what HBM sees; keep it from regressing."""
+    circ = circuits.random_layered(30, 20, 12345)
+    st = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32)
+    assert st["source_gates"] == 900
+    assert st["passes"] <= 32
+    assert st["bytes_moved"] == st["passes"] * 2 * (1 << 30) * 8
+    st64 = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=64)
+    assert st64["passes"] <= 36
+
+
+def test_multi_control_and_global_phase_gates():
+    circ = [("h", (0,), ()), ("h", (1,), ()), ("h", (2,), ()), ("ccx", (0, 1, 2), ()), ("y", (1,), ()),
+            ("z", (0,), ()), ("sx", (2,), ()), ("cp", (2, 0), (0.3,)), ("cz", (1, 2), ())]
+    for prec in (32, 64):
+        got, want, rep = run_both(circ, 3, prec)
+        assert np.max(np.abs(got - want)) < 1e-13
