@@ -39,12 +39,13 @@ template <> struct Lay<double> {
     } while (0)
 
 /* Canonical op: what a source gate becomes before scheduling (logical qubits). */
-enum { C_MAT = 0, C_PHASE = 1, C_X = 2 };
+enum { C_MAT = 0, C_PHASE = 1, C_X = 2, C_MUX = 3 };
 struct COp {
     int kind;
-    int target;      /* C_MAT / C_X */
+    int target;      /* C_MAT / C_X / C_MUX */
     uint64_t ctrl;   /* control mask; for C_PHASE the full mask the phase is conditioned on */
-    double m[8];     /* C_MAT: row-major 2x2; C_PHASE: m[0], m[1] = phase (re, im) */
+    double m[8];     /* C_MAT: row-major 2x2; C_PHASE: m[0], m[1] = phase (re, im); C_MUX: matrix when the controls are NOT all set */
+    double m2[8];    /* C_MUX: matrix when all controls are set (a CX absorbed into a neighbouring gate) */
 };
 
 struct BitPerm { int8_t pos[64]; }; /* logical qubit -> physical bit position */

@@ -20,6 +20,10 @@
  * shared memory with a GF(2)-linear slot map chosen by the planner so that
  * both the store of round k and the load of round k+1 are bank-conflict free.
  *
+ * The whole description of a pass (header, per-round tables, op stream) is a
+ * few KiB and travels as a __grid_constant__ kernel parameter: every table and
+ * coefficient read is a constant-bank load, no global traffic besides the state.
+ *
  * Replaces (reference, /root/reference/): the per-gate launches of
  * naive.cu:163-189, the 2x2/4x4 host fusion of preproces.cu:215-269 and
  * 4x4.cu:327-501, and the static relabel of 4x4_permute.cu:350-434.
@@ -37,53 +41,58 @@
 #define QSB_T_F32 13           /* tile bits f32: pack + NVB + TB             */
 #define QSB_T_F64 12           /* tile bits f64: NVB + TB                    */
 #define QSB_MAX_RUNS 16
+#define QSB_BLOB_SMALL 4000    /* pass descriptor sizes (kernel parameter)   */
+#define QSB_BLOB_LARGE 32000
 
 /* ---- op codes ---------------------------------------------------------- */
 enum {
-    OP_END = 0,
-    OP_MAT_R = 1,  /* target = vector bit; all entries real                  */
-    OP_MAT_I = 2,  /* target = vector bit; real diagonal, imaginary off-diag */
-    OP_MAT_G = 3,  /* target = vector bit; general complex                   */
-    OP_MATP_R = 4, /* target = pack bit (f32 only); real                     */
-    OP_MATP_G = 5, /* target = pack bit (f32 only); general                  */
-    OP_X = 6,      /* swap along a vector bit (X / CX / CCX ...)             */
-    OP_XP = 7,     /* swap along the pack bit                                */
-    OP_DIAG = 8,   /* phase on vectors selected by vmask (per pack lane)     */
-    OP_TPHASE = 9, /* thread-level phase: folded into a per-thread scalar    */
+    OP_MAT_R = 1,    /* target = vector bit; all entries real                  */
+    OP_MAT_I = 2,    /* target = vector bit; real diagonal, imaginary off-diag */
+    OP_MAT_G = 3,    /* target = vector bit; general complex                   */
+    OP_MATP_R = 4,   /* target = pack bit (f32 only); real                     */
+    OP_MATP_G = 5,   /* target = pack bit (f32 only); general                  */
+    /* 6..8 unused: X / CX are issued as OP_MAT_R / OP_MATP_R with [[0,1],[1,0]]   */
+    OP_DIAG_V = 9,   /* phase on the vectors whose vector bit `vb` is set      */
+    OP_DIAG_ALL = 10,/* phase on all vectors (lane-dependent, e.g. rz on the pack qubit) */
+    OP_DIAG_GEN = 11,/* phase on vectors with (v & vmask) == vmask, vmask in kind bits 20..23 */
+    OP_TPHASE = 12,  /* thread-level phase: folded into a per-thread scalar    */
 };
 
-/* kind = opcode | vb << 8 | lanes << 12 | mux << 16
- *   vb    : target vector bit (OP_MAT_*, OP_X)
- *   lanes : which pack lanes the op acts on (bit0 = lane .x, bit1 = .y); f64: 1
+/* kind = opcode | vb << 8 | mux << 16 | vmask << 20
+ *   vb    : target vector bit (OP_MAT_*, OP_X*, OP_DIAG_V)
  *   mux   : thread-level multiplexer: threads whose tmask test fails use
- *           coefficient set 0 instead of skipping                           */
-#define OPK(op, vb, lanes, mux) ((uint32_t)(op) | ((uint32_t)(vb) << 8) | ((uint32_t)(lanes) << 12) | ((uint32_t)(mux) << 16))
+ *           coefficient set 0 instead of skipping (set 1 follows set 0)       */
+#define OPK(op, vb, mux, vmask) ((uint32_t)(op) | ((uint32_t)(vb) << 8) | ((uint32_t)(mux) << 16) | ((uint32_t)(vmask) << 20))
 
-/* One device op.  Same byte size for both precisions (144 B):
- *   f32: c[32] = two sets of 8 coefficient VECTORS (lo, hi pack lane)
- *   f64: c[16] = two sets of 8 coefficients
- * Coefficient order inside a set: m00r m00i m01r m01i m10r m10i m11r m11i
- * (R form uses the four real parts, I form uses m00r m01i m10i m11r).
- * OP_DIAG / OP_TPHASE use the first two entries of set 1 as the phase.       */
-template <typename R> struct DevOp {
+/* Op stream element: 16-byte header followed by the coefficient payload.
+ * Payload entries are 8 bytes in both precisions: f32 = (lo lane, hi lane)
+ * float2, f64 = one double.
+ *   OP_MAT_R : m00 m01 m10 m11                       (4 entries per set)
+ *   OP_MAT_I : a -b b -c c d  for [[a, ib],[ic, d]]  (6 entries per set)
+ *   OP_MAT_G : m00r m00i m01r m01i m10r m10i m11r m11i (8 entries per set)
+ *   OP_MATP_R: A B          out = A*x + B*swap(x), A=(m00,m11) B=(m01,m10)
+ *   OP_MATP_G: Ar Ai Br Bi
+ *   OP_DIAG_*: pr pi
+ *   OP_TPHASE: 16 bytes holding (pr, pi) as two scalars of the state precision */
+struct OpHdr {
     uint32_t kind;
-    uint32_t vmask;  /* condition on the vector index: (v & vmask) == vmask   */
-    uint64_t tmask;  /* condition on the thread's physical index bits         */
-    R c[128 / sizeof(R)];
+    uint32_t size16; /* header + payload, in 16-byte units */
+    uint64_t tmask;  /* condition on the thread's physical index bits */
 };
 
-/* Uniform per-round tables. */
+struct BitEntry {      /* one thread bit or vector bit of a round */
+    uint64_t gidx;     /* physical SOURCE index bit(s) it stands for (tmask tests; round 0: load address) */
+    uint16_t ld, st;   /* smem slot XOR constants, load side / store side */
+    uint32_t pad;
+};
+
 struct DevRound {
     uint32_t n_ops;
-    uint32_t op_begin;          /* index into the pass' op array              */
+    uint32_t op_off16;          /* op stream start, 16-byte units from the blob start */
     uint32_t flags;             /* bit0: round has OP_TPHASE ops              */
     uint32_t pad;
-    uint64_t thr_gidx[QSB_TB];  /* thread bit j set -> these physical SOURCE index bits are set (for tmask tests; round 0: load address) */
-    uint64_t vec_gidx[QSB_NVB]; /* same for the vector bits (round 0: load address)  */
-    uint16_t ld_thr[QSB_TB];    /* smem slot XOR constants, load side (unused in round 0)   */
-    uint16_t ld_vec[QSB_NVB];
-    uint16_t st_thr[QSB_TB];    /* store side (unused in the last round)      */
-    uint16_t st_vec[QSB_NVB];
+    BitEntry thr[QSB_TB];
+    BitEntry vec[QSB_NVB];
 };
 
 struct DevPass {
@@ -98,26 +107,33 @@ struct DevPass {
     uint32_t nloc;              /* local index bits: index >> nloc selects the source rank   */
     uint32_t out_of_place;      /* 1: write to the second buffer              */
     uint64_t n_tiles;
+    uint32_t rounds_off16;      /* DevRound array, 16-byte units from the blob start */
+    uint32_t blob_bytes;
 };
 
+template <int BYTES> struct PassBlob { uint4 q[BYTES / 16]; };
+
 /* ---- host-side plan ----------------------------------------------------- */
-struct HostOp {              /* precision-independent, fp64 coefficients      */
+struct HostOp {              /* precision-independent; lane-expanded fp64 coefficients */
     uint32_t kind;
-    uint32_t vmask;
     uint64_t tmask;
-    double c[32];            /* f32 layout (lane-expanded); f64 uses even entries' .lo semantics, see pack_op() */
+    int n_coef;              /* payload entries per set */
+    double c[2][8][2];       /* [set][entry][lane] */
+    double tph[2];           /* OP_TPHASE */
 };
 
 struct HostPass {
     DevPass hdr;
     std::vector<DevRound> rounds;
     std::vector<HostOp> ops;
+    std::vector<uint8_t> blob;           /* serialised kernel parameter        */
     /* bookkeeping for tests / emulation */
     int T = 0;                           /* tile bits                          */
     int8_t tile_src[16];                 /* tile bit j -> source physical bit  */
     int8_t tile_dst[16];                 /* tile bit j -> destination physical bit */
     std::vector<std::vector<int8_t>> round_thr; /* per round: thread bit j -> tile bit */
     std::vector<std::vector<int8_t>> round_vec; /* per round: vector bit j -> tile bit */
+    std::vector<uint32_t> round_op_begin, round_op_count; /* indices into ops */
     bool is_swap = false;
     int n_source_ops = 0;
 };
@@ -126,10 +142,6 @@ struct TiledPlan {
     int n = 0, prec = QSB_F32, g = 0, nloc = 0, rank = 0;
     std::vector<HostPass> passes;
     BitPerm start_perm{}, end_perm{};
-    /* device image */
-    void *d_blob = nullptr;
-    size_t blob_bytes = 0;
-    std::vector<size_t> pass_off, round_off, op_off; /* byte offsets into the blob */
     double last_exchange_ms = 0.0;
 };
 

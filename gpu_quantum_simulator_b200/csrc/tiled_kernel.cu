@@ -10,6 +10,8 @@
  *      predicates for controls / diagonal phases, then a conflict-free
  *      exchange through shared memory (planner-chosen GF(2)-linear slot map).
  *   3. 16 x 128-bit coalesced stores per thread.
+ * The pass descriptor (tables + op stream) is a __grid_constant__ parameter:
+ * all table / coefficient reads are constant-bank loads.
  * The kernel is HBM-bound by design: algorithmic traffic per launch is
  * 2 * N_loc * sizeof(amplitude), independent of how many gates the pass fuses.
  *
@@ -19,67 +21,76 @@
 #include "sim.h"
 #include "tiled.h"
 
-/* ------------------------------------------------------------ vector algebra */
+/* ------------------------------------------------------------ vector algebra
+ * All updates are written as IN-PLACE inline PTX (read-write operands) so the
+ * tile keeps the same registers through every op body: without this the
+ * compiler materialises a 64-register shuffle at each switch join.
+ *   f32: V = b64 register holding (lo lane, hi lane) -> mul.f32x2 / fma.rn.f32x2
+ *   f64: V = double                                   -> mul.f64   / fma.rn.f64  */
 template <typename R> struct VT;
 template <> struct VT<float> {
-    typedef float2 V;
-    static __device__ __forceinline__ V mul(V a, V b) { return __fmul2_rn(a, b); }
-    static __device__ __forceinline__ V fma(V a, V b, V c) { return __ffma2_rn(a, b, c); }
-    static __device__ __forceinline__ V neg(V a) { return make_float2(-a.x, -a.y); }
-    static __device__ __forceinline__ V bc(float s) { return make_float2(s, s); }
-    static __device__ __forceinline__ V swp(V a) { return make_float2(a.y, a.x); }
-    /* coefficient vector k of a set: (lo lane, hi lane) */
-    static __device__ __forceinline__ V coef(const float *c, int k) { return __ldg(reinterpret_cast<const float2 *>(c) + k); }
-    static __device__ __forceinline__ void swap_lanes(V &a, V &b, uint32_t lanes)
-    {
-        if (lanes & 1) { float t = a.x; a.x = b.x; b.x = t; }
-        if (lanes & 2) { float t = a.y; a.y = b.y; b.y = t; }
-    }
+    typedef unsigned long long V;
+    typedef float S;
+    static __device__ __forceinline__ V mul(V a, V b) { V d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    /* acc += a * b */
+    static __device__ __forceinline__ void acc(V &acc_, V a, V b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc_) : "l"(a), "l"(b)); }
+    /* x = a * x + t */
+    static __device__ __forceinline__ void upd(V &x, V a, V t) { asm("fma.rn.f32x2 %0, %1, %0, %2;" : "+l"(x) : "l"(a), "l"(t)); }
+    static __device__ __forceinline__ V neg(V a) { return a ^ 0x8000000080000000ULL; }
+    static __device__ __forceinline__ V bc(float s) { unsigned u = __float_as_uint(s); return ((V)u << 32) | u; }
+    static __device__ __forceinline__ V swp(V a) { return (a >> 32) | (a << 32); }
+    static __device__ __forceinline__ V coef(const uint2 *c, int k) { return reinterpret_cast<const V *>(c)[k]; }
+    static __device__ __forceinline__ void tphase(const uint2 *c, float &pr, float &pi) { uint2 u = c[0]; pr = __uint_as_float(u.x); pi = __uint_as_float(u.y); }
 };
 template <> struct VT<double> {
     typedef double V;
-    static __device__ __forceinline__ V mul(V a, V b) { return a * b; }
-    static __device__ __forceinline__ V fma(V a, V b, V c) { return ::fma(a, b, c); }
+    typedef double S;
+    static __device__ __forceinline__ V mul(V a, V b) { V d; asm("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b)); return d; }
+    static __device__ __forceinline__ void acc(V &acc_, V a, V b) { asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc_) : "d"(a), "d"(b)); }
+    static __device__ __forceinline__ void upd(V &x, V a, V t) { asm("fma.rn.f64 %0, %1, %0, %2;" : "+d"(x) : "d"(a), "d"(t)); }
     static __device__ __forceinline__ V neg(V a) { return -a; }
     static __device__ __forceinline__ V bc(double s) { return s; }
     static __device__ __forceinline__ V swp(V a) { return a; }
-    static __device__ __forceinline__ V coef(const double *c, int k) { return __ldg(c + k); }
-    static __device__ __forceinline__ void swap_lanes(V &a, V &b, uint32_t) { V t = a; a = b; b = t; }
+    static __device__ __forceinline__ V coef(const uint2 *c, int k) { return reinterpret_cast<const double *>(c)[k]; }
+    static __device__ __forceinline__ void tphase(const uint2 *c, double &pr, double &pi) { pr = coef(c, 0); pi = coef(c, 1); }
 };
 
 #define NV QSB_NV
 
-/* 2x2 on a vector bit.  FORM: 1 real, 2 real-diag/imag-offdiag, 3 general. */
+/* (xr, xi) *= (pr, pi);  npi = -pi */
+template <typename R>
+__device__ __forceinline__ void cmul_inplace(typename VT<R>::V &xr, typename VT<R>::V &xi, typename VT<R>::V pr, typename VT<R>::V pi, typename VT<R>::V npi)
+{
+    typedef VT<R> T;
+    const typename T::V t0 = T::mul(npi, xi), t1 = T::mul(pi, xr);
+    T::upd(xr, pr, t0);
+    T::upd(xi, pr, t1);
+}
+
+/* 2x2 on a vector bit.  FORM: 1 real, 2 real-diag/imag-offdiag, 3 general.
+ * Cross terms go to temporaries first, then each amplitude is updated in place. */
 template <typename R, int VB, int FORM>
-__device__ __forceinline__ void mat_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const R *c, uint32_t vmask)
+__device__ __forceinline__ void mat_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
 {
     typedef VT<R> T; typedef typename T::V V;
     if (FORM == 1) {
-        const V a = T::coef(c, 0), b = T::coef(c, 2), cc = T::coef(c, 4), d = T::coef(c, 6);
+        const V a = T::coef(c, 0), b = T::coef(c, 1), cc = T::coef(c, 2), d = T::coef(c, 3);
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
             const int w = v | (1 << VB);
-            if ((v & vmask) == vmask) {
-                V x0r = re[v], x0i = im[v], x1r = re[w], x1i = im[w];
-                re[v] = T::fma(a, x0r, T::mul(b, x1r));
-                im[v] = T::fma(a, x0i, T::mul(b, x1i));
-                re[w] = T::fma(cc, x0r, T::mul(d, x1r));
-                im[w] = T::fma(cc, x0i, T::mul(d, x1i));
-            }
+            const V t0 = T::mul(b, re[w]), t1 = T::mul(b, im[w]), t2 = T::mul(cc, re[v]), t3 = T::mul(cc, im[v]);
+            T::upd(re[v], a, t0); T::upd(im[v], a, t1);
+            T::upd(re[w], d, t2); T::upd(im[w], d, t3);
         }
     } else if (FORM == 2) {
-        /* [[a, i b],[i c, d]]: slots 0:a 1:-b 2:b 3:-c 4:c 6:d (host pre-negates) */
-        const V a = T::coef(c, 0), nb = T::coef(c, 1), b = T::coef(c, 2), nc = T::coef(c, 3), cc = T::coef(c, 4), d = T::coef(c, 6);
+        /* [[a, i b],[i c, d]]: payload a -b b -c c d (host pre-negates) */
+        const V a = T::coef(c, 0), nb = T::coef(c, 1), b = T::coef(c, 2), nc = T::coef(c, 3), cc = T::coef(c, 4), d = T::coef(c, 5);
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
             const int w = v | (1 << VB);
-            if ((v & vmask) == vmask) {
-                V x0r = re[v], x0i = im[v], x1r = re[w], x1i = im[w];
-                re[v] = T::fma(a, x0r, T::mul(nb, x1i));
-                im[v] = T::fma(a, x0i, T::mul(b, x1r));
-                re[w] = T::fma(nc, x0i, T::mul(d, x1r));
-                im[w] = T::fma(cc, x0r, T::mul(d, x1i));
-            }
+            const V t0 = T::mul(nb, im[w]), t1 = T::mul(b, re[w]), t2 = T::mul(nc, im[v]), t3 = T::mul(cc, re[v]);
+            T::upd(re[v], a, t0); T::upd(im[v], a, t1);
+            T::upd(re[w], d, t2); T::upd(im[w], d, t3);
         }
     } else {
         const V ar = T::coef(c, 0), ai = T::coef(c, 1), br = T::coef(c, 2), bi = T::coef(c, 3);
@@ -88,100 +99,86 @@ __device__ __forceinline__ void mat_v(typename VT<R>::V (&re)[NV], typename VT<R
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
             const int w = v | (1 << VB);
-            if ((v & vmask) == vmask) {
-                V x0r = re[v], x0i = im[v], x1r = re[w], x1i = im[w];
-                re[v] = T::fma(ar, x0r, T::fma(nai, x0i, T::fma(br, x1r, T::mul(nbi, x1i))));
-                im[v] = T::fma(ar, x0i, T::fma(ai, x0r, T::fma(br, x1i, T::mul(bi, x1r))));
-                re[w] = T::fma(cr, x0r, T::fma(nci, x0i, T::fma(dr, x1r, T::mul(ndi, x1i))));
-                im[w] = T::fma(cr, x0i, T::fma(ci, x0r, T::fma(dr, x1i, T::mul(di, x1r))));
-            }
-        }
-    }
-}
-
-template <typename R, int VB>
-__device__ __forceinline__ void x_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], uint32_t vmask, uint32_t lanes)
-{
-#pragma unroll
-    for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
-        const int w = v | (1 << VB);
-        if ((v & vmask) == vmask) {
-            VT<R>::swap_lanes(re[v], re[w], lanes);
-            VT<R>::swap_lanes(im[v], im[w], lanes);
+            V t0 = T::mul(nai, im[v]); T::acc(t0, br, re[w]); T::acc(t0, nbi, im[w]);   /* re[v] minus its own-term */
+            V t1 = T::mul(ai, re[v]);  T::acc(t1, br, im[w]); T::acc(t1, bi, re[w]);    /* im[v] */
+            V t2 = T::mul(cr, re[v]);  T::acc(t2, nci, im[v]); T::acc(t2, ndi, im[w]);  /* re[w] */
+            V t3 = T::mul(cr, im[v]);  T::acc(t3, ci, re[v]); T::acc(t3, di, re[w]);    /* im[w] */
+            T::upd(re[v], ar, t0); T::upd(im[v], ar, t1);
+            T::upd(re[w], dr, t2); T::upd(im[w], dr, t3);
         }
     }
 }
 
 template <typename R, int FORM>
-__device__ __forceinline__ void mat_dispatch(int vb, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const R *c, uint32_t vmask)
+__device__ __forceinline__ void mat_dispatch(int vb, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
 {
     switch (vb) {
-    case 0: mat_v<R, 0, FORM>(re, im, c, vmask); break;
-    case 1: mat_v<R, 1, FORM>(re, im, c, vmask); break;
-    case 2: mat_v<R, 2, FORM>(re, im, c, vmask); break;
-    default: mat_v<R, 3, FORM>(re, im, c, vmask); break;
+    case 0: mat_v<R, 0, FORM>(re, im, c); break;
+    case 1: mat_v<R, 1, FORM>(re, im, c); break;
+    case 2: mat_v<R, 2, FORM>(re, im, c); break;
+    default: mat_v<R, 3, FORM>(re, im, c); break;
     }
+}
+
+/* phase on the vectors whose bit VB is set */
+template <typename R, int VB>
+__device__ __forceinline__ void diag_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::V pr, typename VT<R>::V pi, typename VT<R>::V npi)
+{
+#pragma unroll
+    for (int v = 0; v < NV; v++) if ((v >> VB) & 1) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
 }
 
 /* 2x2 on the pack bit (f32 only): out = A * x + B * swap(x), A = (m00, m11), B = (m01, m10) */
 template <int FORM>
-__device__ __forceinline__ void mat_p(float2 (&re)[NV], float2 (&im)[NV], const float *c, uint32_t vmask)
+__device__ __forceinline__ void mat_p(unsigned long long (&re)[NV], unsigned long long (&im)[NV], const uint2 *c)
 {
-    typedef VT<float> T;
+    typedef VT<float> T; typedef T::V V;
     if (FORM == 1) {
-        const float2 A = T::coef(c, 0), B = T::coef(c, 2);
+        const V A = T::coef(c, 0), B = T::coef(c, 1);
 #pragma unroll
-        for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) {
-            re[v] = T::fma(A, re[v], T::mul(B, T::swp(re[v])));
-            im[v] = T::fma(A, im[v], T::mul(B, T::swp(im[v])));
+        for (int v = 0; v < NV; v++) {
+            const V t0 = T::mul(B, T::swp(re[v])), t1 = T::mul(B, T::swp(im[v]));
+            T::upd(re[v], A, t0); T::upd(im[v], A, t1);
         }
     } else {
-        const float2 Ar = T::coef(c, 0), Ai = T::coef(c, 1), Br = T::coef(c, 2), Bi = T::coef(c, 3);
-        const float2 nAi = T::neg(Ai), nBi = T::neg(Bi);
+        const V Ar = T::coef(c, 0), Ai = T::coef(c, 1), Br = T::coef(c, 2), Bi = T::coef(c, 3);
+        const V nAi = T::neg(Ai), nBi = T::neg(Bi);
 #pragma unroll
-        for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) {
-            float2 xr = re[v], xi = im[v], sr = T::swp(xr), si = T::swp(xi);
-            re[v] = T::fma(Ar, xr, T::fma(nAi, xi, T::fma(Br, sr, T::mul(nBi, si))));
-            im[v] = T::fma(Ar, xi, T::fma(Ai, xr, T::fma(Br, si, T::mul(Bi, sr))));
+        for (int v = 0; v < NV; v++) {
+            const V sr = T::swp(re[v]), si = T::swp(im[v]);
+            V t0 = T::mul(nAi, im[v]); T::acc(t0, Br, sr); T::acc(t0, nBi, si);
+            V t1 = T::mul(Ai, re[v]);  T::acc(t1, Br, si); T::acc(t1, Bi, sr);
+            T::upd(re[v], Ar, t0); T::upd(im[v], Ar, t1);
         }
     }
 }
 template <int FORM>
-__device__ __forceinline__ void mat_p(double (&)[NV], double (&)[NV], const double *, uint32_t) {}
-
-__device__ __forceinline__ void xp(float2 (&re)[NV], float2 (&im)[NV], uint32_t vmask)
-{
-#pragma unroll
-    for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) { re[v] = VT<float>::swp(re[v]); im[v] = VT<float>::swp(im[v]); }
-}
-__device__ __forceinline__ void xp(double (&)[NV], double (&)[NV], uint32_t) {}
+__device__ __forceinline__ void mat_p(double (&)[NV], double (&)[NV], const uint2 *) {}
 
 /* ---------------------------------------------------------- global / shared IO */
-struct PtrTab { void *p[8]; };
-
 template <typename R> struct IO;
 template <> struct IO<float> {
-    typedef float2 V;
+    typedef unsigned long long V;
     /* amplitude pair unit: {re0, re1, im0, im1} at 16 * (index >> 1) */
     static __device__ __forceinline__ void gload(const void *base, uint64_t idx, V &re, V &im)
     {
-        const float4 x = __ldcs(reinterpret_cast<const float4 *>(base) + (idx >> 1));
-        re = make_float2(x.x, x.y); im = make_float2(x.z, x.w);
+        const ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(base) + (idx >> 1));
+        re = x.x; im = x.y;
     }
     static __device__ __forceinline__ void gstore(void *base, uint64_t idx, V re, V im)
     {
-        __stcs(reinterpret_cast<float4 *>(base) + (idx >> 1), make_float4(re.x, re.y, im.x, im.y));
+        __stcs(reinterpret_cast<ulonglong2 *>(base) + (idx >> 1), make_ulonglong2(re, im));
     }
     /* two 32 KiB planes of 8-byte slots */
     static __device__ __forceinline__ void sload(const uint8_t *sm, uint32_t slot, V &re, V &im)
     {
-        re = *reinterpret_cast<const float2 *>(sm + slot * 8u);
-        im = *reinterpret_cast<const float2 *>(sm + 32768u + slot * 8u);
+        re = *reinterpret_cast<const V *>(sm + slot * 8u);
+        im = *reinterpret_cast<const V *>(sm + 32768u + slot * 8u);
     }
     static __device__ __forceinline__ void sstore(uint8_t *sm, uint32_t slot, V re, V im)
     {
-        *reinterpret_cast<float2 *>(sm + slot * 8u) = re;
-        *reinterpret_cast<float2 *>(sm + 32768u + slot * 8u) = im;
+        *reinterpret_cast<V *>(sm + slot * 8u) = re;
+        *reinterpret_cast<V *>(sm + 32768u + slot * 8u) = im;
     }
 };
 template <> struct IO<double> {
@@ -206,15 +203,20 @@ template <> struct IO<double> {
     }
 };
 
-/* ------------------------------------------------------------------ the kernel */
-template <typename R>
+struct PtrTab { void *p[8]; };
+
+/* ------------------------------------------------------------------ the kernel
+ * PEER: source amplitudes may live on other ranks (exchange passes): the index
+ * bits above nloc select the peer buffer. */
+template <typename R, int BLOB, bool PEER>
 __global__ void __launch_bounds__(QSB_THREADS, 2)
-k_tile_pass(const DevPass *__restrict__ pass_p, const DevRound *__restrict__ rounds,
-            const DevOp<R> *__restrict__ ops, PtrTab src, void *dst)
+k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const __grid_constant__ PtrTab src, void *dst)
 {
     typedef VT<R> T; typedef typename T::V V;
     extern __shared__ __align__(16) uint8_t smem[];
-    const DevPass &P = *pass_p;
+    const uint4 *B = blob.q;
+    const DevPass &P = *reinterpret_cast<const DevPass *>(B);
+    const DevRound *rounds = reinterpret_cast<const DevRound *>(B + P.rounds_off16);
     const uint32_t tid = threadIdx.x;
 
     /* tile id -> outer index bits */
@@ -236,26 +238,29 @@ k_tile_pass(const DevPass *__restrict__ pass_p, const DevRound *__restrict__ rou
 
     for (int rd = 0; rd < n_rounds; rd++) {
         const DevRound &RD = rounds[rd];
-        /* this thread's physical index bits (vector bits zero) */
+        /* this thread's physical index bits (vector bits zero) and smem slot bases */
         uint64_t gthr = src_outer;
+        uint32_t sb = 0; /* ld in the low half, st in the high half */
 #pragma unroll
-        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) gthr |= RD.thr_gidx[j];
+        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) {
+            gthr |= RD.thr[j].gidx;
+            sb ^= (uint32_t)RD.thr[j].ld | ((uint32_t)RD.thr[j].st << 16);
+        }
 
         if (rd == 0) {
-            const uint64_t g0 = RD.vec_gidx[0], g1 = RD.vec_gidx[1], g2 = RD.vec_gidx[2], g3 = RD.vec_gidx[3];
+            const uint64_t g0 = RD.vec[0].gidx, g1 = RD.vec[1].gidx, g2 = RD.vec[2].gidx, g3 = RD.vec[3].gidx;
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 const uint64_t gi = gthr | ((v & 1) ? g0 : 0) | ((v & 2) ? g1 : 0) | ((v & 4) ? g2 : 0) | ((v & 8) ? g3 : 0);
-                IO<R>::gload(src.p[gi >> nloc], gi & loc_mask, re[v], im[v]);
+                if (PEER) IO<R>::gload(src.p[gi >> nloc], gi & loc_mask, re[v], im[v]);
+                else IO<R>::gload(src.p[0], gi & loc_mask, re[v], im[v]);
             }
         } else {
-            uint32_t sb = 0;
-#pragma unroll
-            for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.ld_thr[j];
-            const uint32_t s0 = RD.ld_vec[0], s1 = RD.ld_vec[1], s2 = RD.ld_vec[2], s3 = RD.ld_vec[3];
+            const uint32_t sl = sb & 0xffffu;
+            const uint32_t s0 = RD.vec[0].ld, s1 = RD.vec[1].ld, s2 = RD.vec[2].ld, s3 = RD.vec[3].ld;
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                const uint32_t slot = sb ^ ((v & 1) ? s0 : 0) ^ ((v & 2) ? s1 : 0) ^ ((v & 4) ? s2 : 0) ^ ((v & 8) ? s3 : 0);
+                const uint32_t slot = sl ^ ((v & 1) ? s0 : 0) ^ ((v & 2) ? s1 : 0) ^ ((v & 4) ? s2 : 0) ^ ((v & 8) ? s3 : 0);
                 IO<R>::sload(smem, slot, re[v], im[v]);
             }
             __syncthreads(); /* every thread has its registers before anyone overwrites the tile */
@@ -264,46 +269,49 @@ k_tile_pass(const DevPass *__restrict__ pass_p, const DevRound *__restrict__ rou
         /* ---- the fused gates of this round ---- */
         R psr = R(1), psi = R(0); /* per-thread pending phase (OP_TPHASE) */
         const uint32_t n_ops = RD.n_ops;
-        const DevOp<R> *op = ops + RD.op_begin;
-        for (uint32_t i = 0; i < n_ops; i++, op++) {
-            const uint32_t kind = op->kind;
-            const uint32_t code = kind & 0xffu;
-            const uint64_t tmask = op->tmask;
+        const uint4 *op = B + RD.op_off16;
+        for (uint32_t i = 0; i < n_ops; i++) {
+            const uint4 h = *op;
+            const uint32_t kind = h.x;
+            const uint64_t tmask = ((uint64_t)h.w << 32) | h.z;
+            const uint2 *c = reinterpret_cast<const uint2 *>(op + 1);
+            op += h.y;
             const bool pred = (gthr & tmask) == tmask;
             const bool mux = (kind >> 16) & 1u;
             if (!pred && !mux) continue;
-            const uint32_t vmask = op->vmask;
-            const R *c = op->c + (pred ? (64 / sizeof(R)) : 0); /* coefficient set 1 = condition holds */
+            const uint32_t code = kind & 0xffu;
             const int vb = (kind >> 8) & 0xf;
             switch (code) {
-            case OP_MAT_R: mat_dispatch<R, 1>(vb, re, im, c, vmask); break;
-            case OP_MAT_I: mat_dispatch<R, 2>(vb, re, im, c, vmask); break;
-            case OP_MAT_G: mat_dispatch<R, 3>(vb, re, im, c, vmask); break;
-            case OP_MATP_R: mat_p<1>(re, im, c, vmask); break;
-            case OP_MATP_G: mat_p<3>(re, im, c, vmask); break;
-            case OP_X: {
-                const uint32_t lanes = (kind >> 12) & 3u;
+            case OP_MAT_R: mat_dispatch<R, 1>(vb, re, im, c + ((mux && pred) ? 4 : 0)); break;
+            case OP_MAT_I: mat_dispatch<R, 2>(vb, re, im, c + ((mux && pred) ? 6 : 0)); break;
+            case OP_MAT_G: mat_dispatch<R, 3>(vb, re, im, c + ((mux && pred) ? 8 : 0)); break;
+            case OP_MATP_R: mat_p<1>(re, im, c + ((mux && pred) ? 2 : 0)); break;
+            case OP_MATP_G: mat_p<3>(re, im, c + ((mux && pred) ? 4 : 0)); break;
+            case OP_DIAG_V: {
+                const V pr = T::coef(c, 0), pi = T::coef(c, 1), npi = T::neg(pi);
                 switch (vb) {
-                case 0: x_v<R, 0>(re, im, vmask, lanes); break;
-                case 1: x_v<R, 1>(re, im, vmask, lanes); break;
-                case 2: x_v<R, 2>(re, im, vmask, lanes); break;
-                default: x_v<R, 3>(re, im, vmask, lanes); break;
+                case 0: diag_v<R, 0>(re, im, pr, pi, npi); break;
+                case 1: diag_v<R, 1>(re, im, pr, pi, npi); break;
+                case 2: diag_v<R, 2>(re, im, pr, pi, npi); break;
+                default: diag_v<R, 3>(re, im, pr, pi, npi); break;
                 }
                 break;
             }
-            case OP_XP: xp(re, im, vmask); break;
-            case OP_DIAG: {
+            case OP_DIAG_ALL: {
                 const V pr = T::coef(c, 0), pi = T::coef(c, 1), npi = T::neg(pi);
 #pragma unroll
-                for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) {
-                    const V xr = re[v], xi = im[v];
-                    re[v] = T::fma(pr, xr, T::mul(npi, xi));
-                    im[v] = T::fma(pr, xi, T::mul(pi, xr));
-                }
+                for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
+                break;
+            }
+            case OP_DIAG_GEN: {
+                const uint32_t vmask = (kind >> 20) & 0xfu;
+                const V pr = T::coef(c, 0), pi = T::coef(c, 1), npi = T::neg(pi);
+#pragma unroll
+                for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
                 break;
             }
             case OP_TPHASE: {
-                const R pr = __ldg(c), pi = __ldg(c + (sizeof(R) == 4 ? 2 : 1)); /* coef 0 / coef 1, lo lane */
+                R pr, pi; T::tphase(c, pr, pi);
                 const R nr = psr * pr - psi * pi;
                 psi = psr * pi + psi * pr; psr = nr;
                 break;
@@ -315,11 +323,7 @@ k_tile_pass(const DevPass *__restrict__ pass_p, const DevRound *__restrict__ rou
             if (!(psr == R(1) && psi == R(0))) {
                 const V pr = T::bc(psr), pi = T::bc(psi), npi = T::bc(-psi);
 #pragma unroll
-                for (int v = 0; v < NV; v++) {
-                    const V xr = re[v], xi = im[v];
-                    re[v] = T::fma(pr, xr, T::mul(npi, xi));
-                    im[v] = T::fma(pr, xi, T::mul(pi, xr));
-                }
+                for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
             }
         }
 
@@ -334,13 +338,11 @@ k_tile_pass(const DevPass *__restrict__ pass_p, const DevRound *__restrict__ rou
                 IO<R>::gstore(dst, gi & loc_mask, re[v], im[v]);
             }
         } else {
-            uint32_t sb = 0;
-#pragma unroll
-            for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.st_thr[j];
-            const uint32_t s0 = RD.st_vec[0], s1 = RD.st_vec[1], s2 = RD.st_vec[2], s3 = RD.st_vec[3];
+            const uint32_t ss = sb >> 16;
+            const uint32_t s0 = RD.vec[0].st, s1 = RD.vec[1].st, s2 = RD.vec[2].st, s3 = RD.vec[3].st;
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                const uint32_t slot = sb ^ ((v & 1) ? s0 : 0) ^ ((v & 2) ? s1 : 0) ^ ((v & 4) ? s2 : 0) ^ ((v & 8) ? s3 : 0);
+                const uint32_t slot = ss ^ ((v & 1) ? s0 : 0) ^ ((v & 2) ? s1 : 0) ^ ((v & 4) ? s2 : 0) ^ ((v & 8) ? s3 : 0);
                 IO<R>::sstore(smem, slot, re[v], im[v]);
             }
             __syncthreads();
@@ -349,29 +351,33 @@ k_tile_pass(const DevPass *__restrict__ pass_p, const DevRound *__restrict__ rou
 }
 
 /* ------------------------------------------------------------------ launching */
-static bool g_attr_set[2] = {false, false};
-
-template <typename R>
-static int launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const PtrTab &src, void *dst)
+template <typename R, int BLOB, bool PEER>
+static int launch_one(qsb_sim *s, const HostPass &hp, const PtrTab &src, void *dst)
 {
-    const uint8_t *blob = (const uint8_t *)p->d_blob;
-    const HostPass &hp = p->passes[k];
-    const int which = sizeof(R) == 4 ? 0 : 1;
-    if (!g_attr_set[which]) {
-        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        g_attr_set[which] = true;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        attr_set = true;
     }
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
-    k_tile_pass<R><<<(unsigned)hp.hdr.n_tiles, QSB_THREADS, 65536, s->stream>>>(
-        (const DevPass *)(blob + p->pass_off[k]), (const DevRound *)(blob + p->round_off[k]),
-        (const DevOp<R> *)(blob + p->op_off[k]), src, dst);
+    const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
+    k_tile_pass<R, BLOB, PEER><<<(unsigned)hp.hdr.n_tiles, QSB_THREADS, 65536, s->stream>>>(*blob, src, dst);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
 }
 
-int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, void *const *src_ptrs, void *dst)
+template <typename R>
+static int launch_pass(qsb_sim *s, const HostPass &hp, const PtrTab &src, void *dst, bool peer)
+{
+    const bool small = hp.blob.size() <= QSB_BLOB_SMALL;
+    if (peer) return small ? launch_one<R, QSB_BLOB_SMALL, true>(s, hp, src, dst) : launch_one<R, QSB_BLOB_LARGE, true>(s, hp, src, dst);
+    return small ? launch_one<R, QSB_BLOB_SMALL, false>(s, hp, src, dst) : launch_one<R, QSB_BLOB_LARGE, false>(s, hp, src, dst);
+}
+
+int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, void *const *src_ptrs, void *dst, bool peer)
 {
     PtrTab t;
     for (int i = 0; i < 8; i++) t.p[i] = src_ptrs[i];
-    return s->prec == QSB_F32 ? launch_pass<float>(s, p, k, t, dst) : launch_pass<double>(s, p, k, t, dst);
+    const HostPass &hp = p->passes[k];
+    return s->prec == QSB_F32 ? launch_pass<float>(s, hp, t, dst, peer) : launch_pass<double>(s, hp, t, dst, peer);
 }

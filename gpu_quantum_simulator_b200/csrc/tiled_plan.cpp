@@ -2,7 +2,7 @@
  * tiled_plan.cpp -- host-side gate fusion and scheduling (no CUDA in this file).
  *
  * Turns the canonical op list into PASSES (one HBM sweep each) and ROUNDS
- * (register-resident butterfly groups inside a pass) and emits the uniform
+ * (register-resident butterfly groups inside a pass) and emits the constant
  * tables the kernel of tiled_kernel.cu interprets.  This is the B200-native
  * replacement of the reference's host preprocessing:
  *   preproces.cu:215-269   per-qubit 2x2 accumulation, flush before each CX
@@ -13,8 +13,12 @@
  * gates stay sparse: a pass fuses every gate whose target is resident in the
  * tile, costing the 2..4 packed FMAs per amplitude each gate really needs,
  * while the pass count -- the only thing HBM sees -- drops by the fusion
- * factor.  Diagonal gates and controls never need residency: they become
- * per-thread predicates / phases on physical index bits.
+ * factor.  Specialisations:
+ *   - diagonal gates and controls never need residency: they are per-thread
+ *     predicates / phases on physical index bits (OP_TPHASE costs ~nothing);
+ *   - a CX next to a one-qubit gate on its target is absorbed into that gate
+ *     as a thread-level multiplexer (U vs X.U), costing zero extra arithmetic
+ *     (the 4x4.cu pair accumulator did this with dense 4x4 products).
  */
 #include <math.h>
 #include <string.h>
@@ -74,6 +78,9 @@ int tiled_min_local_bits(int prec, const qsb_options_t *) { return prec == QSB_F
 
 namespace {
 
+const int MAX_PASS_OPS = 150;   /* keeps a pass descriptor below QSB_BLOB_LARGE */
+const int MAX_PASS_ROUNDS = 32;
+
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
     bool f32;
@@ -102,6 +109,11 @@ struct Blocker {
 
 /* snap tiny components so that structure tests are exact */
 inline double snap(double x, double scale) { return fabs(x) <= 4e-16 * scale ? 0.0 : x; }
+void snap_mat(const double *in, double *out)
+{
+    double sc = 0; for (int k = 0; k < 8; k++) sc = std::max(sc, fabs(in[k]));
+    for (int k = 0; k < 8; k++) out[k] = snap(in[k], sc);
+}
 
 int classify(const double *m) /* 1 real, 2 real-diag/imag-offdiag, 3 general */
 {
@@ -110,7 +122,75 @@ int classify(const double *m) /* 1 real, 2 real-diag/imag-offdiag, 3 general */
     return 3;
 }
 
-void set_coef(HostOp &op, int set, int coef, double lo, double hi) { op.c[set * 16 + coef * 2] = lo; op.c[set * 16 + coef * 2 + 1] = hi; }
+const double IDENT[8] = {1, 0, 0, 0, 0, 0, 1, 0};
+/* imaginary diagonal, real off-diagonal: i times an rx-form matrix */
+bool is_jform(const double *m) { return m[0] == 0 && m[6] == 0 && m[3] == 0 && m[5] == 0; }
+
+/* CX (any number of controls) next to an uncontrolled one-qubit gate on its
+ * target  ->  one multiplexed gate (U when the controls are off, X.U / U.X when on).
+ * For the rx form, X.U = i * (another rx-form matrix): emit() moves that i into the
+ * per-thread phase, so the multiplexed pair keeps the cheap form. */
+void absorb_cx(std::vector<COp> &ops, int n)
+{
+    const int N = (int)ops.size();
+    std::vector<char> alive(N, 1);
+    auto mergeable = [&](const COp &o, int t) {
+        if (o.kind != C_MAT || o.ctrl != 0 || o.target != t) return false;
+        return true;
+    };
+    /* backward: gate U then CX  ->  mux(U, X.U) at U's position */
+    {
+        std::vector<int> last_touch(n, -1), last_nondiag(n, -1);
+        for (int i = 0; i < N; i++) {
+            COp &o = ops[i];
+            if (o.kind == C_X && o.ctrl) {
+                const int t = o.target, j = last_touch[t];
+                bool ok = j >= 0 && alive[j] && mergeable(ops[j], t);
+                if (ok) for (uint64_t m = o.ctrl; m; m &= m - 1) if (last_nondiag[__builtin_ctzll(m)] > j) ok = false;
+                if (ok) {
+                    COp &u = ops[j];
+                    u.kind = C_MUX; u.ctrl = o.ctrl;
+                    /* X.U: rows swapped */
+                    for (int k = 0; k < 4; k++) { u.m2[k] = u.m[4 + k]; u.m2[4 + k] = u.m[k]; }
+                    alive[i] = 0;
+                }
+            }
+            const uint64_t touch = o.ctrl | (o.target >= 0 ? 1ULL << o.target : 0);
+            for (uint64_t m = touch; m; m &= m - 1) last_touch[__builtin_ctzll(m)] = i;
+            if (o.target >= 0) last_nondiag[o.target] = i;
+        }
+    }
+    /* forward: CX then gate U  ->  mux(U, U.X) at U's position */
+    {
+        std::vector<int> next_touch(n, N), next_nondiag(n, N);
+        for (int i = N - 1; i >= 0; i--) {
+            COp &o = ops[i];
+            if (!alive[i]) continue;
+            if (o.kind == C_X && o.ctrl) {
+                const int t = o.target, j = next_touch[t];
+                bool ok = j < N && alive[j] && mergeable(ops[j], t);
+                if (ok) for (uint64_t m = o.ctrl; m; m &= m - 1) if (next_nondiag[__builtin_ctzll(m)] < j) ok = false;
+                if (ok) {
+                    COp &u = ops[j];
+                    u.kind = C_MUX; u.ctrl = o.ctrl;
+                    /* U.X: columns swapped */
+                    u.m2[0] = u.m[2]; u.m2[1] = u.m[3]; u.m2[2] = u.m[0]; u.m2[3] = u.m[1];
+                    u.m2[4] = u.m[6]; u.m2[5] = u.m[7]; u.m2[6] = u.m[4]; u.m2[7] = u.m[5];
+                    alive[i] = 0;
+                    /* the mux now reads the controls at position j: keep later scans conservative */
+                    for (uint64_t m = u.ctrl; m; m &= m - 1) { int q = __builtin_ctzll(m); next_touch[q] = std::min(next_touch[q], j); }
+                    continue;
+                }
+            }
+            const uint64_t touch = o.ctrl | (o.target >= 0 ? 1ULL << o.target : 0);
+            for (uint64_t m = touch; m; m &= m - 1) next_touch[__builtin_ctzll(m)] = i;
+            if (o.target >= 0) next_nondiag[o.target] = i;
+        }
+    }
+    std::vector<COp> out; out.reserve(N);
+    for (int i = 0; i < N; i++) if (alive[i]) out.push_back(ops[i]);
+    ops.swap(out);
+}
 
 } // namespace
 
@@ -127,7 +207,6 @@ struct PassBuilder {
     /* choose the tile from the set of resident logical qubits */
     void set_tile(uint64_t resident)
     {
-        /* physical positions in the tile */
         uint64_t posmask = 0;
         for (int q = 0; q < M.n; q++) if ((resident >> q) & 1) posmask |= 1ULL << perm.pos[q];
         for (int p = 0; p < M.a; p++) posmask |= 1ULL << p;              /* contiguous low segment */
@@ -144,7 +223,6 @@ struct PassBuilder {
             if (inv[p] >= 0) tile_of_qubit[inv[p]] = j;
             j++;
         }
-        /* outer runs */
         memset(&hp.hdr, 0, sizeof hp.hdr);
         int nr = 0, p = 0, outer_bits = 0;
         while (p < M.nloc) {
@@ -169,34 +247,41 @@ struct PassBuilder {
         return f;
     }
 
-    /* Build rounds for the ordered op list `ops` (all targets resident). */
-    int build_rounds(const std::vector<COp> &ops)
+    /* Build rounds for the ordered op list `ops` (all targets resident).  done[i] tells the
+     * caller which ops were consumed (a pass is cut at MAX_PASS_ROUNDS). */
+    int build_rounds(const std::vector<COp> &ops, std::vector<char> &done)
     {
         const int P = M.f32 ? 0 : -1;             /* pack tile bit */
         const uint32_t F = lane_forbidden();
         const size_t n = ops.size();
-        std::vector<char> done(n, 0);
+        done.assign(n, 0);
         size_t left = n, first_open = 0;
         std::vector<uint32_t> roundR;             /* vector-bit set (tile-bit mask) per round */
         std::vector<std::vector<int>> round_ops;
         while (left || roundR.empty()) {
+            if ((int)roundR.size() >= MAX_PASS_ROUNDS - 1) break;
             const bool is_first = roundR.empty();
-            uint32_t R = 0; int nR = 0;
+            uint32_t R = 0, ctrl_used = 0; int nR = 0;
             Blocker B; B.clear();
             std::vector<int> mine;
             for (size_t i = first_open; i < n; i++) {
                 if (done[i]) continue;
                 const COp &o = ops[i];
                 bool can = B.ok(o);
+                uint32_t cbits = 0; /* tile bits this op uses as (non-diagonal-gate) controls */
+                if (can && o.kind != C_PHASE) {
+                    for (uint64_t m = o.ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) cbits |= 1u << tb; }
+                    if (cbits & R) can = false;           /* controls must stay thread-level */
+                }
                 if (can && o.target >= 0) {
                     int tb = tile_of_qubit[o.target];
                     if (tb == P) { /* pack variants */ }
                     else if (is_first && ((F >> tb) & 1)) can = false;
                     else if ((R >> tb) & 1) {}
-                    else if (nR < QSB_NVB) { R |= 1u << tb; nR++; }
+                    else if (nR < QSB_NVB && !((ctrl_used >> tb) & 1)) { R |= 1u << tb; nR++; }
                     else can = false;
                 }
-                if (can) { mine.push_back((int)i); done[i] = 1; left--; }
+                if (can) { mine.push_back((int)i); done[i] = 1; left--; ctrl_used |= cbits; }
                 else { B.block(o); if (B.full >= M.n) break; }
             }
             while (first_open < n && done[first_open]) first_open++;
@@ -209,11 +294,20 @@ struct PassBuilder {
         const int nrounds = (int)roundR.size();
         hp.rounds.assign(nrounds, DevRound());
         hp.round_thr.assign(nrounds, {}); hp.round_vec.assign(nrounds, {});
+        std::vector<uint32_t> ctrl_of_round(nrounds, 0);
+        for (int r = 0; r < nrounds; r++)
+            for (int i : round_ops[r]) if (ops[i].kind != C_PHASE)
+                for (uint64_t m = ops[i].ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) ctrl_of_round[r] |= 1u << tb; }
         for (int r = 0; r < nrounds; r++) {
             uint32_t R = roundR[r];
             const bool edge = (r == 0 || r == nrounds - 1);
-            /* pad R with the highest free tile bits */
+            /* pad R with the highest free tile bits (never a control of this round) */
             for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) {
+                if (tb == P || ((R >> tb) & 1) || ((ctrl_of_round[r] >> tb) & 1)) continue;
+                if (edge && ((F >> tb) & 1)) continue;
+                R |= 1u << tb;
+            }
+            for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) { /* cannot happen in practice: relax the control rule */
                 if (tb == P || ((R >> tb) & 1)) continue;
                 if (edge && ((F >> tb) & 1)) continue;
                 R |= 1u << tb;
@@ -225,28 +319,25 @@ struct PassBuilder {
             hp.round_vec[r] = vec; hp.round_thr[r] = thr;
             DevRound &D = hp.rounds[r];
             memset(&D, 0, sizeof D);
-            for (int j = 0; j < QSB_TB; j++) D.thr_gidx[j] = 1ULL << hp.tile_src[thr[j]];
-            for (int j = 0; j < QSB_NVB; j++) D.vec_gidx[j] = 1ULL << hp.tile_src[vec[j]];
+            for (int j = 0; j < QSB_TB; j++) D.thr[j].gidx = 1ULL << hp.tile_src[thr[j]];
+            for (int j = 0; j < QSB_NVB; j++) D.vec[j].gidx = 1ULL << hp.tile_src[vec[j]];
         }
-        /* destination tables (last round) */
         for (int j = 0; j < QSB_TB; j++) hp.hdr.dst_thr[j] = 1ULL << hp.tile_dst[hp.round_thr[nrounds - 1][j]];
         for (int j = 0; j < QSB_NVB; j++) hp.hdr.dst_vec[j] = 1ULL << hp.tile_dst[hp.round_vec[nrounds - 1][j]];
         hp.hdr.n_rounds = nrounds;
 
-        /* shared-memory slot maps between consecutive rounds */
         for (int r = 0; r + 1 < nrounds; r++) slot_map(r);
 
-        /* ops */
         hp.ops.clear();
+        hp.round_op_begin.assign(nrounds, 0); hp.round_op_count.assign(nrounds, 0);
         for (int r = 0; r < nrounds; r++) {
-            DevRound &D = hp.rounds[r];
-            D.op_begin = (uint32_t)hp.ops.size();
+            hp.round_op_begin[r] = (uint32_t)hp.ops.size();
             for (int i : round_ops[r]) emit(ops[i], r);
-            D.n_ops = (uint32_t)hp.ops.size() - D.op_begin;
-            for (uint32_t k = D.op_begin; k < D.op_begin + D.n_ops; k++)
-                if ((hp.ops[k].kind & 0xff) == OP_TPHASE) D.flags |= 1u;
+            hp.round_op_count[r] = (uint32_t)hp.ops.size() - hp.round_op_begin[r];
+            for (uint32_t k = hp.round_op_begin[r]; k < hp.ops.size(); k++)
+                if ((hp.ops[k].kind & 0xff) == OP_TPHASE) hp.rounds[r].flags |= 1u;
         }
-        hp.n_source_ops = (int)n;
+        hp.n_source_ops = (int)(n - left);
         return QSB_OK;
     }
 
@@ -267,7 +358,6 @@ struct PassBuilder {
             int b = 0; while (used[b]) b++;
             used[b] = true; col[wt[i]] = (uint16_t)(1u << b); has[wt[i]] = true;
         }
-        /* upper slot bits: every tile bit that is not one of the reader's bank lanes */
         bool isD[16] = {false};
         for (int i = 0; i < nb; i++) isD[rt[i]] = true;
         int up = nb;
@@ -276,34 +366,59 @@ struct PassBuilder {
             col[tb] |= (uint16_t)(1u << up); up++;
         }
         DevRound &W = hp.rounds[r], &Rd = hp.rounds[r + 1];
-        for (int j = 0; j < QSB_TB; j++) { W.st_thr[j] = col[wt[j]]; Rd.ld_thr[j] = col[rt[j]]; }
-        for (int j = 0; j < QSB_NVB; j++) { W.st_vec[j] = col[hp.round_vec[r][j]]; Rd.ld_vec[j] = col[hp.round_vec[r + 1][j]]; }
+        for (int j = 0; j < QSB_TB; j++) { W.thr[j].st = col[wt[j]]; Rd.thr[j].ld = col[rt[j]]; }
+        for (int j = 0; j < QSB_NVB; j++) { W.vec[j].st = col[hp.round_vec[r][j]]; Rd.vec[j].ld = col[hp.round_vec[r + 1][j]]; }
+    }
+
+    static void set_c(HostOp &h, int set, int k, double lo, double hi) { h.c[set][k][0] = lo; h.c[set][k][1] = hi; }
+
+    /* fill coefficient set `set` of a vector-bit matrix op: lo lane uses mlo, hi lane mhi */
+    static void fill_mat(HostOp &h, int set, int form, const double *mlo, const double *mhi)
+    {
+        if (form == 1) {
+            set_c(h, set, 0, mlo[0], mhi[0]); set_c(h, set, 1, mlo[2], mhi[2]);
+            set_c(h, set, 2, mlo[4], mhi[4]); set_c(h, set, 3, mlo[6], mhi[6]);
+        } else if (form == 2) { /* [[a, ib],[ic, d]] -> a -b b -c c d */
+            set_c(h, set, 0, mlo[0], mhi[0]);
+            set_c(h, set, 1, -mlo[3], -mhi[3]); set_c(h, set, 2, mlo[3], mhi[3]);
+            set_c(h, set, 3, -mlo[5], -mhi[5]); set_c(h, set, 4, mlo[5], mhi[5]);
+            set_c(h, set, 5, mlo[6], mhi[6]);
+        } else {
+            for (int k = 0; k < 8; k++) set_c(h, set, k, mlo[k], mhi[k]);
+        }
+    }
+    /* pack-bit matrix op: A = (m00, m11), B = (m01, m10) */
+    static void fill_matp(HostOp &h, int set, int form, const double *m)
+    {
+        if (form == 1) { set_c(h, set, 0, m[0], m[6]); set_c(h, set, 1, m[2], m[4]); }
+        else { set_c(h, set, 0, m[0], m[6]); set_c(h, set, 1, m[1], m[7]); set_c(h, set, 2, m[2], m[4]); set_c(h, set, 3, m[3], m[5]); }
     }
 
     void emit(const COp &o, int r)
     {
         const int P = M.f32 ? 0 : -1;
         HostOp h; memset(&h, 0, sizeof h);
-        /* split the condition mask */
         bool pack_ctrl = false;
+        uint32_t vmask = 0;
         for (uint64_t m = o.ctrl; m; m &= m - 1) {
             int q = __builtin_ctzll(m);
             int tb = tile_of_qubit[q];
             int vi = -1;
             if (tb >= 0) for (int j = 0; j < QSB_NVB; j++) if (hp.round_vec[r][j] == tb) vi = j;
             if (tb >= 0 && tb == P) pack_ctrl = true;
-            else if (vi >= 0) h.vmask |= 1u << vi;
+            else if (vi >= 0) vmask |= 1u << vi;
             else h.tmask |= 1ULL << perm.pos[q];
         }
-        const double lo_id = pack_ctrl ? 1.0 : 0.0; /* helper: identity entries for the lo lane */
         if (o.kind == C_PHASE) {
-            if (!pack_ctrl && h.vmask == 0) {
-                h.kind = OPK(OP_TPHASE, 0, 3, 0);
-                set_coef(h, 1, 0, o.m[0], o.m[0]); set_coef(h, 1, 1, o.m[1], o.m[1]);
+            if (!pack_ctrl && vmask == 0) {
+                h.kind = OPK(OP_TPHASE, 0, 0, 0); h.n_coef = 0; h.tph[0] = o.m[0]; h.tph[1] = o.m[1];
             } else {
-                h.kind = OPK(OP_DIAG, 0, 3, 0);
-                set_coef(h, 1, 0, pack_ctrl ? 1.0 : o.m[0], o.m[0]);
-                set_coef(h, 1, 1, pack_ctrl ? 0.0 : o.m[1], o.m[1]);
+                if (vmask == 0) h.kind = OPK(OP_DIAG_ALL, 0, 0, 0);
+                else if (popc(vmask) == 1) h.kind = OPK(OP_DIAG_V, __builtin_ctz(vmask), 0, 0);
+                else h.kind = OPK(OP_DIAG_GEN, 0, 0, vmask);
+                h.n_coef = 2;
+                set_c(h, 0, 0, pack_ctrl ? 1.0 : o.m[0], o.m[0]);
+                set_c(h, 0, 1, pack_ctrl ? 0.0 : o.m[1], o.m[1]);
             }
             hp.ops.push_back(h);
             return;
@@ -311,39 +426,97 @@ struct PassBuilder {
         const int tb = tile_of_qubit[o.target];
         int vb = -1;
         for (int j = 0; j < QSB_NVB; j++) if (hp.round_vec[r][j] == tb) vb = j;
-        if (o.kind == C_X) {
-            if (tb == P) h.kind = OPK(OP_XP, 0, 3, 0);
-            else h.kind = OPK(OP_X, vb, pack_ctrl ? 2 : 3, 0);
-            hp.ops.push_back(h);
-            return;
+        double m0[8], m1[8]; /* m0: controls not satisfied, m1: satisfied */
+        /* X / CX that could not be absorbed: the swap is issued as the real matrix [[0,1],[1,0]] --
+         * 0*x + y is exact, costs fewer instructions than register moves and keeps every update in place */
+        static const double XMAT[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+        if (o.kind == C_MUX) { snap_mat(o.m, m0); snap_mat(o.m2, m1); }
+        else if (o.kind == C_X) { memcpy(m0, IDENT, sizeof m0); memcpy(m1, XMAT, sizeof m1); }
+        else { memcpy(m0, IDENT, sizeof m0); snap_mat(o.m, m1); }
+        const bool is_mux = (o.kind == C_MUX);
+        /* rx-form multiplexer: m1 = i * m1' with m1' in rx form; the i becomes a thread phase */
+        bool extra_i = false;
+        if (is_mux && classify(m0) == 2 && classify(m1) == 3 && is_jform(m1) && !pack_ctrl && h.tmask && tile_of_qubit[o.target] != P) {
+            for (int k = 0; k < 4; k++) { double re_ = m1[2 * k], im_ = m1[2 * k + 1]; m1[2 * k] = im_; m1[2 * k + 1] = -re_; }
+            extra_i = true;
         }
-        /* C_MAT */
-        double m[8];
-        double sc = 0; for (int k = 0; k < 8; k++) sc = std::max(sc, fabs(o.m[k]));
-        for (int k = 0; k < 8; k++) m[k] = snap(o.m[k], sc);
-        const int form = classify(m);
+        int form = classify(m1);
+        if (is_mux || pack_ctrl) form = std::max(form, classify(m0));
+        if (form == 2 && is_mux && classify(m0) != classify(m1)) form = 3;
+        if (form == 2 && pack_ctrl && !is_mux) form = 2; /* identity fits the rx form */
         if (tb == P) {
-            /* out = A*x + B*swap(x): A = (m00, m11), B = (m01, m10) */
-            h.kind = OPK(form == 1 ? OP_MATP_R : OP_MATP_G, 0, 3, 0);
-            set_coef(h, 1, 0, m[0], m[6]); set_coef(h, 1, 1, m[1], m[7]);
-            set_coef(h, 1, 2, m[2], m[4]); set_coef(h, 1, 3, m[3], m[5]);
-        } else if (form == 1) {
-            h.kind = OPK(OP_MAT_R, vb, 3, 0);
-            set_coef(h, 1, 0, pack_ctrl ? 1.0 : m[0], m[0]); set_coef(h, 1, 2, pack_ctrl ? 0.0 : m[2], m[2]);
-            set_coef(h, 1, 4, pack_ctrl ? 0.0 : m[4], m[4]); set_coef(h, 1, 6, pack_ctrl ? 1.0 : m[6], m[6]);
-        } else if (form == 2) {
-            h.kind = OPK(OP_MAT_I, vb, 3, 0);
-            const double a = m[0], b = m[3], c = m[5], d = m[6];
-            set_coef(h, 1, 0, pack_ctrl ? 1.0 : a, a);
-            set_coef(h, 1, 1, pack_ctrl ? 0.0 : -b, -b); set_coef(h, 1, 2, pack_ctrl ? 0.0 : b, b);
-            set_coef(h, 1, 3, pack_ctrl ? 0.0 : -c, -c); set_coef(h, 1, 4, pack_ctrl ? 0.0 : c, c);
-            set_coef(h, 1, 6, pack_ctrl ? 1.0 : d, d);
+            if (form == 2) form = 3;
+            h.kind = OPK(form == 1 ? OP_MATP_R : OP_MATP_G, 0, (is_mux && h.tmask) ? 1 : 0, 0);
+            h.n_coef = form == 1 ? 2 : 4;
+            fill_matp(h, (is_mux && h.tmask) ? 1 : 0, form, m1);
+            if (is_mux && h.tmask) fill_matp(h, 0, form, m0);
+            else if (is_mux) fill_matp(h, 0, form, m1); /* mux without any control left cannot occur */
         } else {
-            h.kind = OPK(OP_MAT_G, vb, 3, 0);
-            for (int k = 0; k < 8; k++) set_coef(h, 1, k, pack_ctrl ? ((k == 0 || k == 6) ? 1.0 : 0.0) : m[k], m[k]);
+            const int opc = form == 1 ? OP_MAT_R : form == 2 ? OP_MAT_I : OP_MAT_G;
+            h.n_coef = form == 1 ? 4 : form == 2 ? 6 : 8;
+            if (is_mux && h.tmask) {
+                /* thread-level select: failing threads use m0; passing threads use m1 (hi lane only if the pack bit is a control too) */
+                h.kind = OPK(opc, vb, 1, 0);
+                fill_mat(h, 0, form, m0, m0);
+                fill_mat(h, 1, form, pack_ctrl ? m0 : m1, m1);
+            } else {
+                /* no thread-level control (mux on the pack bit alone) or plain controlled gate: one set */
+                h.kind = OPK(opc, vb, 0, 0);
+                fill_mat(h, 0, form, pack_ctrl ? m0 : m1, m1);
+            }
         }
-        (void)lo_id;
         hp.ops.push_back(h);
+        if (extra_i) {
+            HostOp t; memset(&t, 0, sizeof t);
+            t.kind = OPK(OP_TPHASE, 0, 0, 0); t.tmask = h.tmask; t.tph[0] = 0.0; t.tph[1] = 1.0;
+            hp.ops.push_back(t);
+        }
+    }
+
+    /* serialise header + rounds + op stream into the kernel-parameter blob */
+    int serialise()
+    {
+        const bool f32 = M.f32;
+        std::vector<uint8_t> &b = hp.blob;
+        auto al16 = [](size_t x) { return (x + 15) / 16 * 16; };
+        size_t off = al16(sizeof(DevPass));
+        hp.hdr.rounds_off16 = (uint32_t)(off / 16);
+        off += al16(sizeof(DevRound) * hp.rounds.size());
+        std::vector<uint8_t> stream;
+        for (size_t r = 0; r < hp.rounds.size(); r++) {
+            hp.rounds[r].op_off16 = (uint32_t)((off + stream.size()) / 16);
+            hp.rounds[r].n_ops = hp.round_op_count[r];
+            for (uint32_t k = hp.round_op_begin[r]; k < hp.round_op_begin[r] + hp.round_op_count[r]; k++) {
+                const HostOp &h = hp.ops[k];
+                const int code = h.kind & 0xff;
+                const bool mux = (h.kind >> 16) & 1;
+                const int sets = mux ? 2 : 1;
+                size_t payload = (code == OP_TPHASE) ? 16 : al16((size_t)h.n_coef * 8 * sets);
+                OpHdr oh; oh.kind = h.kind; oh.size16 = (uint32_t)((16 + payload) / 16); oh.tmask = h.tmask;
+                size_t at = stream.size();
+                stream.resize(at + 16 + payload, 0);
+                memcpy(&stream[at], &oh, 16);
+                uint8_t *p = &stream[at + 16];
+                if (code == OP_TPHASE) {
+                    if (f32) { float v[2] = {(float)h.tph[0], (float)h.tph[1]}; memcpy(p, v, 8); }
+                    else memcpy(p, h.tph, 16);
+                } else {
+                    for (int s = 0; s < sets; s++) for (int k = 0; k < h.n_coef; k++) {
+                        if (f32) { float v[2] = {(float)h.c[s][k][0], (float)h.c[s][k][1]}; memcpy(p, v, 8); }
+                        else memcpy(p, &h.c[s][k][1], 8); /* f64 has no pack lanes: the "hi" entry is the value */
+                        p += 8;
+                    }
+                }
+            }
+        }
+        const size_t total = off + stream.size();
+        if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_ERR_ARG; }
+        hp.hdr.blob_bytes = (uint32_t)total;
+        b.assign(total <= QSB_BLOB_SMALL ? QSB_BLOB_SMALL : QSB_BLOB_LARGE, 0);
+        memcpy(&b[0], &hp.hdr, sizeof(DevPass));
+        memcpy(&b[(size_t)hp.hdr.rounds_off16 * 16], hp.rounds.data(), sizeof(DevRound) * hp.rounds.size());
+        memcpy(&b[off], stream.data(), stream.size());
+        return QSB_OK;
     }
 };
 
@@ -366,6 +539,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     plan->passes.clear();
 
     std::vector<COp> cops = cops_in;
+    absorb_cx(cops, n);
     if (!(gphase[0] == 1.0 && gphase[1] == 0.0)) {
         COp c; memset(&c, 0, sizeof c); c.kind = C_PHASE; c.target = -1; c.ctrl = 0; c.m[0] = gphase[0]; c.m[1] = gphase[1];
         cops.push_back(c);
@@ -375,7 +549,6 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     std::vector<char> done(N, 0);
     size_t left = N, first_open = 0;
 
-    /* logical qubits sitting on the forced low positions */
     while (left) {
         uint64_t S = 0; int nS = 0;
         for (int q = 0; q < n; q++) if (perm.pos[q] < M.a) { S |= 1ULL << q; }
@@ -383,7 +556,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         Blocker B; B.clear();
         std::vector<COp> mine;
         std::vector<size_t> mine_idx;
-        for (size_t i = first_open; i < N; i++) {
+        for (size_t i = first_open; i < N && (int)mine.size() < MAX_PASS_OPS; i++) {
             if (done[i]) continue;
             const COp &o = cops[i];
             bool can = B.ok(o);
@@ -397,12 +570,17 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             else { B.block(o); if (B.full >= n) break; }
         }
         if (mine.empty()) { qsb_set_error("scheduler made no progress (gate on a non-local qubit?)"); return QSB_ERR_ARG; }
-        for (size_t i : mine_idx) { done[i] = 1; left--; }
-        while (first_open < N && done[first_open]) first_open++;
 
         PassBuilder pb(M, perm);
         pb.set_tile(S);
-        int rc = pb.build_rounds(mine);
+        std::vector<char> used;
+        int rc = pb.build_rounds(mine, used);
+        if (rc) return rc;
+        size_t consumed = 0;
+        for (size_t k = 0; k < mine_idx.size(); k++) if (used[k]) { done[mine_idx[k]] = 1; left--; consumed++; }
+        if (!consumed) { qsb_set_error("scheduler made no progress inside a pass"); return QSB_ERR_ARG; }
+        while (first_open < N && done[first_open]) first_open++;
+        rc = pb.serialise();
         if (rc) return rc;
         plan->passes.push_back(std::move(pb.hp));
     }

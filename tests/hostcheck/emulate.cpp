@@ -46,19 +46,19 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
             /* ---- load ---- */
             for (int tid = 0; tid < QSB_THREADS; tid++) {
                 uint64_t g = src_outer;
-                for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) g |= RD.thr_gidx[j];
+                for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) g |= RD.thr[j].gidx;
                 gthr[tid] = g;
                 uint32_t sb = 0;
-                for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.ld_thr[j];
+                for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr[j].ld;
                 for (int v = 0; v < QSB_NV; v++) {
                     if (rd == 0) {
                         uint64_t gi = g;
-                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) gi |= RD.vec_gidx[b];
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) gi |= RD.vec[b].gidx;
                         for (int l = 0; l < L; l++) regs[((size_t)tid * QSB_NV + v) * L + l] = st[(gi & loc_mask) | (uint64_t)l];
                         if (f32 && (gi & 1)) rep.noncontig++;
                     } else {
                         uint32_t slot = sb;
-                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.ld_vec[b];
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.vec[b].ld;
                         for (int l = 0; l < L; l++) regs[((size_t)tid * QSB_NV + v) * L + l] = smem[(size_t)slot * L + l];
                     }
                 }
@@ -79,8 +79,8 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                     for (int ln = 0; ln < phase_lanes; ln++) {
                         int tid = w * phase_lanes + ln;
                         uint32_t slot = 0;
-                        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) slot ^= RD.ld_thr[j];
-                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.ld_vec[b];
+                        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) slot ^= RD.thr[j].ld;
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.vec[b].ld;
                         banks.insert(slot & ((1u << nb) - 1));
                     }
                     int conflict = phase_lanes / (int)banks.size();
@@ -91,23 +91,23 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
             for (int tid = 0; tid < QSB_THREADS; tid++) {
                 cd *R = &regs[(size_t)tid * QSB_NV * L];
                 cd pend(1.0, 0.0);
-                for (uint32_t i = 0; i < RD.n_ops; i++) {
-                    const HostOp &op = hp.ops[RD.op_begin + i];
-                    const uint32_t code = op.kind & 0xff, vb = (op.kind >> 8) & 0xf, lanes = (op.kind >> 12) & 3;
+                for (uint32_t i = 0; i < hp.round_op_count[rd]; i++) {
+                    const HostOp &op = hp.ops[hp.round_op_begin[rd] + i];
+                    const uint32_t code = op.kind & 0xff, vb = (op.kind >> 8) & 0xf, vmask = (op.kind >> 20) & 0xf;
                     const bool mux = (op.kind >> 16) & 1;
                     const bool pred = (gthr[tid] & op.tmask) == op.tmask;
                     if (!pred && !mux) continue;
-                    const double *c = op.c + (pred ? 16 : 0);
-                    auto C = [&](int k, int l) { return c[k * 2 + (f32 ? l : 0)]; };
+                    const int set = (mux && pred) ? 1 : 0;
+                    auto C = [&](int k, int l) { return op.c[set][k][f32 ? l : 1]; };
+                    if (code == OP_TPHASE) { pend *= cd(op.tph[0], op.tph[1]); continue; }
                     for (int v = 0; v < QSB_NV; v++) {
-                        if ((v & op.vmask) != op.vmask) continue;
                         if (code == OP_MAT_R || code == OP_MAT_I || code == OP_MAT_G) {
                             if ((v >> vb) & 1) continue;
                             int w = v | (1 << vb);
                             for (int l = 0; l < L; l++) {
                                 cd x0 = R[v * L + l], x1 = R[w * L + l], m00, m01, m10, m11;
-                                if (code == OP_MAT_R) { m00 = C(0, l); m01 = C(2, l); m10 = C(4, l); m11 = C(6, l); }
-                                else if (code == OP_MAT_I) { m00 = C(0, l); m01 = cd(0, C(2, l)); m10 = cd(0, C(4, l)); m11 = C(6, l);
+                                if (code == OP_MAT_R) { m00 = C(0, l); m01 = C(1, l); m10 = C(2, l); m11 = C(3, l); }
+                                else if (code == OP_MAT_I) { m00 = C(0, l); m01 = cd(0, C(2, l)); m10 = cd(0, C(4, l)); m11 = C(5, l);
                                     if (C(1, l) != -C(2, l) || C(3, l) != -C(4, l)) rep.bad_slots++; }
                                 else { m00 = cd(C(0, l), C(1, l)); m01 = cd(C(2, l), C(3, l)); m10 = cd(C(4, l), C(5, l)); m11 = cd(C(6, l), C(7, l)); }
                                 R[v * L + l] = m00 * x0 + m01 * x1;
@@ -116,23 +116,18 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                         } else if (code == OP_MATP_R || code == OP_MATP_G) {
                             cd x0 = R[v * L], x1 = R[v * L + 1];
                             cd A0, A1, B0, B1;
-                            if (code == OP_MATP_R) { A0 = C(0, 0); A1 = C(0, 1); B0 = C(2, 0); B1 = C(2, 1); }
+                            if (code == OP_MATP_R) { A0 = C(0, 0); A1 = C(0, 1); B0 = C(1, 0); B1 = C(1, 1); }
                             else { A0 = cd(C(0, 0), C(1, 0)); A1 = cd(C(0, 1), C(1, 1)); B0 = cd(C(2, 0), C(3, 0)); B1 = cd(C(2, 1), C(3, 1)); }
                             R[v * L] = A0 * x0 + B0 * x1;
                             R[v * L + 1] = A1 * x1 + B1 * x0;
-                        } else if (code == OP_X) {
-                            if ((v >> vb) & 1) continue;
-                            int w = v | (1 << vb);
-                            for (int l = 0; l < L; l++) if (!f32 || ((lanes >> l) & 1)) std::swap(R[v * L + l], R[w * L + l]);
-                        } else if (code == OP_XP) {
-                            std::swap(R[v * L], R[v * L + 1]);
-                        } else if (code == OP_DIAG) {
+                        } else if (code == OP_DIAG_V || code == OP_DIAG_ALL || code == OP_DIAG_GEN) {
+                            if (code == OP_DIAG_V && !((v >> vb) & 1)) continue;
+                            if (code == OP_DIAG_GEN && (v & vmask) != vmask) continue;
                             for (int l = 0; l < L; l++) R[v * L + l] *= cd(C(0, l), C(1, l));
-                        }
+                        } else rep.bad_slots++;
                     }
-                    if (code == OP_TPHASE) pend *= cd(C(0, 0), C(1, 0));
                 }
-                if (RD.flags & 1) for (int k = 0; k < QSB_NV * L; k++) R[k] *= pend;
+                if (hp.rounds[rd].flags & 1) for (int k = 0; k < QSB_NV * L; k++) R[k] *= pend;
                 else if (pend != cd(1.0, 0.0)) rep.bad_slots++;
             }
             /* ---- store ---- */
@@ -150,10 +145,10 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                 std::fill(written.begin(), written.end(), 0);
                 for (int tid = 0; tid < QSB_THREADS; tid++) {
                     uint32_t sb = 0;
-                    for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.st_thr[j];
+                    for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr[j].st;
                     for (int v = 0; v < QSB_NV; v++) {
                         uint32_t slot = sb;
-                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.st_vec[b];
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.vec[b].st;
                         if (slot >= 4096) { rep.bad_slots++; continue; }
                         written[slot]++;
                         for (int l = 0; l < L; l++) smem[(size_t)slot * L + l] = regs[((size_t)tid * QSB_NV + v) * L + l];
@@ -165,8 +160,8 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                     for (int ln = 0; ln < phase_lanes; ln++) {
                         int tid = w * phase_lanes + ln;
                         uint32_t slot = 0;
-                        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) slot ^= RD.st_thr[j];
-                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.st_vec[b];
+                        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) slot ^= RD.thr[j].st;
+                        for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.vec[b].st;
                         banks.insert(slot & ((1u << nb) - 1));
                     }
                     int conflict = phase_lanes / (int)banks.size();

@@ -41,7 +41,7 @@ def test_grover_argmax_set_and_probabilities(precision):
         probs = s.probabilities()
     assert idx in (3, 18)                      # p[3] - p[18] = 1.4e-15 in the reference
     assert abs(p - 0.49959115777166263) < 1e-5
-    assert abs(norm - 1.0) < 1e-5
+    assert abs(norm - 1.0) < (1e-4 if precision == F32 else 1e-12)   # 2445 sequential f32 gates
     assert set(np.argsort(probs)[-2:]) == {3, 18}
 
 
