@@ -51,7 +51,10 @@ enum {
     OP_MAT_G = 3,    /* target = vector bit; general complex                   */
     OP_MATP_R = 4,   /* target = pack bit (f32 only); real                     */
     OP_MATP_G = 5,   /* target = pack bit (f32 only); general                  */
-    /* 6..8 unused: X / CX are issued as OP_MAT_R / OP_MATP_R with [[0,1],[1,0]]   */
+    OP_MAT_U = 6,    /* real, unit form a*[[1,p],[q,r]]: x0 += p*x1; x1 = k*x1 + q*x0 (k = r - q*p);
+                        the scale a goes to the per-thread pending scalar.  Pure in-place chain. */
+    OP_MAT_UI = 7,   /* rx form a*[[1,ip],[iq,r]] in the same unit form (k = r + q*p)       */
+    /* X / CX that were not absorbed are issued as OP_MAT_R / OP_MATP_R with [[0,1],[1,0]]    */
     OP_DIAG_V = 9,   /* phase on the vectors whose vector bit `vb` is set      */
     OP_DIAG_ALL = 10,/* phase on all vectors (lane-dependent, e.g. rz on the pack qubit) */
     OP_DIAG_GEN = 11,/* phase on vectors with (v & vmask) == vmask, vmask in kind bits 20..23 */
@@ -70,6 +73,7 @@ enum {
  *   OP_MAT_R : m00 m01 m10 m11                       (4 entries per set)
  *   OP_MAT_I : a -b b -c c d  for [[a, ib],[ic, d]]  (6 entries per set)
  *   OP_MAT_G : m00r m00i m01r m01i m10r m10i m11r m11i (8 entries per set)
+ *   OP_MAT_U : p q k a   (a: scale, lo lane = value)    OP_MAT_UI: p -p q -q k a
  *   OP_MATP_R: A B          out = A*x + B*swap(x), A=(m00,m11) B=(m01,m10)
  *   OP_MATP_G: Ar Ai Br Bi
  *   OP_DIAG_*: pr pi

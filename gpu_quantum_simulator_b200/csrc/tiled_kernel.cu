@@ -36,11 +36,17 @@ template <> struct VT<float> {
     static __device__ __forceinline__ void acc(V &acc_, V a, V b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc_) : "l"(a), "l"(b)); }
     /* x = a * x + t */
     static __device__ __forceinline__ void upd(V &x, V a, V t) { asm("fma.rn.f32x2 %0, %1, %0, %2;" : "+l"(x) : "l"(a), "l"(t)); }
+    /* x = a * x + t, ordered after the producers of d1..d3 (they read the old x): keeps ptxas from
+     * hoisting the in-place update above those reads, which would cost a register copy */
+    static __device__ __forceinline__ void updd(V &x, V a, V t, V d1) { asm("fma.rn.f32x2 %0, %1, %0, %2; // %3" : "+l"(x) : "l"(a), "l"(t), "l"(d1)); }
+    static __device__ __forceinline__ void updd(V &x, V a, V t, V d1, V d2, V d3) { asm("fma.rn.f32x2 %0, %1, %0, %2; // %3 %4 %5" : "+l"(x) : "l"(a), "l"(t), "l"(d1), "l"(d2), "l"(d3)); }
     static __device__ __forceinline__ V neg(V a) { return a ^ 0x8000000080000000ULL; }
     static __device__ __forceinline__ V bc(float s) { unsigned u = __float_as_uint(s); return ((V)u << 32) | u; }
     static __device__ __forceinline__ V swp(V a) { return (a >> 32) | (a << 32); }
     static __device__ __forceinline__ V coef(const uint2 *c, int k) { return reinterpret_cast<const V *>(c)[k]; }
+    static __device__ __forceinline__ void coef2(const uint2 *c, int k, V &x, V &y) { const ulonglong2 u = reinterpret_cast<const ulonglong2 *>(c)[k >> 1]; x = u.x; y = u.y; }
     static __device__ __forceinline__ void tphase(const uint2 *c, float &pr, float &pi) { uint2 u = c[0]; pr = __uint_as_float(u.x); pi = __uint_as_float(u.y); }
+    static __device__ __forceinline__ float scalar(const uint2 *c, int k) { return __uint_as_float(c[k].x); }
 };
 template <> struct VT<double> {
     typedef double V;
@@ -48,11 +54,15 @@ template <> struct VT<double> {
     static __device__ __forceinline__ V mul(V a, V b) { V d; asm("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b)); return d; }
     static __device__ __forceinline__ void acc(V &acc_, V a, V b) { asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc_) : "d"(a), "d"(b)); }
     static __device__ __forceinline__ void upd(V &x, V a, V t) { asm("fma.rn.f64 %0, %1, %0, %2;" : "+d"(x) : "d"(a), "d"(t)); }
+    static __device__ __forceinline__ void updd(V &x, V a, V t, V d1) { asm("fma.rn.f64 %0, %1, %0, %2; // %3" : "+d"(x) : "d"(a), "d"(t), "d"(d1)); }
+    static __device__ __forceinline__ void updd(V &x, V a, V t, V d1, V d2, V d3) { asm("fma.rn.f64 %0, %1, %0, %2; // %3 %4 %5" : "+d"(x) : "d"(a), "d"(t), "d"(d1), "d"(d2), "d"(d3)); }
     static __device__ __forceinline__ V neg(V a) { return -a; }
     static __device__ __forceinline__ V bc(double s) { return s; }
     static __device__ __forceinline__ V swp(V a) { return a; }
     static __device__ __forceinline__ V coef(const uint2 *c, int k) { return reinterpret_cast<const double *>(c)[k]; }
+    static __device__ __forceinline__ void coef2(const uint2 *c, int k, V &x, V &y) { const double2 u = reinterpret_cast<const double2 *>(c)[k >> 1]; x = u.x; y = u.y; }
     static __device__ __forceinline__ void tphase(const uint2 *c, double &pr, double &pi) { pr = coef(c, 0); pi = coef(c, 1); }
+    static __device__ __forceinline__ double scalar(const uint2 *c, int k) { return coef(c, k); }
 };
 
 #define NV QSB_NV
@@ -63,8 +73,8 @@ __device__ __forceinline__ void cmul_inplace(typename VT<R>::V &xr, typename VT<
 {
     typedef VT<R> T;
     const typename T::V t0 = T::mul(npi, xi), t1 = T::mul(pi, xr);
-    T::upd(xr, pr, t0);
-    T::upd(xi, pr, t1);
+    T::updd(xr, pr, t0, t1);
+    T::updd(xi, pr, t1, t0);
 }
 
 /* 2x2 on a vector bit.  FORM: 1 real, 2 real-diag/imag-offdiag, 3 general.
@@ -74,27 +84,29 @@ __device__ __forceinline__ void mat_v(typename VT<R>::V (&re)[NV], typename VT<R
 {
     typedef VT<R> T; typedef typename T::V V;
     if (FORM == 1) {
-        const V a = T::coef(c, 0), b = T::coef(c, 1), cc = T::coef(c, 2), d = T::coef(c, 3);
+        V a, b, cc, d;                       /* payload order: m01 m10 | m00 m11 (cross terms first) */
+        T::coef2(c, 0, b, cc); T::coef2(c, 2, a, d);
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
             const int w = v | (1 << VB);
             const V t0 = T::mul(b, re[w]), t1 = T::mul(b, im[w]), t2 = T::mul(cc, re[v]), t3 = T::mul(cc, im[v]);
-            T::upd(re[v], a, t0); T::upd(im[v], a, t1);
-            T::upd(re[w], d, t2); T::upd(im[w], d, t3);
+            T::updd(re[v], a, t0, t2); T::updd(im[v], a, t1, t3);
+            T::updd(re[w], d, t2, t0); T::updd(im[w], d, t3, t1);
         }
     } else if (FORM == 2) {
-        /* [[a, i b],[i c, d]]: payload a -b b -c c d (host pre-negates) */
-        const V a = T::coef(c, 0), nb = T::coef(c, 1), b = T::coef(c, 2), nc = T::coef(c, 3), cc = T::coef(c, 4), d = T::coef(c, 5);
+        /* [[a, i b],[i c, d]] (host pre-negates) */
+        V a, nb, b, nc, cc, d;               /* payload order: -b b | -c c | a d */
+        T::coef2(c, 0, nb, b); T::coef2(c, 2, nc, cc); T::coef2(c, 4, a, d);
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
             const int w = v | (1 << VB);
             const V t0 = T::mul(nb, im[w]), t1 = T::mul(b, re[w]), t2 = T::mul(nc, im[v]), t3 = T::mul(cc, re[v]);
-            T::upd(re[v], a, t0); T::upd(im[v], a, t1);
-            T::upd(re[w], d, t2); T::upd(im[w], d, t3);
+            T::updd(re[v], a, t0, t3); T::updd(im[v], a, t1, t2);
+            T::updd(re[w], d, t2, t1); T::updd(im[w], d, t3, t0);
         }
     } else {
-        const V ar = T::coef(c, 0), ai = T::coef(c, 1), br = T::coef(c, 2), bi = T::coef(c, 3);
-        const V cr = T::coef(c, 4), ci = T::coef(c, 5), dr = T::coef(c, 6), di = T::coef(c, 7);
+        V ar, ai, br, bi, cr, ci, dr, di;    /* payload order: m00i m01r | m01i m10r | m10i m11i | m00r m11r */
+        T::coef2(c, 0, ai, br); T::coef2(c, 2, bi, cr); T::coef2(c, 4, ci, di); T::coef2(c, 6, ar, dr);
         const V nai = T::neg(ai), nbi = T::neg(bi), nci = T::neg(ci), ndi = T::neg(di);
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
@@ -103,9 +115,46 @@ __device__ __forceinline__ void mat_v(typename VT<R>::V (&re)[NV], typename VT<R
             V t1 = T::mul(ai, re[v]);  T::acc(t1, br, im[w]); T::acc(t1, bi, re[w]);    /* im[v] */
             V t2 = T::mul(cr, re[v]);  T::acc(t2, nci, im[v]); T::acc(t2, ndi, im[w]);  /* re[w] */
             V t3 = T::mul(cr, im[v]);  T::acc(t3, ci, re[v]); T::acc(t3, di, re[w]);    /* im[w] */
-            T::upd(re[v], ar, t0); T::upd(im[v], ar, t1);
-            T::upd(re[w], dr, t2); T::upd(im[w], dr, t3);
+            T::updd(re[v], ar, t0, t1, t2, t3); T::updd(im[v], ar, t1, t0, t2, t3);
+            T::updd(re[w], dr, t2, t0, t1, t3); T::updd(im[w], dr, t3, t0, t1, t2);
         }
+    }
+}
+
+/* unit form on a vector bit (see tiled.h): strictly in-place dependency chains.
+ *   real: x0 += p*x1 ; x1 = k*x1 + q*x0        rx form: x0 += i p x1 ; x1 = k*x1 + i q x0 */
+template <typename R, int VB, bool IMAG>
+__device__ __forceinline__ void unit_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
+{
+    typedef VT<R> T; typedef typename T::V V;
+    if (!IMAG) {
+        V p, q, k, a_; T::coef2(c, 0, p, q); T::coef2(c, 2, k, a_);
+#pragma unroll
+        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
+            const int w = v | (1 << VB);
+            T::acc(re[v], p, re[w]); T::acc(im[v], p, im[w]);
+            const V t = T::mul(q, re[v]), u = T::mul(q, im[v]);
+            T::upd(re[w], k, t); T::upd(im[w], k, u);
+        }
+    } else {
+        V p, np, q, nq, k, a_; T::coef2(c, 0, p, np); T::coef2(c, 2, q, nq); T::coef2(c, 4, k, a_);
+#pragma unroll
+        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
+            const int w = v | (1 << VB);
+            T::acc(re[v], np, im[w]); T::acc(im[v], p, re[w]);
+            const V t = T::mul(nq, im[v]), u = T::mul(q, re[v]);
+            T::upd(re[w], k, t); T::upd(im[w], k, u);
+        }
+    }
+}
+template <typename R, bool IMAG>
+__device__ __forceinline__ void unit_dispatch(int vb, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
+{
+    switch (vb) {
+    case 0: unit_v<R, 0, IMAG>(re, im, c); break;
+    case 1: unit_v<R, 1, IMAG>(re, im, c); break;
+    case 2: unit_v<R, 2, IMAG>(re, im, c); break;
+    default: unit_v<R, 3, IMAG>(re, im, c); break;
     }
 }
 
@@ -148,7 +197,7 @@ __device__ __forceinline__ void mat_p(unsigned long long (&re)[NV], unsigned lon
             const V sr = T::swp(re[v]), si = T::swp(im[v]);
             V t0 = T::mul(nAi, im[v]); T::acc(t0, Br, sr); T::acc(t0, nBi, si);
             V t1 = T::mul(Ai, re[v]);  T::acc(t1, Br, si); T::acc(t1, Bi, sr);
-            T::upd(re[v], Ar, t0); T::upd(im[v], Ar, t1);
+            T::updd(re[v], Ar, t0, t1); T::updd(im[v], Ar, t1, t0);
         }
     }
 }
@@ -282,6 +331,8 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const __grid_constant__
             const uint32_t code = kind & 0xffu;
             const int vb = (kind >> 8) & 0xf;
             switch (code) {
+            case OP_MAT_U: { const uint2 *cs = c + ((mux && pred) ? 4 : 0); unit_dispatch<R, false>(vb, re, im, cs); const R a = T::scalar(cs, 3); psr *= a; psi *= a; break; }
+            case OP_MAT_UI: { const uint2 *cs = c + ((mux && pred) ? 6 : 0); unit_dispatch<R, true>(vb, re, im, cs); const R a = T::scalar(cs, 5); psr *= a; psi *= a; break; }
             case OP_MAT_R: mat_dispatch<R, 1>(vb, re, im, c + ((mux && pred) ? 4 : 0)); break;
             case OP_MAT_I: mat_dispatch<R, 2>(vb, re, im, c + ((mux && pred) ? 6 : 0)); break;
             case OP_MAT_G: mat_dispatch<R, 3>(vb, re, im, c + ((mux && pred) ? 8 : 0)); break;

@@ -335,7 +335,7 @@ struct PassBuilder {
             for (int i : round_ops[r]) emit(ops[i], r);
             hp.round_op_count[r] = (uint32_t)hp.ops.size() - hp.round_op_begin[r];
             for (uint32_t k = hp.round_op_begin[r]; k < hp.ops.size(); k++)
-                if ((hp.ops[k].kind & 0xff) == OP_TPHASE) hp.rounds[r].flags |= 1u;
+                { const uint32_t cd_ = hp.ops[k].kind & 0xff; if (cd_ == OP_TPHASE || cd_ == OP_MAT_U || cd_ == OP_MAT_UI) hp.rounds[r].flags |= 1u; }
         }
         hp.n_source_ops = (int)(n - left);
         return QSB_OK;
@@ -375,16 +375,18 @@ struct PassBuilder {
     /* fill coefficient set `set` of a vector-bit matrix op: lo lane uses mlo, hi lane mhi */
     static void fill_mat(HostOp &h, int set, int form, const double *mlo, const double *mhi)
     {
-        if (form == 1) {
-            set_c(h, set, 0, mlo[0], mhi[0]); set_c(h, set, 1, mlo[2], mhi[2]);
-            set_c(h, set, 2, mlo[4], mhi[4]); set_c(h, set, 3, mlo[6], mhi[6]);
-        } else if (form == 2) { /* [[a, ib],[ic, d]] -> a -b b -c c d */
-            set_c(h, set, 0, mlo[0], mhi[0]);
-            set_c(h, set, 1, -mlo[3], -mhi[3]); set_c(h, set, 2, mlo[3], mhi[3]);
-            set_c(h, set, 3, -mlo[5], -mhi[5]); set_c(h, set, 4, mlo[5], mhi[5]);
-            set_c(h, set, 5, mlo[6], mhi[6]);
-        } else {
-            for (int k = 0; k < 8; k++) set_c(h, set, k, mlo[k], mhi[k]);
+        if (form == 1) {        /* m01 m10 | m00 m11 */
+            set_c(h, set, 0, mlo[2], mhi[2]); set_c(h, set, 1, mlo[4], mhi[4]);
+            set_c(h, set, 2, mlo[0], mhi[0]); set_c(h, set, 3, mlo[6], mhi[6]);
+        } else if (form == 2) { /* [[a, ib],[ic, d]] -> -b b | -c c | a d */
+            set_c(h, set, 0, -mlo[3], -mhi[3]); set_c(h, set, 1, mlo[3], mhi[3]);
+            set_c(h, set, 2, -mlo[5], -mhi[5]); set_c(h, set, 3, mlo[5], mhi[5]);
+            set_c(h, set, 4, mlo[0], mhi[0]); set_c(h, set, 5, mlo[6], mhi[6]);
+        } else {                /* m00i m01r | m01i m10r | m10i m11i | m00r m11r */
+            set_c(h, set, 0, mlo[1], mhi[1]); set_c(h, set, 1, mlo[2], mhi[2]);
+            set_c(h, set, 2, mlo[3], mhi[3]); set_c(h, set, 3, mlo[4], mhi[4]);
+            set_c(h, set, 4, mlo[5], mhi[5]); set_c(h, set, 5, mlo[7], mhi[7]);
+            set_c(h, set, 6, mlo[0], mhi[0]); set_c(h, set, 7, mlo[6], mhi[6]);
         }
     }
     /* pack-bit matrix op: A = (m00, m11), B = (m01, m10) */
@@ -452,6 +454,32 @@ struct PassBuilder {
             if (is_mux && h.tmask) fill_matp(h, 0, form, m0);
             else if (is_mux) fill_matp(h, 0, form, m1); /* mux without any control left cannot occur */
         } else {
+            /* unit form (see tiled.h): needs a well-conditioned m00 in every variant and no lane dependence */
+            const bool two = is_mux && h.tmask;
+            auto unit_ok = [&](const double *m) { return fabs(m[0]) >= 0.3; };
+            if (!pack_ctrl && (form == 1 || form == 2) && unit_ok(m1) && (!two || unit_ok(m0)) && (is_mux ? (two || true) : true) && !(is_mux && !h.tmask)) {
+                auto fill_unit = [&](int set, const double *m) {
+                    const double a = m[0];
+                    if (form == 1) {
+                        const double pp = m[2] / a, q = m[4] / a, r = m[6] / a;
+                        set_c(h, set, 0, pp, pp); set_c(h, set, 1, q, q); set_c(h, set, 2, r - q * pp, r - q * pp); set_c(h, set, 3, a, a);
+                    } else {
+                        const double pp = m[3] / a, q = m[5] / a, r = m[6] / a;
+                        set_c(h, set, 0, pp, pp); set_c(h, set, 1, -pp, -pp); set_c(h, set, 2, q, q); set_c(h, set, 3, -q, -q);
+                        set_c(h, set, 4, r + q * pp, r + q * pp); set_c(h, set, 5, a, a);
+                    }
+                };
+                h.kind = OPK(form == 1 ? OP_MAT_U : OP_MAT_UI, vb, two ? 1 : 0, 0);
+                h.n_coef = form == 1 ? 4 : 6;
+                if (two) { fill_unit(0, m0); fill_unit(1, m1); } else fill_unit(0, m1);
+                hp.ops.push_back(h);
+                if (extra_i) {
+                    HostOp t; memset(&t, 0, sizeof t);
+                    t.kind = OPK(OP_TPHASE, 0, 0, 0); t.tmask = h.tmask; t.tph[0] = 0.0; t.tph[1] = 1.0;
+                    hp.ops.push_back(t);
+                }
+                return;
+            }
             const int opc = form == 1 ? OP_MAT_R : form == 2 ? OP_MAT_I : OP_MAT_G;
             h.n_coef = form == 1 ? 4 : form == 2 ? 6 : 8;
             if (is_mux && h.tmask) {

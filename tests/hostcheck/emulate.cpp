@@ -101,15 +101,27 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                     auto C = [&](int k, int l) { return op.c[set][k][f32 ? l : 1]; };
                     if (code == OP_TPHASE) { pend *= cd(op.tph[0], op.tph[1]); continue; }
                     for (int v = 0; v < QSB_NV; v++) {
-                        if (code == OP_MAT_R || code == OP_MAT_I || code == OP_MAT_G) {
+                        if (code == OP_MAT_U || code == OP_MAT_UI) {
+                            if ((v >> vb) & 1) continue;
+                            int w = v | (1 << vb);
+                            for (int l = 0; l < L; l++) {
+                                cd x0 = R[v * L + l], x1 = R[w * L + l];
+                                if (code == OP_MAT_U) { double p_ = C(0, l), q = C(1, l), k = C(2, l); x0 += p_ * x1; x1 = k * x1 + q * x0; }
+                                else { double p_ = C(0, l), q = C(2, l), k = C(4, l);
+                                    if (C(1, l) != -p_ || C(3, l) != -q) rep.bad_slots++;
+                                    x0 += cd(0, p_) * x1; x1 = k * x1 + cd(0, q) * x0; }
+                                R[v * L + l] = x0; R[w * L + l] = x1;
+                            }
+                            if (v == 0) pend *= (code == OP_MAT_U ? C(3, 0) : C(5, 0));
+                        } else if (code == OP_MAT_R || code == OP_MAT_I || code == OP_MAT_G) {
                             if ((v >> vb) & 1) continue;
                             int w = v | (1 << vb);
                             for (int l = 0; l < L; l++) {
                                 cd x0 = R[v * L + l], x1 = R[w * L + l], m00, m01, m10, m11;
-                                if (code == OP_MAT_R) { m00 = C(0, l); m01 = C(1, l); m10 = C(2, l); m11 = C(3, l); }
-                                else if (code == OP_MAT_I) { m00 = C(0, l); m01 = cd(0, C(2, l)); m10 = cd(0, C(4, l)); m11 = C(5, l);
-                                    if (C(1, l) != -C(2, l) || C(3, l) != -C(4, l)) rep.bad_slots++; }
-                                else { m00 = cd(C(0, l), C(1, l)); m01 = cd(C(2, l), C(3, l)); m10 = cd(C(4, l), C(5, l)); m11 = cd(C(6, l), C(7, l)); }
+                                if (code == OP_MAT_R) { m01 = C(0, l); m10 = C(1, l); m00 = C(2, l); m11 = C(3, l); }
+                                else if (code == OP_MAT_I) { m01 = cd(0, C(1, l)); m10 = cd(0, C(3, l)); m00 = C(4, l); m11 = C(5, l);
+                                    if (C(0, l) != -C(1, l) || C(2, l) != -C(3, l)) rep.bad_slots++; }
+                                else { m00 = cd(C(6, l), C(0, l)); m01 = cd(C(1, l), C(2, l)); m10 = cd(C(3, l), C(4, l)); m11 = cd(C(7, l), C(5, l)); }
                                 R[v * L + l] = m00 * x0 + m01 * x1;
                                 R[w * L + l] = m10 * x0 + m11 * x1;
                             }
