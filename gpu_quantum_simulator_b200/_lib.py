@@ -52,6 +52,8 @@ SYMBOLS = {
     "qsb_plan_dry_run": (C.c_int, [C.c_int, C.POINTER(Options), C.POINTER(Gate), C.c_size_t, C.POINTER(RunStats)]),
     "qsb_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "qsb_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "qsb_download_physical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "qsb_get_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "qsb_download_native": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "qsb_norm_argmax": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "qsb_probabilities": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),

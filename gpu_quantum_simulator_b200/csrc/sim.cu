@@ -515,6 +515,35 @@ extern "C" int qsb_download_native(qsb_t *s, void *dst, uint64_t first, uint64_t
                               : download_native_impl<double>(s, (double *)dst, first, count);
 }
 
+extern "C" int qsb_get_layout(const qsb_t *s, int8_t *perm64, int *nloc)
+{
+    if (!s || !perm64) { qsb_set_error("qsb_get_layout: null argument"); return QSB_ERR_ARG; }
+    for (int q = 0; q < 64; q++) perm64[q] = q < s->n ? s->perm.pos[q] : (int8_t)-1;
+    if (nloc) *nloc = s->nloc;
+    return QSB_OK;
+}
+
+extern "C" int qsb_download_physical(qsb_t *s, double *re_im, uint64_t first, uint64_t count)
+{
+    if (!s || (!re_im && count)) { qsb_set_error("qsb_download_physical: null argument"); return QSB_ERR_ARG; }
+    const uint64_t nl = 1ULL << s->nloc;
+    if (first > nl || count > nl - first) { qsb_set_error("range exceeds the local shard"); return QSB_ERR_ARG; }
+    QSB_CUDA(cudaSetDevice(s->device));
+    PermArg P; memset(&P, 0, sizeof P);
+    P.n = s->nloc;
+    for (int q = 0; q < s->nloc; q++) P.pos[q] = (int8_t)q;   /* identity: physical order */
+    const uint64_t chunk = s->staging_bytes / 16;
+    for (uint64_t off = 0; off < count; off += chunk) {
+        uint64_t c = std::min(chunk, count - off);
+        if (s->prec == QSB_F32) k_export<float><<<(unsigned)((c + 255) / 256), 256, 0, s->stream>>>((const float *)s->state, (double *)s->staging, first + off, c, P, nl - 1);
+        else k_export<double><<<(unsigned)((c + 255) / 256), 256, 0, s->stream>>>((const double *)s->state, (double *)s->staging, first + off, c, P, nl - 1);
+        QSB_CUDA(cudaGetLastError());
+        QSB_CUDA(cudaMemcpyAsync(re_im + 2 * off, s->staging, c * 16, cudaMemcpyDeviceToHost, s->stream));
+        QSB_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return QSB_OK;
+}
+
 extern "C" int qsb_upload(qsb_t *s, const double *re_im, uint64_t first, uint64_t count)
 {
     if (!s || (!re_im && count)) { qsb_set_error("qsb_upload: null argument"); return QSB_ERR_ARG; }

@@ -204,10 +204,12 @@ struct PassBuilder {
 
     PassBuilder(const Machine &m, const BitPerm &p) : M(m), perm(p) {}
 
-    /* choose the tile from the set of resident logical qubits */
-    void set_tile(uint64_t resident)
+    /* choose the tile from the set of resident logical qubits (+ positions that must be resident);
+     * pos_map, if given, relocates physical positions inside the tile (in-tile qubit permutation:
+     * free, because the tile is gathered and scattered anyway). */
+    void set_tile(uint64_t resident, uint64_t forced_pos = 0, const int8_t *pos_map = nullptr)
     {
-        uint64_t posmask = 0;
+        uint64_t posmask = forced_pos;
         for (int q = 0; q < M.n; q++) if ((resident >> q) & 1) posmask |= 1ULL << perm.pos[q];
         for (int p = 0; p < M.a; p++) posmask |= 1ULL << p;              /* contiguous low segment */
         for (int p = 0; p < M.nloc && popc(posmask) < M.T; p++) posmask |= 1ULL << p; /* pad from the bottom */
@@ -218,7 +220,8 @@ struct PassBuilder {
         for (int q = 0; q < 64; q++) tile_of_qubit[q] = -1;
         int j = 0;
         for (int p = 0; p < M.nloc + M.g; p++) if ((posmask >> p) & 1) {
-            hp.tile_src[j] = (int8_t)p; hp.tile_dst[j] = (int8_t)p;
+            hp.tile_src[j] = (int8_t)p;
+            hp.tile_dst[j] = pos_map ? pos_map[p] : (int8_t)p;
             tile_qubit[j] = inv[p];
             if (inv[p] >= 0) tile_of_qubit[inv[p]] = j;
             j++;
@@ -330,12 +333,36 @@ struct PassBuilder {
 
         hp.ops.clear();
         hp.round_op_begin.assign(nrounds, 0); hp.round_op_count.assign(nrounds, 0);
+        /* The scale of an un-multiplexed unit-form op is the same for every thread: collect those
+         * into one factor per pass instead of forcing a pending-scalar multiply in each round. */
+        double pass_scale = 1.0;
+        std::vector<std::vector<HostOp>> rops(nrounds);
+        int flagged = -1;
+        for (int r = 0; r < nrounds; r++) {
+            for (int i : round_ops[r]) emit(ops[i], r);
+            rops[r].swap(hp.ops);
+            bool need = false;
+            for (HostOp &h : rops[r]) {
+                const uint32_t cd_ = h.kind & 0xff; const bool mux = (h.kind >> 16) & 1;
+                if (cd_ == OP_TPHASE) need = true;
+                else if (cd_ == OP_MAT_U || cd_ == OP_MAT_UI) {
+                    const int ai = cd_ == OP_MAT_U ? 3 : 5;
+                    if (mux || h.tmask) need = true;   /* per-thread scale */
+                    else { pass_scale *= h.c[0][ai][0]; h.c[0][ai][0] = h.c[0][ai][1] = 1.0; }
+                }
+            }
+            if (need) { hp.rounds[r].flags |= 1u; if (flagged < 0) flagged = r; }
+        }
+        if (pass_scale != 1.0) {
+            if (flagged < 0) { flagged = nrounds - 1; hp.rounds[flagged].flags |= 1u; }
+            HostOp t; memset(&t, 0, sizeof t);
+            t.kind = OPK(OP_TPHASE, 0, 0, 0); t.tmask = 0; t.tph[0] = pass_scale; t.tph[1] = 0.0;
+            rops[flagged].push_back(t);
+        }
         for (int r = 0; r < nrounds; r++) {
             hp.round_op_begin[r] = (uint32_t)hp.ops.size();
-            for (int i : round_ops[r]) emit(ops[i], r);
-            hp.round_op_count[r] = (uint32_t)hp.ops.size() - hp.round_op_begin[r];
-            for (uint32_t k = hp.round_op_begin[r]; k < hp.ops.size(); k++)
-                { const uint32_t cd_ = hp.ops[k].kind & 0xff; if (cd_ == OP_TPHASE || cd_ == OP_MAT_U || cd_ == OP_MAT_UI) hp.rounds[r].flags |= 1u; }
+            for (HostOp &h : rops[r]) hp.ops.push_back(h);
+            hp.round_op_count[r] = (uint32_t)rops[r].size();
         }
         hp.n_source_ops = (int)(n - left);
         return QSB_OK;
@@ -560,7 +587,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 6 : 5);
     if (M.a < (M.f32 ? 3 : 2) || M.a > (M.f32 ? 6 : 5)) { qsb_set_error("low_bits %d unsupported for this precision", M.a); return QSB_ERR_ARG; }
     if (nloc < M.T) { qsb_set_error("internal: local register smaller than a tile"); return QSB_ERR_ARG; }
-    if (g > 0) { qsb_set_error("multi-GPU tiled schedule not available in this build"); return QSB_ERR_ARG; }
+    if (g > 0 && nloc - g < M.a + g) { qsb_set_error("local register too small to exchange %d qubits", g); return QSB_ERR_ARG; }
 
     plan->n = n; plan->prec = prec; plan->g = g; plan->nloc = nloc; plan->rank = rank;
     plan->start_perm = start;
@@ -576,14 +603,13 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     const size_t N = cops.size();
     std::vector<char> done(N, 0);
     size_t left = N, first_open = 0;
+    const int SWAP_MIN_OPS = opt && opt->reserved[0] > 0 ? opt->reserved[0] : 10;
 
-    while (left) {
-        uint64_t S = 0; int nS = 0;
-        for (int q = 0; q < n; q++) if (perm.pos[q] < M.a) { S |= 1ULL << q; }
-        nS = M.a; /* the low positions always occupy `a` tile slots, whether or not a logical qubit lives there */
+    /* greedy op collection for one pass.  S0/n0: qubits / slots already resident. */
+    auto collect = [&](uint64_t S0, int n0, std::vector<COp> &mine, std::vector<size_t> &mine_idx, uint64_t &S_out) {
+        uint64_t S = S0; int nS = n0;
         Blocker B; B.clear();
-        std::vector<COp> mine;
-        std::vector<size_t> mine_idx;
+        mine.clear(); mine_idx.clear();
         for (size_t i = first_open; i < N && (int)mine.size() < MAX_PASS_OPS; i++) {
             if (done[i]) continue;
             const COp &o = cops[i];
@@ -597,20 +623,100 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             if (can) { mine.push_back(o); mine_idx.push_back(i); }
             else { B.block(o); if (B.full >= n) break; }
         }
-        if (mine.empty()) { qsb_set_error("scheduler made no progress (gate on a non-local qubit?)"); return QSB_ERR_ARG; }
-
+        S_out = S;
+    };
+    auto emit_pass = [&](uint64_t S, uint64_t forced_pos, const int8_t *pos_map, const std::vector<COp> &mine,
+                         const std::vector<size_t> &mine_idx, bool allow_empty) -> int {
         PassBuilder pb(M, perm);
-        pb.set_tile(S);
+        pb.set_tile(S, forced_pos, pos_map);
         std::vector<char> used;
         int rc = pb.build_rounds(mine, used);
         if (rc) return rc;
         size_t consumed = 0;
         for (size_t k = 0; k < mine_idx.size(); k++) if (used[k]) { done[mine_idx[k]] = 1; left--; consumed++; }
-        if (!consumed) { qsb_set_error("scheduler made no progress inside a pass"); return QSB_ERR_ARG; }
+        if (!consumed && !allow_empty) { qsb_set_error("scheduler made no progress inside a pass"); return QSB_ERR_ARG; }
         while (first_open < N && done[first_open]) first_open++;
         rc = pb.serialise();
         if (rc) return rc;
+        if (pos_map) for (int q = 0; q < n; q++) if (perm.pos[q] < nloc) perm.pos[q] = pos_map[perm.pos[q]];
         plan->passes.push_back(std::move(pb.hp));
+        return QSB_OK;
+    };
+
+    while (left) {
+        uint64_t lowS = 0;
+        for (int q = 0; q < n; q++) if (perm.pos[q] < M.a) lowS |= 1ULL << q;
+        std::vector<COp> mine; std::vector<size_t> mine_idx; uint64_t S = 0;
+        /* the low positions always occupy `a` tile slots, whether or not a logical qubit lives there */
+        collect(lowS, M.a, mine, mine_idx, S);
+
+        bool want_swap = false;
+        if (g > 0) {
+            int nd = 0; for (const COp &o : mine) if (o.target >= 0) nd++;
+            bool blocked_global = false;
+            size_t seen = 0;
+            for (size_t i = first_open; i < N && seen < (size_t)8 * n; i++) {
+                if (done[i]) continue;
+                seen++;
+                if (cops[i].target >= 0 && perm.pos[cops[i].target] >= nloc) { blocked_global = true; break; }
+            }
+            if (blocked_global && nd < SWAP_MIN_OPS) want_swap = true;
+        }
+        if (!want_swap) {
+            if (mine.empty()) { qsb_set_error("scheduler made no progress (gate on a non-local qubit?)"); return QSB_ERR_ARG; }
+            int rc = emit_pass(S, 0, nullptr, mine, mine_idx, false);
+            if (rc) return rc;
+            continue;
+        }
+
+        /* ---- global <-> local exchange --------------------------------------------------------
+         * victims: the g local qubits whose next non-diagonal use lies furthest ahead (Belady).
+         * They are moved to the top g local positions by an in-tile permutation pass (which also
+         * runs whatever gates fit), then those positions are exchanged with the rank bits. */
+        std::vector<size_t> next_use(n, N + 1);
+        {
+            std::vector<char> seenq(n, 0); int found = 0;
+            for (size_t i = first_open; i < N && found < n; i++) {
+                if (done[i] || cops[i].target < 0) continue;
+                int q = cops[i].target;
+                if (!seenq[q]) { seenq[q] = 1; next_use[q] = i; found++; }
+            }
+        }
+        std::vector<int> cand;
+        for (int q = 0; q < n; q++) if (perm.pos[q] >= M.a && perm.pos[q] < nloc) cand.push_back(q);
+        std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) {
+            if (next_use[x] != next_use[y]) return next_use[x] > next_use[y];
+            return perm.pos[x] > perm.pos[y];
+        });
+        if ((int)cand.size() < g) { qsb_set_error("not enough local qubits to exchange"); return QSB_ERR_ARG; }
+        int8_t pos_map[64]; for (int p = 0; p < 64; p++) pos_map[p] = (int8_t)p;
+        uint64_t forced = 0, vict_pos = 0, top_pos = 0;
+        for (int k = 0; k < g; k++) { vict_pos |= 1ULL << perm.pos[cand[k]]; top_pos |= 1ULL << (nloc - g + k); }
+        uint64_t v_only = vict_pos & ~top_pos, t_only = top_pos & ~vict_pos;
+        while (v_only) {
+            int pv = __builtin_ctzll(v_only), pt = __builtin_ctzll(t_only);
+            v_only &= v_only - 1; t_only &= t_only - 1;
+            pos_map[pv] = (int8_t)pt; pos_map[pt] = (int8_t)pv;
+            forced |= (1ULL << pv) | (1ULL << pt);
+        }
+        if (forced) {
+            /* resident set: low qubits + the qubits living on the forced positions */
+            uint64_t S0 = lowS; int n0 = M.a;
+            for (int q = 0; q < n; q++) if ((forced >> perm.pos[q]) & 1) { if (!((S0 >> q) & 1)) S0 |= 1ULL << q; }
+            n0 += popc(forced);   /* forced positions are >= a: each takes a slot, qubit or padding */
+            collect(S0, n0, mine, mine_idx, S);
+            int rc = emit_pass(S, forced, pos_map, mine, mine_idx, true);
+            if (rc) return rc;
+        }
+        /* exchange marker: top g local positions <-> rank bits */
+        HostPass sw; memset(&sw.hdr, 0, sizeof sw.hdr);
+        sw.is_swap = true; sw.hdr.nloc = nloc;
+        plan->passes.push_back(std::move(sw));
+        for (int q = 0; q < n; q++) {
+            int p = perm.pos[q];
+            if (p >= nloc) perm.pos[q] = (int8_t)(p - g);
+            else if (p >= nloc - g) perm.pos[q] = (int8_t)(p + g);
+        }
     }
     plan->end_perm = perm;
     return QSB_OK;

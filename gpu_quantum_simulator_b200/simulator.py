@@ -198,6 +198,20 @@ class Simulator:
         check(lib.qsb_download_native(self._h, out.ctypes.data, first, count))
         return out
 
+    def layout(self):
+        """-> (perm, nloc): perm[q] = physical index bit of logical qubit q; bits >= nloc are rank bits."""
+        perm = np.zeros(64, dtype=np.int8)
+        nloc = C.c_int()
+        check(lib.qsb_get_layout(self._h, perm.ctypes.data, C.byref(nloc)))
+        return perm, nloc.value
+
+    def shard_physical(self):
+        """The local shard exactly as stored (physical index order), complex128."""
+        _, nloc = self.layout()
+        out = np.empty(2 << nloc, dtype=np.float64)
+        check(lib.qsb_download_physical(self._h, out.ctypes.data, 0, 1 << nloc))
+        return out.view(np.complex128)
+
     def set_state(self, amps, first=0):
         a = np.ascontiguousarray(np.asarray(amps, dtype=np.complex128))
         check(lib.qsb_upload(self._h, a.view(np.float64).ctypes.data, first, a.size))

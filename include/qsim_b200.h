@@ -126,6 +126,12 @@ int qsb_plan_dry_run(int num_qubits, const qsb_options_t *opt, const qsb_gate_t 
  * multi-GPU run each rank may only read its own shard. */
 int qsb_download(qsb_t *s, double *re_im, uint64_t first, uint64_t count);
 int qsb_upload(qsb_t *s, const double *re_im, uint64_t first, uint64_t count);
+/* The shard as it lies on the device: amplitudes first..first+count of the LOCAL PHYSICAL index space
+ * (fp64 pairs), plus the qubit layout needed to interpret it: perm64[q] = physical index bit of
+ * logical qubit q (bits >= *nloc are the rank bits).  This is how a sharded state is gathered:
+ * fused passes may leave the qubits permuted, and no rank owns a contiguous logical range. */
+int qsb_download_physical(qsb_t *s, double *re_im, uint64_t first, uint64_t count);
+int qsb_get_layout(const qsb_t *s, int8_t *perm64, int *nloc);
 /* Raw copy in the device dtype (float or double pairs), logical order. */
 int qsb_download_native(qsb_t *s, void *dst, uint64_t first, uint64_t count);
 /* sum |a|^2 over the local shard, and the local argmax (global index). */

@@ -189,3 +189,80 @@ def parse_reference_style_file(path):
         q = tuple(int(x) for x in re.findall(r"\[(\d+)\]", ops))
         circ.append((name, q, (float(arg),) if arg else ()))
     return circ, n
+
+
+# ---- sharded schedules on the host -------------------------------------------------------------
+def _hc():
+    from gpu_quantum_simulator_b200 import Gate
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck")))
+    L.qsb_hostcheck_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Gate), C.c_size_t]
+    L.qsb_hostcheck_plan.restype = C.c_void_p
+    L.qsb_hostcheck_num_steps.argtypes = [C.c_void_p]
+    L.qsb_hostcheck_step_is_swap.argtypes = [C.c_void_p, C.c_int]
+    L.qsb_hostcheck_nloc.argtypes = [C.c_void_p]
+    L.qsb_hostcheck_run_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.qsb_hostcheck_finish.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+    return L
+
+
+class ShardedHostRun:
+    """One rank of a sharded schedule, interpreted on the host.  Exchanges are the caller's job."""
+
+    def __init__(self, gates, n, world, rank, precision=32, low_bits=0, swap_min_ops=0):
+        self.L = _hc()
+        self.h = self.L.qsb_hostcheck_plan(n, precision, low_bits, world, rank, swap_min_ops, gates, len(gates))
+        if not self.h:
+            raise RuntimeError("hostcheck planning failed")
+        self.n, self.world, self.rank = n, world, rank
+        self.nloc = self.L.qsb_hostcheck_nloc(self.h)
+        self.shard = np.zeros(1 << self.nloc, dtype=np.complex128)
+        if rank == 0:
+            self.shard[0] = 1.0
+        self.steps = self.L.qsb_hostcheck_num_steps(self.h)
+
+    def is_swap(self, i):
+        return bool(self.L.qsb_hostcheck_step_is_swap(self.h, i))
+
+    def run(self, i):
+        assert self.L.qsb_hostcheck_run_step(self.h, i, self.shard.ctypes.data) == 0
+
+    def chunks(self):
+        return self.shard.reshape(self.world, -1)
+
+    def finish(self):
+        rep = (C.c_int * 5)()
+        perm = np.zeros(64, dtype=np.int8)
+        self.L.qsb_hostcheck_finish(self.h, rep, perm.ctypes.data)
+        self.h = None
+        return perm, dict(max_conflict=rep[0], bad_slots=rep[1], noncontig=rep[2], passes=rep[3], swaps=rep[4])
+
+
+def gather_logical(shards, perm, n, nloc):
+    """shards[rank][local physical index] -> complex128 state in logical order."""
+    full = np.concatenate(shards)
+    idx = np.arange(1 << n, dtype=np.uint64)
+    phys = np.zeros_like(idx)
+    for q in range(n):
+        phys |= ((idx >> np.uint64(q)) & np.uint64(1)) << np.uint64(int(perm[q]))
+    return full[phys]
+
+
+def sharded_host_run(circ_gates, n, world, precision=32, low_bits=0, swap_min_ops=0):
+    """All ranks in one process; the exchange is the chunk transpose the NCCL path performs."""
+    ranks = [ShardedHostRun(circ_gates, n, world, r, precision, low_bits, swap_min_ops) for r in range(world)]
+    for i in range(ranks[0].steps):
+        if ranks[0].is_swap(i):
+            ch = [r.chunks().copy() for r in ranks]
+            for r in ranks:
+                for j in range(world):
+                    r.chunks()[j] = ch[j][r.rank]      # chunk r.rank of rank j lands at position j
+        else:
+            for r in ranks:
+                r.run(i)
+    nloc = ranks[0].nloc
+    shards = [r.shard for r in ranks]
+    out = [r.finish() for r in ranks]
+    perm, rep = out[0]
+    for p2, _ in out[1:]:
+        assert np.array_equal(perm, p2)
+    return gather_logical(shards, perm, n, nloc), rep

@@ -210,3 +210,49 @@ extern "C" int qsb_hostcheck_run(int num_q, int prec, int low_bits, const qsb_ga
     for (int q = 0; q < 64; q++) perm_out[q] = plan.end_perm.pos[q];
     return 0;
 }
+
+
+/* ---- step-wise interface for sharded schedules (multi-rank tests) ------------------------------
+ * The caller owns one local shard per rank (2^nloc complex doubles) and performs the exchanges
+ * itself (numpy in one process, or torch.distributed/gloo across processes). */
+struct HcPlan { TiledPlan plan; int prec; int nloc; Report rep; };
+
+extern "C" void *qsb_hostcheck_plan(int num_q, int prec, int low_bits, int world, int rank, int swap_min_ops,
+                                    const qsb_gate_t *gates, size_t n)
+{
+    qsb_options_t opt; memset(&opt, 0, sizeof opt);
+    opt.precision = prec; opt.low_bits = low_bits; opt.world_size = world; opt.rank = rank; opt.reserved[0] = swap_min_ops;
+    int g = 0; while ((1 << g) < world) g++;
+    const int T = tiled_min_local_bits(prec, &opt);
+    const int nloc = std::max(num_q - g, T);
+    std::vector<COp> cops; double gph[2];
+    if (qsb_canonicalise(gates, n, num_q, cops, gph)) return nullptr;
+    BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
+    HcPlan *h = new HcPlan();
+    h->prec = prec; h->nloc = nloc; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
+    if (tiled_schedule(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan)) { delete h; return nullptr; }
+    return h;
+}
+extern "C" int qsb_hostcheck_num_steps(void *h) { return (int)((HcPlan *)h)->plan.passes.size(); }
+extern "C" int qsb_hostcheck_step_is_swap(void *h, int i) { return ((HcPlan *)h)->plan.passes[i].is_swap ? 1 : 0; }
+extern "C" int qsb_hostcheck_nloc(void *h) { return ((HcPlan *)h)->nloc; }
+extern "C" int qsb_hostcheck_run_step(void *hv, int i, double *state)
+{
+    HcPlan *h = (HcPlan *)hv;
+    const HostPass &hp = h->plan.passes[i];
+    if (hp.is_swap) return 1;
+    std::vector<cd> st((size_t)1 << h->nloc);
+    memcpy((void *)st.data(), state, sizeof(cd) * st.size());
+    run_pass(hp, h->prec == QSB_F32, h->nloc, st, h->rep);
+    memcpy(state, st.data(), sizeof(cd) * st.size());
+    return 0;
+}
+extern "C" void qsb_hostcheck_finish(void *hv, int *report5, int8_t *perm_out)
+{
+    HcPlan *h = (HcPlan *)hv;
+    report5[0] = h->rep.max_conflict; report5[1] = h->rep.bad_slots; report5[2] = h->rep.noncontig;
+    int sw = 0; for (auto &p : h->plan.passes) sw += p.is_swap;
+    report5[3] = (int)h->plan.passes.size() - sw; report5[4] = sw;
+    for (int q = 0; q < 64; q++) perm_out[q] = h->plan.end_perm.pos[q];
+    delete h;
+}

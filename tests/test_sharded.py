@@ -1,0 +1,55 @@
+"""Multi-GPU host logic on the CPU: the sharded schedule (exchange planning, in-tile qubit permutation
+passes, rank-bit predicates) interpreted by the host test double must reproduce the oracle; plus a
+world_size-2 torch.distributed/gloo run where every process holds one shard."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+import gpu_quantum_simulator_b200 as q
+from gpu_quantum_simulator_b200 import circuits
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("n,world,depth,seed", [(19, 2, 6, 1), (20, 4, 5, 2), (21, 8, 4, 3)])
+def test_sharded_schedule_reproduces_oracle(n, world, depth, seed, precision):
+    circ = circuits.random_layered(n, depth=depth, seed=seed)
+    got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, precision)
+    want = helpers.oracle_run_circuit(circ, n)
+    assert rep["swaps"] >= 1 and rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_sharded_superset_and_qft():
+    for circ, n, world in ((circuits.random_superset(19, 150, 9), 19, 4), (circuits.qft(19), 19, 2)):
+        got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, 32, swap_min_ops=4)
+        want = helpers.oracle_run_circuit(circ, n)
+        assert rep["bad_slots"] == 0
+        assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_exchange_count_on_the_34_qubit_workload():
+    circ = circuits.random_layered(34, 20, 12345)
+    g = q.gates_from_circuit(circ)
+    one = q.plan_dry_run(34, g, world_size=1)
+    for world in (2, 4, 8):
+        st = q.plan_dry_run(34, g, world_size=world)
+        assert 1 <= st["swaps"] <= 8
+        assert st["passes"] <= one["passes"] + 6
+        local = (1 << 34) // world * 8
+        assert st["bytes_exchanged"] == st["swaps"] * (local - local // world)
+
+
+def test_two_process_gloo_run(tmp_path):
+    script = os.path.join(os.path.dirname(__file__), "dist_host_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script, str(tmp_path)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "max_abs_err" in r.stdout
+    err = float(r.stdout.split("max_abs_err=")[1].split()[0])
+    assert err < 1e-12
