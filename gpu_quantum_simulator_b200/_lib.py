@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqsim_b200.so")
+LIB_PATH = os.path.join(_HERE, "libqsim_b200%s.so" % os.environ.get("QSB_LIB_SUFFIX", ""))
 
 F32, F64 = 32, 64
 MODE_TILED, MODE_SWEEP = 0, 1

@@ -34,10 +34,12 @@
 
 #include "common.cuh"
 
-#define QSB_NVB 4              /* vector bits per round                      */
+#ifndef QSB_NVB
+#define QSB_NVB 4              /* vector bits per round (build-time: 4 -> 256 threads x 16 vectors, 3 -> 512 x 8) */
+#endif
 #define QSB_NV (1 << QSB_NVB)  /* vectors per thread                         */
-#define QSB_THREADS 256
-#define QSB_TB 8               /* thread bits: log2(QSB_THREADS)             */
+#define QSB_TB (12 - QSB_NVB)  /* thread bits                                */
+#define QSB_THREADS (1 << QSB_TB)
 #define QSB_T_F32 13           /* tile bits f32: pack + NVB + TB             */
 #define QSB_T_F64 12           /* tile bits f64: NVB + TB                    */
 #define QSB_MAX_RUNS 16

@@ -153,8 +153,12 @@ __device__ __forceinline__ void unit_dispatch(int vb, typename VT<R>::V (&re)[NV
     switch (vb) {
     case 0: unit_v<R, 0, IMAG>(re, im, c); break;
     case 1: unit_v<R, 1, IMAG>(re, im, c); break;
+#if QSB_NVB > 3
     case 2: unit_v<R, 2, IMAG>(re, im, c); break;
     default: unit_v<R, 3, IMAG>(re, im, c); break;
+#else
+    default: unit_v<R, 2, IMAG>(re, im, c); break;
+#endif
     }
 }
 
@@ -164,8 +168,12 @@ __device__ __forceinline__ void mat_dispatch(int vb, typename VT<R>::V (&re)[NV]
     switch (vb) {
     case 0: mat_v<R, 0, FORM>(re, im, c); break;
     case 1: mat_v<R, 1, FORM>(re, im, c); break;
+#if QSB_NVB > 3
     case 2: mat_v<R, 2, FORM>(re, im, c); break;
     default: mat_v<R, 3, FORM>(re, im, c); break;
+#else
+    default: mat_v<R, 2, FORM>(re, im, c); break;
+#endif
     }
 }
 
@@ -254,6 +262,22 @@ template <> struct IO<double> {
 
 struct PtrTab { void *p[8]; };
 
+/* OR / XOR of the per-vector-bit constants selected by the bits of v (v is a compile-time index) */
+template <typename X> __device__ __forceinline__ X vcomb_or(int v, const X (&g)[QSB_NVB])
+{
+    X r = 0;
+#pragma unroll
+    for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) r |= g[b];
+    return r;
+}
+template <typename X> __device__ __forceinline__ X vcomb_xor(int v, const X (&g)[QSB_NVB])
+{
+    X r = 0;
+#pragma unroll
+    for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) r ^= g[b];
+    return r;
+}
+
 /* ------------------------------------------------------------------ the kernel
  * PEER: source amplitudes may live on other ranks (exchange passes): the index
  * bits above nloc select the peer buffer. */
@@ -297,19 +321,23 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const __grid_constant__
         }
 
         if (rd == 0) {
-            const uint64_t g0 = RD.vec[0].gidx, g1 = RD.vec[1].gidx, g2 = RD.vec[2].gidx, g3 = RD.vec[3].gidx;
+            uint64_t gv[QSB_NVB];
+#pragma unroll
+            for (int b = 0; b < QSB_NVB; b++) gv[b] = RD.vec[b].gidx;
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                const uint64_t gi = gthr | ((v & 1) ? g0 : 0) | ((v & 2) ? g1 : 0) | ((v & 4) ? g2 : 0) | ((v & 8) ? g3 : 0);
+                const uint64_t gi = gthr | vcomb_or(v, gv);
                 if (PEER) IO<R>::gload(src.p[gi >> nloc], gi & loc_mask, re[v], im[v]);
                 else IO<R>::gload(src.p[0], gi & loc_mask, re[v], im[v]);
             }
         } else {
             const uint32_t sl = sb & 0xffffu;
-            const uint32_t s0 = RD.vec[0].ld, s1 = RD.vec[1].ld, s2 = RD.vec[2].ld, s3 = RD.vec[3].ld;
+            uint32_t sv[QSB_NVB];
+#pragma unroll
+            for (int b = 0; b < QSB_NVB; b++) sv[b] = RD.vec[b].ld;
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                const uint32_t slot = sl ^ ((v & 1) ? s0 : 0) ^ ((v & 2) ? s1 : 0) ^ ((v & 4) ? s2 : 0) ^ ((v & 8) ? s3 : 0);
+                const uint32_t slot = sl ^ vcomb_xor(v, sv);
                 IO<R>::sload(smem, slot, re[v], im[v]);
             }
             __syncthreads(); /* every thread has its registers before anyone overwrites the tile */
@@ -343,8 +371,12 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const __grid_constant__
                 switch (vb) {
                 case 0: diag_v<R, 0>(re, im, pr, pi, npi); break;
                 case 1: diag_v<R, 1>(re, im, pr, pi, npi); break;
+#if QSB_NVB > 3
                 case 2: diag_v<R, 2>(re, im, pr, pi, npi); break;
                 default: diag_v<R, 3>(re, im, pr, pi, npi); break;
+#else
+                default: diag_v<R, 2>(re, im, pr, pi, npi); break;
+#endif
                 }
                 break;
             }
@@ -382,18 +414,22 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const __grid_constant__
             uint64_t dthr = outer | P.dst_fixed;
 #pragma unroll
             for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) dthr |= P.dst_thr[j];
-            const uint64_t g0 = P.dst_vec[0], g1 = P.dst_vec[1], g2 = P.dst_vec[2], g3 = P.dst_vec[3];
+            uint64_t gv[QSB_NVB];
+#pragma unroll
+            for (int b = 0; b < QSB_NVB; b++) gv[b] = P.dst_vec[b];
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                const uint64_t gi = dthr | ((v & 1) ? g0 : 0) | ((v & 2) ? g1 : 0) | ((v & 4) ? g2 : 0) | ((v & 8) ? g3 : 0);
+                const uint64_t gi = dthr | vcomb_or(v, gv);
                 IO<R>::gstore(dst, gi & loc_mask, re[v], im[v]);
             }
         } else {
             const uint32_t ss = sb >> 16;
-            const uint32_t s0 = RD.vec[0].st, s1 = RD.vec[1].st, s2 = RD.vec[2].st, s3 = RD.vec[3].st;
+            uint32_t sv[QSB_NVB];
+#pragma unroll
+            for (int b = 0; b < QSB_NVB; b++) sv[b] = RD.vec[b].st;
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                const uint32_t slot = ss ^ ((v & 1) ? s0 : 0) ^ ((v & 2) ? s1 : 0) ^ ((v & 4) ? s2 : 0) ^ ((v & 8) ? s3 : 0);
+                const uint32_t slot = ss ^ vcomb_xor(v, sv);
                 IO<R>::sstore(smem, slot, re[v], im[v]);
             }
             __syncthreads();

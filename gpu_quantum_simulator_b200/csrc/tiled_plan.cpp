@@ -564,7 +564,7 @@ struct PassBuilder {
                 }
             }
         }
-        const size_t total = off + stream.size();
+        const size_t total = off + stream.size() + 96;   /* slack: the kernel prefetches one op ahead */
         if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_ERR_ARG; }
         hp.hdr.blob_bytes = (uint32_t)total;
         b.assign(total <= QSB_BLOB_SMALL ? QSB_BLOB_SMALL : QSB_BLOB_LARGE, 0);
@@ -584,7 +584,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.f32 = (prec == QSB_F32);
     M.T = M.f32 ? QSB_T_F32 : QSB_T_F64;
     M.nb = M.f32 ? 4 : 3;
-    M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 6 : 5);
+    M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
     if (M.a < (M.f32 ? 3 : 2) || M.a > (M.f32 ? 6 : 5)) { qsb_set_error("low_bits %d unsupported for this precision", M.a); return QSB_ERR_ARG; }
     if (nloc < M.T) { qsb_set_error("internal: local register smaller than a tile"); return QSB_ERR_ARG; }
     if (g > 0 && nloc - g < M.a + g) { qsb_set_error("local register too small to exchange %d qubits", g); return QSB_ERR_ARG; }

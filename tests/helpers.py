@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libqsim_ref.so")
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "ref_cexe")
-HOSTCHECK_SO = os.path.join(ROOT, "tests", "hostcheck", "libqsb_hostcheck.so")
+HOSTCHECK_SO = os.path.join(ROOT, "tests", "hostcheck", "libqsb_hostcheck%s.so" % os.environ.get("QSB_LIB_SUFFIX", ""))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 REFERENCE_DIR = "/root/reference"
 

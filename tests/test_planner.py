@@ -27,7 +27,7 @@ def test_tables_reproduce_oracle_on_superset_circuits(n, ng, seed, precision):
     assert np.max(np.abs(got - want)) < 1e-12
 
 
-@pytest.mark.parametrize("precision,low_bits", [(32, 3), (32, 4), (32, 5), (64, 2), (64, 3), (64, 4)])
+@pytest.mark.parametrize("precision,low_bits", [(32, 3), (32, 5), (32, 6), (64, 2), (64, 4), (64, 5)])
 def test_low_bits_option(precision, low_bits):
     circ = circuits.random_layered(15, depth=4, seed=7)
     got, want, rep = run_both(circ, 15, precision, low_bits)
@@ -55,10 +55,10 @@ def test_fusion_factor_on_headline_workload():
     circ = circuits.random_layered(30, 20, 12345)
     st = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32)
     assert st["source_gates"] == 900
-    assert st["passes"] <= 32
+    assert st["passes"] <= 26
     assert st["bytes_moved"] == st["passes"] * 2 * (1 << 30) * 8
     st64 = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=64)
-    assert st64["passes"] <= 36
+    assert st64["passes"] <= 29
 
 
 def test_multi_control_and_global_phase_gates():
