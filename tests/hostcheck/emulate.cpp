@@ -256,3 +256,25 @@ extern "C" void qsb_hostcheck_finish(void *hv, int *report5, int8_t *perm_out)
     for (int q = 0; q < 64; q++) perm_out[q] = h->plan.end_perm.pos[q];
     delete h;
 }
+
+/* plan statistics for tuning: per pass "rounds ops | histogram of op codes" on stdout */
+extern "C" void qsb_hostcheck_describe(void *hv)
+{
+    HcPlan *h = (HcPlan *)hv;
+    static const char *nm[16] = {"?", "MAT_R", "MAT_I", "MAT_G", "MATP_R", "MATP_G", "U", "UI", "?", "DIAG_V", "DIAG_ALL", "DIAG_GEN", "TPHASE", "?", "?", "?"};
+    int tot[16] = {0}, totmux = 0, k = 0;
+    for (const HostPass &hp : h->plan.passes) {
+        if (hp.is_swap) { printf("pass %d: SWAP\n", k++); continue; }
+        int cnt[16] = {0}, mux = 0, flagged = 0;
+        for (const HostOp &o : hp.ops) { cnt[o.kind & 0xf]++; tot[o.kind & 0xf]++; if ((o.kind >> 16) & 1) { mux++; totmux++; } }
+        for (const DevRound &r : hp.rounds) flagged += r.flags & 1;
+        printf("pass %d: rounds %d flagged %d src_ops %d ops %zu mux %d |", k++, (int)hp.hdr.n_rounds, flagged, hp.n_source_ops, hp.ops.size(), mux);
+        for (int c = 0; c < 16; c++) if (cnt[c]) printf(" %s:%d", nm[c], cnt[c]);
+        printf(" | per-round ops:");
+        for (size_t r = 0; r < hp.round_op_count.size(); r++) printf(" %u", hp.round_op_count[r]);
+        printf("\n");
+    }
+    printf("total:");
+    for (int c = 0; c < 16; c++) if (tot[c]) printf(" %s:%d", nm[c], tot[c]);
+    printf(" mux:%d\n", totmux);
+}
