@@ -44,6 +44,7 @@
 #define QSB_T_F64 12           /* tile bits f64: NVB + TB                    */
 #define QSB_MAX_RUNS 16
 #define QSB_BLOB_SMALL 4000    /* pass descriptor sizes (kernel parameter)   */
+#define QSB_BLOB_MEDIUM 12000
 #define QSB_BLOB_LARGE 32000
 
 /* ---- op codes ---------------------------------------------------------- */
@@ -61,6 +62,8 @@ enum {
     OP_DIAG_ALL = 10,/* phase on all vectors (lane-dependent, e.g. rz on the pack qubit) */
     OP_DIAG_GEN = 11,/* phase on vectors with (v & vmask) == vmask, vmask in kind bits 20..23 */
     OP_TPHASE = 12,  /* thread-level phase: folded into a per-thread scalar    */
+    OP_XDEF = 13,    /* X on vector bit vb for the threads that pass: a swap of the two halves, which the
+                        kernel defers into its next store address.  Last op on its qubit in the round. */
 };
 
 /* kind = opcode | vb << 8 | mux << 16 | vmask << 20
@@ -118,6 +121,98 @@ struct DevPass {
 };
 
 template <int BYTES> struct PassBlob { uint4 q[BYTES / 16]; };
+
+/* ---- device encoding -------------------------------------------------------
+ * DevPass / DevRound / HostOp above are the LOGICAL tables (the host test double
+ * interprets them).  PassBuilder::serialise() lowers them to the compact form the
+ * kernel reads, with everything that does not depend on the thread pre-computed:
+ * byte offsets per vector for the global gather / scatter, shared-memory XOR
+ * constants per vector, and predicates as ONE 32-bit mask over the per-thread
+ * word  tw = threadIdx.x | W << 8,  where bit i of W says whether the CTA's outer
+ * index bits satisfy the i-th outer condition of the pass (GPass::cond).
+ *
+ * The ops of a round are laid out as SEGMENTS.  A segment is a (usually empty)
+ * list of SPECIAL ops, run by a generic interpreter, followed by GROUPS.  A
+ * group holds one SLOT per vector bit at a fixed position: slot j is the next
+ * op whose target is vector bit j (ops on different vector bits commute, their
+ * predicates never involve vector bits), so the common gates are dispatched
+ * with a uniform load at a static offset and a 5-way uniform branch instead of
+ * an op-stream walk.  Everything else (general complex or lane-dependent
+ * matrices, pack-bit targets, multi-vector-bit phases) is a special. */
+enum {              /* slot forms (one-hot bytes, so the kernel dispatches with bit tests); S = scalar of the state precision */
+    S_SKIP = 0,
+    S_UNIT_R = 1,   /* real unit form  a[[1,p],[q,r]]: x0 += p x1; x1 = k x1 + q x0     S: p q k a */
+    S_UNIT_I = 2,   /* rx unit form    a[[1,ip],[iq,r]]                                 S: p q k a */
+    S_FULL_R = 4,   /* real 2x2                                               S: m00 m01 m10 m11 */
+    S_DIAG = 8,     /* phase on the vectors whose bit is set                           S: pr pi   */
+    S_XDEF = 16,    /* X (swap of the two halves) under the predicate, DEFERRED: the thread only
+                       flips bit j of its vector-index mask; the swap happens for free in the
+                       address of the next shared / global store.  Last op on its bit in a round. */
+    S_FULL_I = 32,  /* [[a, ib],[ic, d]]                                               S: a b c d */
+};
+/* A group (16-byte units): [0] x = form of slot 0 | slot 1 << 8 | slot 2 << 16 | slot 3 << 24
+ *                          [1] the four predicate masks: (tw & pmask) == pmask
+ *                          then per slot two coefficient sets of 4 scalars: threads whose predicate
+ *                          fails use set 0 (the identity for a controlled gate, the control-off matrix
+ *                          for a multiplexer), the others set 1. */
+#define QSB_SET16(f32) ((f32) ? 1 : 2)             /* one 4-scalar coefficient set, 16-byte units */
+#define QSB_GROUP16(f32) (2 + QSB_NVB * 2 * QSB_SET16(f32))
+
+enum {              /* special op codes (generic interpreter); V = 8 bytes (f32: (lo, hi) lanes, f64: one double) */
+    G_FULL_G = 16,   /* +vb: complex 2x2             V: m00r m00i m01r m01i m10r m10i m11r m11i */
+    G_DIAG_V = 20,   /* +vb: phase where vector bit vb is set          V: pr pi       */
+    G_DIAG_ALL = 24, /* phase on every vector (lane dependent)         V: pr pi       */
+    G_DIAG_GEN = 25, /* phase where (v & vmask) == vmask               V: pr pi       */
+    G_MATP_R = 26,   /* pack-bit target, real (f32 only)               V: A B         */
+    G_MATP_G = 27,   /* pack-bit target, complex (f32 only)            V: Ar Ai Br Bi */
+    G_NCODES = 28
+};
+/* Special op header (16 bytes):
+ *   x = code | two << 8 | skip << 9 | vmask << 12 | size16 << 16
+ *       two : a multiplexer -- two coefficient sets follow; threads whose predicate fails use set 0
+ *             (the control-off matrix), the others set 1.  Otherwise one set: threads whose predicate
+ *             fails skip the op (a controlled gate)
+ *       skip: informational, the op has a predicate and one set
+ *   y = 8-bit mask over threadIdx.x          z, w = 64-bit mask over the outer (per-CTA) index bits
+ * predicate = (tid & y) == y && (outer & zw) == zw.  Coefficient sets are padded to 16 bytes. */
+#define GOPK(code, two, skip, vmask, size16) \
+    ((uint32_t)(code) | ((uint32_t)(two) << 8) | ((uint32_t)(skip) << 9) | ((uint32_t)(vmask) << 12) | ((uint32_t)(size16) << 16))
+
+struct GTPhase {               /* thread-level phase, applied through the pending scalar (32 bytes) */
+    uint32_t tmask, pad;
+    uint64_t omask;
+    uint8_t val[16];           /* (pr, pi) in the state precision */
+};
+
+struct GSegment {              /* 16 bytes */
+    uint32_t n_special, special_off16;
+    uint32_t n_groups, group_off16;
+};
+
+#define QSB_MAX_COND 24        /* distinct outer conditions a pass can name through W */
+
+struct GRound {
+    uint32_t n_seg, seg_off16; /* GSegment array, 16-byte units from the blob start                  */
+    uint32_t n_tph, tph_off16; /* GTPhase array                                                      */
+    uint32_t flags, pad[3];    /* bit0: apply the pending scalar at the end of the round             */
+    uint32_t thr_x[QSB_TB];    /* smem byte XOR per thread bit: load side | store side << 16         */
+    uint32_t vld_x[QSB_NV];    /* smem byte XOR per vector, load side                                */
+    uint32_t vst_x[QSB_NV];    /*                            store side                              */
+};
+
+struct GPass {
+    uint32_t n_rounds, n_runs;
+    uint8_t run_start[QSB_MAX_RUNS], run_len[QSB_MAX_RUNS];
+    uint64_t src_fixed;        /* constant source index bits (rank bits): predicates see them         */
+    uint64_t n_tiles;
+    uint32_t nloc, rounds_off16;
+    uint32_t n_cond, pad;
+    uint64_t cond[QSB_MAX_COND]; /* outer conditions: W bit i = (outer & cond[i]) == cond[i]          */
+    uint64_t ld_thr[QSB_TB];   /* local BYTE offset of thread bit j, round-0 gather                   */
+    uint64_t st_thr[QSB_TB];   /*                                    last-round scatter               */
+    uint64_t ld_vec[QSB_NV];   /* local BYTE offset of vector v                                       */
+    uint64_t st_vec[QSB_NV];
+};
 
 /* ---- host-side plan ----------------------------------------------------- */
 struct HostOp {              /* precision-independent; lane-expanded fp64 coefficients */

@@ -18,7 +18,7 @@
 #include "sim.h"
 #include "tiled.h"
 
-int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, void *const *src_ptrs, void *dst, bool peer);
+int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst);
 
 int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
                      const std::vector<COp> &cops, const double gphase[2], bool /*with_device*/,
@@ -146,9 +146,7 @@ int tiled_execute(qsb_sim *s, TiledPlan *p)
             ev.push_back(a); ev.push_back(b);
             continue;
         }
-        void *src[8];
-        for (int i = 0; i < 8; i++) src[i] = s->state;
-        int rc = tiled_launch_pass(s, p, k, src, s->state, false);
+        int rc = tiled_launch_pass(s, p, k, s->state, s->state);
         if (rc) return rc;
     }
     s->perm = p->end_perm;

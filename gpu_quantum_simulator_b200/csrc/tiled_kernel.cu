@@ -2,18 +2,24 @@
  * tiled_kernel.cu -- the sm_100a apply kernel: one launch = one PASS (one
  * read + one write of the local state), any number of gates.
  *
- * See tiled.h for the schedule this kernel interprets.  Per CTA:
- *   1. 16 x 128-bit coalesced loads per thread pull the tile (64 KiB) straight
- *      from HBM into registers (f32: {re,re',im,im'} units -> two float2
- *      vectors that feed FFMA2/FMUL2 directly; f64: one (re,im) double2).
- *   2. per round: butterflies on register-resident vector bits, per-thread
- *      predicates for controls / diagonal phases, then a conflict-free
- *      exchange through shared memory (planner-chosen GF(2)-linear slot map).
- *   3. 16 x 128-bit coalesced stores per thread.
- * The pass descriptor (tables + op stream) is a __grid_constant__ parameter:
- * all table / coefficient reads are constant-bank loads.
- * The kernel is HBM-bound by design: algorithmic traffic per launch is
- * 2 * N_loc * sizeof(amplitude), independent of how many gates the pass fuses.
+ * See tiled.h for the schedule this kernel interprets.  Per CTA (256 threads,
+ * two CTAs per SM):
+ *   1. gather: 16 x 128-bit loads per thread pull the 64 KiB tile straight from
+ *      HBM into registers; a warp instruction covers 128-byte contiguous segments
+ *      (f32: one load = {re,re',im,im'} of an amplitude pair = two packed
+ *      operands for FFMA2/FMUL2; f64: one (re,im) double2).
+ *   2. per round: an interpreter applies the fused gates whose target is one of
+ *      the 4 register-resident vector bits (or the pack bit); controls and
+ *      diagonal phases are per-thread predicates.  Between rounds the tile is
+ *      transposed through shared memory in 16-byte slots with a planner-chosen
+ *      GF(2)-linear, bank-conflict-free slot map.
+ *   3. scatter: 16 x 128-bit stores per thread.
+ * Everything that does not depend on the thread is pre-computed by the planner
+ * (byte offsets per vector, smem XOR constants, predicate masks) and travels
+ * with the op stream as ONE __grid_constant__ kernel parameter: all table and
+ * coefficient reads are uniform constant-bank loads, the only global traffic is
+ * the state itself.  Algorithmic traffic per launch is 2 * N_loc *
+ * sizeof(amplitude), independent of how many gates the pass fuses.
  *
  * Reference kernels replaced: kernel_gate / kernel_gate_2 (naive.cu:72-95),
  * kernel_cnot (naive.cu:97-122), kernel_gate_4 (4x4.cu:109-146).
@@ -23,8 +29,7 @@
 
 /* ------------------------------------------------------------ vector algebra
  * All updates are written as IN-PLACE inline PTX (read-write operands) so the
- * tile keeps the same registers through every op body: without this the
- * compiler materialises a 64-register shuffle at each switch join.
+ * tile keeps the same registers through every op body of the interpreter.
  *   f32: V = b64 register holding (lo lane, hi lane) -> mul.f32x2 / fma.rn.f32x2
  *   f64: V = double                                   -> mul.f64   / fma.rn.f64  */
 template <typename R> struct VT;
@@ -40,13 +45,21 @@ template <> struct VT<float> {
      * hoisting the in-place update above those reads, which would cost a register copy */
     static __device__ __forceinline__ void updd(V &x, V a, V t, V d1) { asm("fma.rn.f32x2 %0, %1, %0, %2; // %3" : "+l"(x) : "l"(a), "l"(t), "l"(d1)); }
     static __device__ __forceinline__ void updd(V &x, V a, V t, V d1, V d2, V d3) { asm("fma.rn.f32x2 %0, %1, %0, %2; // %3 %4 %5" : "+l"(x) : "l"(a), "l"(t), "l"(d1), "l"(d2), "l"(d3)); }
-    static __device__ __forceinline__ V neg(V a) { return a ^ 0x8000000080000000ULL; }
+    /* negated products: ptxas folds the neg into the operand modifier of FMUL2 / FFMA2 (no extra register) */
+    static __device__ __forceinline__ V nmul(V a, V b) { V d; asm("{ .reg .b64 t; .reg .f32 lo, hi; mov.b64 {lo, hi}, %1; neg.f32 lo, lo; neg.f32 hi, hi; mov.b64 t, {lo, hi}; mul.rn.f32x2 %0, t, %2; }" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    static __device__ __forceinline__ void nacc(V &acc_, V a, V b) { asm("{ .reg .b64 t; .reg .f32 lo, hi; mov.b64 {lo, hi}, %1; neg.f32 lo, lo; neg.f32 hi, hi; mov.b64 t, {lo, hi}; fma.rn.f32x2 %0, t, %2, %0; }" : "+l"(acc_) : "l"(a), "l"(b)); }
     static __device__ __forceinline__ V bc(float s) { unsigned u = __float_as_uint(s); return ((V)u << 32) | u; }
     static __device__ __forceinline__ V swp(V a) { return (a >> 32) | (a << 32); }
-    static __device__ __forceinline__ V coef(const uint2 *c, int k) { return reinterpret_cast<const V *>(c)[k]; }
-    static __device__ __forceinline__ void coef2(const uint2 *c, int k, V &x, V &y) { const ulonglong2 u = reinterpret_cast<const ulonglong2 *>(c)[k >> 1]; x = u.x; y = u.y; }
-    static __device__ __forceinline__ void tphase(const uint2 *c, float &pr, float &pi) { uint2 u = c[0]; pr = __uint_as_float(u.x); pi = __uint_as_float(u.y); }
-    static __device__ __forceinline__ float scalar(const uint2 *c, int k) { return __uint_as_float(c[k].x); }
+    static __device__ __forceinline__ V as_v(uint2 u) { return ((V)u.y << 32) | u.x; }
+    /* scalar k of a coefficient set (16-byte units starting at c) */
+    static __device__ __forceinline__ void scalars4(const uint4 *c, S &a, S &b, S &cc, S &d)
+    {
+        const uint4 u = c[0];
+        a = __uint_as_float(u.x); b = __uint_as_float(u.y); cc = __uint_as_float(u.z); d = __uint_as_float(u.w);
+    }
+    static __device__ __forceinline__ void vec2(const uint4 *c, int k, V &x, V &y) { const uint4 u = c[k]; x = ((V)u.y << 32) | u.x; y = ((V)u.w << 32) | u.z; }
+    static __device__ __forceinline__ void tph(const uint4 u, S &pr, S &pi) { pr = __uint_as_float(u.x); pi = __uint_as_float(u.y); }
+    enum { SET4 = 1 };   /* 16-byte units per 4-scalar coefficient set */
 };
 template <> struct VT<double> {
     typedef double V;
@@ -56,79 +69,41 @@ template <> struct VT<double> {
     static __device__ __forceinline__ void upd(V &x, V a, V t) { asm("fma.rn.f64 %0, %1, %0, %2;" : "+d"(x) : "d"(a), "d"(t)); }
     static __device__ __forceinline__ void updd(V &x, V a, V t, V d1) { asm("fma.rn.f64 %0, %1, %0, %2; // %3" : "+d"(x) : "d"(a), "d"(t), "d"(d1)); }
     static __device__ __forceinline__ void updd(V &x, V a, V t, V d1, V d2, V d3) { asm("fma.rn.f64 %0, %1, %0, %2; // %3 %4 %5" : "+d"(x) : "d"(a), "d"(t), "d"(d1), "d"(d2), "d"(d3)); }
-    static __device__ __forceinline__ V neg(V a) { return -a; }
+    static __device__ __forceinline__ V nmul(V a, V b) { V d; asm("{ .reg .f64 t; neg.f64 t, %1; mul.rn.f64 %0, t, %2; }" : "=d"(d) : "d"(a), "d"(b)); return d; }
+    static __device__ __forceinline__ void nacc(V &acc_, V a, V b) { asm("{ .reg .f64 t; neg.f64 t, %1; fma.rn.f64 %0, t, %2, %0; }" : "+d"(acc_) : "d"(a), "d"(b)); }
     static __device__ __forceinline__ V bc(double s) { return s; }
     static __device__ __forceinline__ V swp(V a) { return a; }
-    static __device__ __forceinline__ V coef(const uint2 *c, int k) { return reinterpret_cast<const double *>(c)[k]; }
-    static __device__ __forceinline__ void coef2(const uint2 *c, int k, V &x, V &y) { const double2 u = reinterpret_cast<const double2 *>(c)[k >> 1]; x = u.x; y = u.y; }
-    static __device__ __forceinline__ void tphase(const uint2 *c, double &pr, double &pi) { pr = coef(c, 0); pi = coef(c, 1); }
-    static __device__ __forceinline__ double scalar(const uint2 *c, int k) { return coef(c, k); }
+    static __device__ __forceinline__ double lohi(unsigned lo, unsigned hi) { return __hiloint2double((int)hi, (int)lo); }
+    static __device__ __forceinline__ void scalars4(const uint4 *c, S &a, S &b, S &cc, S &d)
+    {
+        const uint4 u = c[0], w = c[1];
+        a = lohi(u.x, u.y); b = lohi(u.z, u.w); cc = lohi(w.x, w.y); d = lohi(w.z, w.w);
+    }
+    static __device__ __forceinline__ void vec2(const uint4 *c, int k, V &x, V &y) { const uint4 u = c[k]; x = lohi(u.x, u.y); y = lohi(u.z, u.w); }
+    static __device__ __forceinline__ void tph(const uint4 u, S &pr, S &pi) { pr = lohi(u.x, u.y); pi = lohi(u.z, u.w); }
+    enum { SET4 = 2 };
 };
 
 #define NV QSB_NV
 
-/* (xr, xi) *= (pr, pi);  npi = -pi */
+/* (xr, xi) *= (pr, pi) */
 template <typename R>
-__device__ __forceinline__ void cmul_inplace(typename VT<R>::V &xr, typename VT<R>::V &xi, typename VT<R>::V pr, typename VT<R>::V pi, typename VT<R>::V npi)
+__device__ __forceinline__ void cmul_inplace(typename VT<R>::V &xr, typename VT<R>::V &xi, typename VT<R>::V pr, typename VT<R>::V pi)
 {
     typedef VT<R> T;
-    const typename T::V t0 = T::mul(npi, xi), t1 = T::mul(pi, xr);
+    const typename T::V t0 = T::nmul(pi, xi), t1 = T::mul(pi, xr);
     T::updd(xr, pr, t0, t1);
     T::updd(xi, pr, t1, t0);
 }
 
-/* 2x2 on a vector bit.  FORM: 1 real, 2 real-diag/imag-offdiag, 3 general.
- * Cross terms go to temporaries first, then each amplitude is updated in place. */
-template <typename R, int VB, int FORM>
-__device__ __forceinline__ void mat_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
-{
-    typedef VT<R> T; typedef typename T::V V;
-    if (FORM == 1) {
-        V a, b, cc, d;                       /* payload order: m01 m10 | m00 m11 (cross terms first) */
-        T::coef2(c, 0, b, cc); T::coef2(c, 2, a, d);
-#pragma unroll
-        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
-            const int w = v | (1 << VB);
-            const V t0 = T::mul(b, re[w]), t1 = T::mul(b, im[w]), t2 = T::mul(cc, re[v]), t3 = T::mul(cc, im[v]);
-            T::updd(re[v], a, t0, t2); T::updd(im[v], a, t1, t3);
-            T::updd(re[w], d, t2, t0); T::updd(im[w], d, t3, t1);
-        }
-    } else if (FORM == 2) {
-        /* [[a, i b],[i c, d]] (host pre-negates) */
-        V a, nb, b, nc, cc, d;               /* payload order: -b b | -c c | a d */
-        T::coef2(c, 0, nb, b); T::coef2(c, 2, nc, cc); T::coef2(c, 4, a, d);
-#pragma unroll
-        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
-            const int w = v | (1 << VB);
-            const V t0 = T::mul(nb, im[w]), t1 = T::mul(b, re[w]), t2 = T::mul(nc, im[v]), t3 = T::mul(cc, re[v]);
-            T::updd(re[v], a, t0, t3); T::updd(im[v], a, t1, t2);
-            T::updd(re[w], d, t2, t1); T::updd(im[w], d, t3, t0);
-        }
-    } else {
-        V ar, ai, br, bi, cr, ci, dr, di;    /* payload order: m00i m01r | m01i m10r | m10i m11i | m00r m11r */
-        T::coef2(c, 0, ai, br); T::coef2(c, 2, bi, cr); T::coef2(c, 4, ci, di); T::coef2(c, 6, ar, dr);
-        const V nai = T::neg(ai), nbi = T::neg(bi), nci = T::neg(ci), ndi = T::neg(di);
-#pragma unroll
-        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
-            const int w = v | (1 << VB);
-            V t0 = T::mul(nai, im[v]); T::acc(t0, br, re[w]); T::acc(t0, nbi, im[w]);   /* re[v] minus its own-term */
-            V t1 = T::mul(ai, re[v]);  T::acc(t1, br, im[w]); T::acc(t1, bi, re[w]);    /* im[v] */
-            V t2 = T::mul(cr, re[v]);  T::acc(t2, nci, im[v]); T::acc(t2, ndi, im[w]);  /* re[w] */
-            V t3 = T::mul(cr, im[v]);  T::acc(t3, ci, re[v]); T::acc(t3, di, re[w]);    /* im[w] */
-            T::updd(re[v], ar, t0, t1, t2, t3); T::updd(im[v], ar, t1, t0, t2, t3);
-            T::updd(re[w], dr, t2, t0, t1, t3); T::updd(im[w], dr, t3, t0, t1, t2);
-        }
-    }
-}
-
-/* unit form on a vector bit (see tiled.h): strictly in-place dependency chains.
+/* unit form on vector bit VB: strictly in-place dependency chains.
  *   real: x0 += p*x1 ; x1 = k*x1 + q*x0        rx form: x0 += i p x1 ; x1 = k*x1 + i q x0 */
 template <typename R, int VB, bool IMAG>
-__device__ __forceinline__ void unit_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
+__device__ __forceinline__ void unit_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::S ps, typename VT<R>::S qs, typename VT<R>::S ks)
 {
     typedef VT<R> T; typedef typename T::V V;
+    const V p = T::bc(ps), q = T::bc(qs), k = T::bc(ks);
     if (!IMAG) {
-        V p, q, k, a_; T::coef2(c, 0, p, q); T::coef2(c, 2, k, a_);
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
             const int w = v | (1 << VB);
@@ -137,162 +112,168 @@ __device__ __forceinline__ void unit_v(typename VT<R>::V (&re)[NV], typename VT<
             T::upd(re[w], k, t); T::upd(im[w], k, u);
         }
     } else {
-        V p, np, q, nq, k, a_; T::coef2(c, 0, p, np); T::coef2(c, 2, q, nq); T::coef2(c, 4, k, a_);
 #pragma unroll
         for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
             const int w = v | (1 << VB);
-            T::acc(re[v], np, im[w]); T::acc(im[v], p, re[w]);
-            const V t = T::mul(nq, im[v]), u = T::mul(q, re[v]);
+            T::nacc(re[v], p, im[w]); T::acc(im[v], p, re[w]);
+            const V t = T::nmul(q, im[v]), u = T::mul(q, re[v]);
             T::upd(re[w], k, t); T::upd(im[w], k, u);
         }
     }
 }
-template <typename R, bool IMAG>
-__device__ __forceinline__ void unit_dispatch(int vb, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
+
+/* full 2x2 on vector bit VB.  FORM 1: real [[a,b],[c,d]]; 2: [[a, ib],[ic, d]].
+ * Cross terms go to temporaries first, then each amplitude is updated in place. */
+template <typename R, int VB, int FORM>
+__device__ __forceinline__ void full_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::S as, typename VT<R>::S bs, typename VT<R>::S cs, typename VT<R>::S ds)
 {
-    switch (vb) {
-    case 0: unit_v<R, 0, IMAG>(re, im, c); break;
-    case 1: unit_v<R, 1, IMAG>(re, im, c); break;
-#if QSB_NVB > 3
-    case 2: unit_v<R, 2, IMAG>(re, im, c); break;
-    default: unit_v<R, 3, IMAG>(re, im, c); break;
-#else
-    default: unit_v<R, 2, IMAG>(re, im, c); break;
-#endif
+    typedef VT<R> T; typedef typename T::V V;
+    const V a = T::bc(as), b = T::bc(bs), cc = T::bc(cs), d = T::bc(ds);
+    if (FORM == 1) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
+            const int w = v | (1 << VB);
+            const V t0 = T::mul(b, re[w]), t1 = T::mul(b, im[w]), t2 = T::mul(cc, re[v]), t3 = T::mul(cc, im[v]);
+            T::updd(re[v], a, t0, t2); T::updd(im[v], a, t1, t3);
+            T::updd(re[w], d, t2, t0); T::updd(im[w], d, t3, t1);
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
+            const int w = v | (1 << VB);
+            const V t0 = T::nmul(b, im[w]), t1 = T::mul(b, re[w]), t2 = T::nmul(cc, im[v]), t3 = T::mul(cc, re[v]);
+            T::updd(re[v], a, t0, t3); T::updd(im[v], a, t1, t2);
+            T::updd(re[w], d, t2, t1); T::updd(im[w], d, t3, t0);
+        }
     }
 }
 
-template <typename R, int FORM>
-__device__ __forceinline__ void mat_dispatch(int vb, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const uint2 *c)
+/* complex 2x2 on vector bit VB; coefficients are V-typed (lane pairs in f32) */
+template <typename R, int VB>
+__device__ __forceinline__ void gen_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const typename VT<R>::V (&m)[8])
 {
-    switch (vb) {
-    case 0: mat_v<R, 0, FORM>(re, im, c); break;
-    case 1: mat_v<R, 1, FORM>(re, im, c); break;
-#if QSB_NVB > 3
-    case 2: mat_v<R, 2, FORM>(re, im, c); break;
-    default: mat_v<R, 3, FORM>(re, im, c); break;
-#else
-    default: mat_v<R, 2, FORM>(re, im, c); break;
-#endif
+    typedef VT<R> T; typedef typename T::V V;
+    const V ar = m[0], ai = m[1], br = m[2], bi = m[3], cr = m[4], ci = m[5], dr = m[6], di = m[7];
+#pragma unroll
+    for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
+        const int w = v | (1 << VB);
+        V t0 = T::nmul(ai, im[v]); T::acc(t0, br, re[w]); T::nacc(t0, bi, im[w]);   /* re[v] minus its own-term */
+        V t1 = T::mul(ai, re[v]);  T::acc(t1, br, im[w]); T::acc(t1, bi, re[w]);    /* im[v] */
+        V t2 = T::mul(cr, re[v]);  T::nacc(t2, ci, im[v]); T::nacc(t2, di, im[w]);  /* re[w] */
+        V t3 = T::mul(cr, im[v]);  T::acc(t3, ci, re[v]); T::acc(t3, di, re[w]);    /* im[w] */
+        T::updd(re[v], ar, t0, t1, t2, t3); T::updd(im[v], ar, t1, t0, t2, t3);
+        T::updd(re[w], dr, t2, t0, t1, t3); T::updd(im[w], dr, t3, t0, t1, t2);
     }
 }
 
 /* phase on the vectors whose bit VB is set */
 template <typename R, int VB>
-__device__ __forceinline__ void diag_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::V pr, typename VT<R>::V pi, typename VT<R>::V npi)
+__device__ __forceinline__ void diag_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::V pr, typename VT<R>::V pi)
 {
 #pragma unroll
-    for (int v = 0; v < NV; v++) if ((v >> VB) & 1) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
+    for (int v = 0; v < NV; v++) if ((v >> VB) & 1) cmul_inplace<R>(re[v], im[v], pr, pi);
+}
+/* (pr, pi) of a diagonal op: set 0, or set 1 for the threads that pass (uniform loads + select) */
+template <typename R>
+__device__ __forceinline__ void load_phase(const uint4 *c, bool two, bool s1, typename VT<R>::V &pr, typename VT<R>::V &pi)
+{
+    typedef VT<R> T;
+    T::vec2(c, 0, pr, pi);
+    if (two) { typename T::V pr1, pi1; T::vec2(c, 1, pr1, pi1); if (s1) { pr = pr1; pi = pi1; } }
 }
 
 /* 2x2 on the pack bit (f32 only): out = A * x + B * swap(x), A = (m00, m11), B = (m01, m10) */
-template <int FORM>
-__device__ __forceinline__ void mat_p(unsigned long long (&re)[NV], unsigned long long (&im)[NV], const uint2 *c)
+__device__ __forceinline__ void matp_r(unsigned long long (&re)[NV], unsigned long long (&im)[NV], unsigned long long A, unsigned long long B)
 {
     typedef VT<float> T; typedef T::V V;
-    if (FORM == 1) {
-        const V A = T::coef(c, 0), B = T::coef(c, 1);
 #pragma unroll
-        for (int v = 0; v < NV; v++) {
-            const V t0 = T::mul(B, T::swp(re[v])), t1 = T::mul(B, T::swp(im[v]));
-            T::upd(re[v], A, t0); T::upd(im[v], A, t1);
-        }
-    } else {
-        const V Ar = T::coef(c, 0), Ai = T::coef(c, 1), Br = T::coef(c, 2), Bi = T::coef(c, 3);
-        const V nAi = T::neg(Ai), nBi = T::neg(Bi);
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-            const V sr = T::swp(re[v]), si = T::swp(im[v]);
-            V t0 = T::mul(nAi, im[v]); T::acc(t0, Br, sr); T::acc(t0, nBi, si);
-            V t1 = T::mul(Ai, re[v]);  T::acc(t1, Br, si); T::acc(t1, Bi, sr);
-            T::updd(re[v], Ar, t0, t1); T::updd(im[v], Ar, t1, t0);
-        }
+    for (int v = 0; v < NV; v++) {
+        const V t0 = T::mul(B, T::swp(re[v])), t1 = T::mul(B, T::swp(im[v]));
+        T::upd(re[v], A, t0); T::upd(im[v], A, t1);
     }
 }
-template <int FORM>
-__device__ __forceinline__ void mat_p(double (&)[NV], double (&)[NV], const uint2 *) {}
+__device__ __forceinline__ void matp_g(unsigned long long (&re)[NV], unsigned long long (&im)[NV], unsigned long long Ar, unsigned long long Ai, unsigned long long Br, unsigned long long Bi)
+{
+    typedef VT<float> T; typedef T::V V;
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const V sr = T::swp(re[v]), si = T::swp(im[v]);
+        V t0 = T::nmul(Ai, im[v]); T::acc(t0, Br, sr); T::nacc(t0, Bi, si);
+        V t1 = T::mul(Ai, re[v]);  T::acc(t1, Br, si); T::acc(t1, Bi, sr);
+        T::updd(re[v], Ar, t0, t1); T::updd(im[v], Ar, t1, t0);
+    }
+}
+__device__ __forceinline__ void matp_r(double (&)[NV], double (&)[NV], double, double) {}
+__device__ __forceinline__ void matp_g(double (&)[NV], double (&)[NV], double, double, double, double) {}
 
-/* ---------------------------------------------------------- global / shared IO */
+/* ---------------------------------------------------------- global / shared IO
+ * One 16-byte unit per vector in both precisions: f32 {re0, re1, im0, im1} (an
+ * amplitude pair), f64 {re, im}. */
 template <typename R> struct IO;
 template <> struct IO<float> {
     typedef unsigned long long V;
-    /* amplitude pair unit: {re0, re1, im0, im1} at 16 * (index >> 1) */
-    static __device__ __forceinline__ void gload(const void *base, uint64_t idx, V &re, V &im)
-    {
-        const ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(base) + (idx >> 1));
-        re = x.x; im = x.y;
-    }
-    static __device__ __forceinline__ void gstore(void *base, uint64_t idx, V re, V im)
-    {
-        __stcs(reinterpret_cast<ulonglong2 *>(base) + (idx >> 1), make_ulonglong2(re, im));
-    }
-    /* two 32 KiB planes of 8-byte slots */
-    static __device__ __forceinline__ void sload(const uint8_t *sm, uint32_t slot, V &re, V &im)
-    {
-        re = *reinterpret_cast<const V *>(sm + slot * 8u);
-        im = *reinterpret_cast<const V *>(sm + 32768u + slot * 8u);
-    }
-    static __device__ __forceinline__ void sstore(uint8_t *sm, uint32_t slot, V re, V im)
-    {
-        *reinterpret_cast<V *>(sm + slot * 8u) = re;
-        *reinterpret_cast<V *>(sm + 32768u + slot * 8u) = im;
-    }
+    static __device__ __forceinline__ void gload(const char *p, V &re, V &im) { const ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(p)); re = x.x; im = x.y; }
+    static __device__ __forceinline__ void gstore(char *p, V re, V im) { __stcs(reinterpret_cast<ulonglong2 *>(p), make_ulonglong2(re, im)); }
+    static __device__ __forceinline__ void sload(const uint8_t *sm, uint32_t off, V &re, V &im) { const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(sm + off); re = x.x; im = x.y; }
+    static __device__ __forceinline__ void sstore(uint8_t *sm, uint32_t off, V re, V im) { *reinterpret_cast<ulonglong2 *>(sm + off) = make_ulonglong2(re, im); }
 };
 template <> struct IO<double> {
     typedef double V;
-    static __device__ __forceinline__ void gload(const void *base, uint64_t idx, V &re, V &im)
-    {
-        const double2 x = __ldcs(reinterpret_cast<const double2 *>(base) + idx);
-        re = x.x; im = x.y;
-    }
-    static __device__ __forceinline__ void gstore(void *base, uint64_t idx, V re, V im)
-    {
-        __stcs(reinterpret_cast<double2 *>(base) + idx, make_double2(re, im));
-    }
-    static __device__ __forceinline__ void sload(const uint8_t *sm, uint32_t slot, V &re, V &im)
-    {
-        const double2 x = *reinterpret_cast<const double2 *>(sm + slot * 16u);
-        re = x.x; im = x.y;
-    }
-    static __device__ __forceinline__ void sstore(uint8_t *sm, uint32_t slot, V re, V im)
-    {
-        *reinterpret_cast<double2 *>(sm + slot * 16u) = make_double2(re, im);
-    }
+    static __device__ __forceinline__ void gload(const char *p, V &re, V &im) { const double2 x = __ldcs(reinterpret_cast<const double2 *>(p)); re = x.x; im = x.y; }
+    static __device__ __forceinline__ void gstore(char *p, V re, V im) { __stcs(reinterpret_cast<double2 *>(p), make_double2(re, im)); }
+    static __device__ __forceinline__ void sload(const uint8_t *sm, uint32_t off, V &re, V &im) { const double2 x = *reinterpret_cast<const double2 *>(sm + off); re = x.x; im = x.y; }
+    static __device__ __forceinline__ void sstore(uint8_t *sm, uint32_t off, V re, V im) { *reinterpret_cast<double2 *>(sm + off) = make_double2(re, im); }
 };
 
-struct PtrTab { void *p[8]; };
+/* ------------------------------------------------------------------ the kernel */
+#define CASE4(base, ...)                              \
+    case (base) + 0: { enum { VB = 0 }; __VA_ARGS__ } break; \
+    case (base) + 1: { enum { VB = 1 }; __VA_ARGS__ } break; \
+    case (base) + 2: { enum { VB = 2 }; __VA_ARGS__ } break; \
+    case (base) + 3: { enum { VB = 3 }; __VA_ARGS__ } break;
 
-/* OR / XOR of the per-vector-bit constants selected by the bits of v (v is a compile-time index) */
-template <typename X> __device__ __forceinline__ X vcomb_or(int v, const X (&g)[QSB_NVB])
+/* One slot of a group = the op on vector bit VB: a one-hot form byte, a predicate mask and two
+ * 4-scalar coefficient sets.  Slots are software-pipelined: the coefficient loads of the next
+ * non-empty slot are issued before the current slot's packed FMAs, the header of the next group
+ * before the current group.  No per-thread branches: threads whose predicate fails use coefficient
+ * set 0 (the identity for a controlled gate, the control-off matrix for a multiplexer). */
+template <typename R> struct SlotC { typename VT<R>::S c[4], d[4]; };
+template <typename R>
+__device__ __forceinline__ void slot_fetch(const uint4 *cp, SlotC<R> &s)
 {
-    X r = 0;
-#pragma unroll
-    for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) r |= g[b];
-    return r;
+    typedef VT<R> T;
+    T::scalars4(cp, s.c[0], s.c[1], s.c[2], s.c[3]);
+    T::scalars4(cp + T::SET4, s.d[0], s.d[1], s.d[2], s.d[3]);
 }
-template <typename X> __device__ __forceinline__ X vcomb_xor(int v, const X (&g)[QSB_NVB])
+template <typename R, int VB>
+__device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const SlotC<R> &s, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV],
+                                          uint32_t tw, typename VT<R>::S &psr, typename VT<R>::S &psi, uint32_t &xm)
 {
-    X r = 0;
-#pragma unroll
-    for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) r ^= g[b];
-    return r;
+    typedef VT<R> T; typedef typename T::S S;
+    const bool pred = (tw & pmask) == pmask;
+    const S c0 = pred ? s.d[0] : s.c[0], c1 = pred ? s.d[1] : s.c[1], c2 = pred ? s.d[2] : s.c[2], c3 = pred ? s.d[3] : s.c[3];
+    if (form & S_UNIT_R) { unit_v<R, VB, false>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
+    else if (form & S_UNIT_I) { unit_v<R, VB, true>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
+    else if (form & S_FULL_R) full_v<R, VB, 1>(re, im, c0, c1, c2, c3);
+    else if (form & S_DIAG) diag_v<R, VB>(re, im, T::bc(c0), T::bc(c1));
+    else if (form & S_FULL_I) full_v<R, VB, 2>(re, im, c0, c1, c2, c3);
+    else xm ^= pred ? (1u << VB) : 0u;   /* S_XDEF */
 }
 
-/* ------------------------------------------------------------------ the kernel
- * PEER: source amplitudes may live on other ranks (exchange passes): the index
- * bits above nloc select the peer buffer. */
-template <typename R, int BLOB, bool PEER>
+template <typename R, int BLOB>
 __global__ void __launch_bounds__(QSB_THREADS, 2)
-k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const __grid_constant__ PtrTab src, void *dst)
+k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst)
 {
-    typedef VT<R> T; typedef typename T::V V;
+    typedef VT<R> T; typedef typename T::V V; typedef typename T::S S;
+    static_assert(QSB_NVB == 4, "the interpreter is written for 4 vector bits");
     extern __shared__ __align__(16) uint8_t smem[];
     const uint4 *B = blob.q;
-    const DevPass &P = *reinterpret_cast<const DevPass *>(B);
-    const DevRound *rounds = reinterpret_cast<const DevRound *>(B + P.rounds_off16);
+    const GPass &P = *reinterpret_cast<const GPass *>(B);
+    const GRound *rounds = reinterpret_cast<const GRound *>(B + P.rounds_off16);
     const uint32_t tid = threadIdx.x;
+    const uint64_t AMP = sizeof(R) * 2;
 
-    /* tile id -> outer index bits */
+    /* tile id -> outer index bits (uniform) */
     uint64_t tile = blockIdx.x, outer = 0;
     {
         const int nr = (int)P.n_runs;
@@ -302,169 +283,197 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const __grid_constant__
             tile >>= len;
         }
     }
-    const uint64_t src_outer = outer | P.src_fixed;
-    const uint32_t nloc = P.nloc;
-    const uint64_t loc_mask = (1ULL << nloc) - 1;
+    const uint64_t src_outer = outer | P.src_fixed;   /* what the outer predicates test */
+    /* per-thread predicate word: tid in bits 0..7, the CTA's outer-condition bits above */
+    uint32_t tw = tid;
+    {
+        const int nc = (int)P.n_cond;
+        for (int i = 0; i < nc; i++) { const uint64_t m = P.cond[i]; if ((src_outer & m) == m) tw |= 256u << i; }
+    }
     const int n_rounds = (int)P.n_rounds;
 
     V re[NV], im[NV];
 
-    for (int rd = 0; rd < n_rounds; rd++) {
-        const DevRound &RD = rounds[rd];
-        /* this thread's physical index bits (vector bits zero) and smem slot bases */
-        uint64_t gthr = src_outer;
-        uint32_t sb = 0; /* ld in the low half, st in the high half */
+    /* ---- gather ---- */
+    {
+        uint64_t off = outer * AMP;
 #pragma unroll
-        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) {
-            gthr |= RD.thr[j].gidx;
-            sb ^= (uint32_t)RD.thr[j].ld | ((uint32_t)RD.thr[j].st << 16);
-        }
+        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) off += P.ld_thr[j];
+        const char *p = src + off;
+#pragma unroll
+        for (int v = 0; v < NV; v++) IO<R>::gload(p + P.ld_vec[v], re[v], im[v]);
+    }
 
-        if (rd == 0) {
-            uint64_t gv[QSB_NVB];
+    uint32_t xm = 0;   /* deferred X: this thread's register v holds logical vector v ^ xm */
+    for (int rd = 0; rd < n_rounds; rd++) {
+        const GRound &RD = rounds[rd];
+        uint32_t sb = 0; /* this thread's smem byte offset: load side in the low half, store side in the high half */
 #pragma unroll
-            for (int b = 0; b < QSB_NVB; b++) gv[b] = RD.vec[b].gidx;
-#pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const uint64_t gi = gthr | vcomb_or(v, gv);
-                if (PEER) IO<R>::gload(src.p[gi >> nloc], gi & loc_mask, re[v], im[v]);
-                else IO<R>::gload(src.p[0], gi & loc_mask, re[v], im[v]);
-            }
-        } else {
+        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr_x[j];
+
+        if (rd > 0) {
             const uint32_t sl = sb & 0xffffu;
-            uint32_t sv[QSB_NVB];
 #pragma unroll
-            for (int b = 0; b < QSB_NVB; b++) sv[b] = RD.vec[b].ld;
-#pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const uint32_t slot = sl ^ vcomb_xor(v, sv);
-                IO<R>::sload(smem, slot, re[v], im[v]);
-            }
+            for (int v = 0; v < NV; v++) IO<R>::sload(smem, sl ^ RD.vld_x[v], re[v], im[v]);
             __syncthreads(); /* every thread has its registers before anyone overwrites the tile */
         }
 
         /* ---- the fused gates of this round ---- */
-        R psr = R(1), psi = R(0); /* per-thread pending phase (OP_TPHASE) */
-        const uint32_t n_ops = RD.n_ops;
-        const uint4 *op = B + RD.op_off16;
-        for (uint32_t i = 0; i < n_ops; i++) {
-            const uint4 h = *op;
-            const uint32_t kind = h.x;
-            const uint64_t tmask = ((uint64_t)h.w << 32) | h.z;
-            const uint2 *c = reinterpret_cast<const uint2 *>(op + 1);
-            op += h.y;
-            const bool pred = (gthr & tmask) == tmask;
-            const bool mux = (kind >> 16) & 1u;
-            if (!pred && !mux) continue;
-            const uint32_t code = kind & 0xffu;
-            const int vb = (kind >> 8) & 0xf;
-            switch (code) {
-            case OP_MAT_U: { const uint2 *cs = c + ((mux && pred) ? 4 : 0); unit_dispatch<R, false>(vb, re, im, cs); const R a = T::scalar(cs, 3); psr *= a; psi *= a; break; }
-            case OP_MAT_UI: { const uint2 *cs = c + ((mux && pred) ? 6 : 0); unit_dispatch<R, true>(vb, re, im, cs); const R a = T::scalar(cs, 5); psr *= a; psi *= a; break; }
-            case OP_MAT_R: mat_dispatch<R, 1>(vb, re, im, c + ((mux && pred) ? 4 : 0)); break;
-            case OP_MAT_I: mat_dispatch<R, 2>(vb, re, im, c + ((mux && pred) ? 6 : 0)); break;
-            case OP_MAT_G: mat_dispatch<R, 3>(vb, re, im, c + ((mux && pred) ? 8 : 0)); break;
-            case OP_MATP_R: mat_p<1>(re, im, c + ((mux && pred) ? 2 : 0)); break;
-            case OP_MATP_G: mat_p<3>(re, im, c + ((mux && pred) ? 4 : 0)); break;
-            case OP_DIAG_V: {
-                const V pr = T::coef(c, 0), pi = T::coef(c, 1), npi = T::neg(pi);
-                switch (vb) {
-                case 0: diag_v<R, 0>(re, im, pr, pi, npi); break;
-                case 1: diag_v<R, 1>(re, im, pr, pi, npi); break;
-#if QSB_NVB > 3
-                case 2: diag_v<R, 2>(re, im, pr, pi, npi); break;
-                default: diag_v<R, 3>(re, im, pr, pi, npi); break;
-#else
-                default: diag_v<R, 2>(re, im, pr, pi, npi); break;
-#endif
+        S psr = S(1), psi = S(0); /* per-thread pending scalar: unit-form scales and thread-level phases */
+        const uint32_t n_seg = RD.n_seg;
+        const GSegment *seg = reinterpret_cast<const GSegment *>(B + RD.seg_off16);
+        for (uint32_t sg = 0; sg < n_seg; sg++) {
+            /* -- specials: generic interpreter -- */
+            const uint32_t n_ops = seg[sg].n_special;
+            const uint4 *op = B + seg[sg].special_off16;
+            for (uint32_t i = 0; i < n_ops; i++) {
+                const uint4 h = *op;
+                const uint4 *c = op + 1;
+                op += h.x >> 16;
+                const uint32_t code = h.x & 0xffu;
+                const uint64_t om = ((uint64_t)h.w << 32) | h.z;
+                const bool two = (h.x >> 8) & 1u;
+                const bool pred = ((src_outer & om) == om) && ((tid & h.y) == h.y);
+                if (!two && !pred) continue;   /* controlled gate: the other threads sit this op out */
+                const bool s1 = two && pred;   /* multiplexer: threads that pass use coefficient set 1 */
+                switch (code) {
+                CASE4(G_FULL_G, {
+                    const uint4 *cs = c + (s1 ? 4 : 0);     /* rare form: per-thread constant loads are fine */
+                    V m[8];
+                    T::vec2(cs, 0, m[0], m[1]); T::vec2(cs, 1, m[2], m[3]); T::vec2(cs, 2, m[4], m[5]); T::vec2(cs, 3, m[6], m[7]);
+                    gen_v<R, VB>(re, im, m);
+                })
+                CASE4(G_DIAG_V, {
+                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
+                    diag_v<R, VB>(re, im, pr, pi);
+                })
+                case G_DIAG_ALL: {
+                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
+#pragma unroll
+                    for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi);
+                    break;
                 }
-                break;
-            }
-            case OP_DIAG_ALL: {
-                const V pr = T::coef(c, 0), pi = T::coef(c, 1), npi = T::neg(pi);
+                case G_DIAG_GEN: {
+                    const uint32_t vmask = (h.x >> 12) & 0xfu;
+                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
 #pragma unroll
-                for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
-                break;
+                    for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) cmul_inplace<R>(re[v], im[v], pr, pi);
+                    break;
+                }
+                case G_MATP_R: {
+                    V A, Bc; T::vec2(c + (s1 ? 1 : 0), 0, A, Bc);
+                    matp_r(re, im, A, Bc);
+                    break;
+                }
+                case G_MATP_G: {
+                    const uint4 *cs = c + (s1 ? 2 : 0);
+                    V Ar, Ai, Br, Bi; T::vec2(cs, 0, Ar, Ai); T::vec2(cs, 1, Br, Bi);
+                    matp_g(re, im, Ar, Ai, Br, Bi);
+                    break;
+                }
+                default: break;
+                }
             }
-            case OP_DIAG_GEN: {
-                const uint32_t vmask = (kind >> 20) & 0xfu;
-                const V pr = T::coef(c, 0), pi = T::coef(c, 1), npi = T::neg(pi);
-#pragma unroll
-                for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
-                break;
+            /* -- groups: one slot per vector bit at a fixed position -- */
+            const uint32_t n_groups = seg[sg].n_groups;
+            const uint4 *gp = B + seg[sg].group_off16;
+            if (n_groups) {
+                const int G16 = QSB_GROUP16(sizeof(R) == 4), S16 = 2 * T::SET4;
+                uint4 nh = gp[0], nm = gp[1];
+                for (uint32_t g = 0; g < n_groups; g++, gp += G16) {
+                    const uint4 gh = nh, gm = nm;
+                    nh = gp[G16]; nm = gp[G16 + 1];            /* next group's header (or slack) */
+                    const uint32_t f0 = gh.x & 0xffu, f1 = (gh.x >> 8) & 0xffu, f2 = (gh.x >> 16) & 0xffu, f3 = gh.x >> 24;
+                    const uint4 *cp = gp + 2;
+                    SlotC<R> sa, sc;
+                    if (f0) slot_fetch<R>(cp, sa);
+                    if (f1) slot_fetch<R>(cp + S16, sc);
+                    if (f0) slot_exec<R, 0>(f0, gm.x, sa, re, im, tw, psr, psi, xm);
+                    if (f2) slot_fetch<R>(cp + 2 * S16, sa);
+                    if (f1) slot_exec<R, 1>(f1, gm.y, sc, re, im, tw, psr, psi, xm);
+                    if (f3) slot_fetch<R>(cp + 3 * S16, sc);
+                    if (f2) slot_exec<R, 2>(f2, gm.z, sa, re, im, tw, psr, psi, xm);
+                    if (f3) slot_exec<R, 3>(f3, gm.w, sc, re, im, tw, psr, psi, xm);
+                }
             }
-            case OP_TPHASE: {
-                R pr, pi; T::tphase(c, pr, pi);
-                const R nr = psr * pr - psi * pi;
+        }
+        /* ---- thread-level phases of this round ---- */
+        {
+            const uint32_t n_tph = RD.n_tph;
+            const uint4 *e = B + RD.tph_off16;
+            for (uint32_t i = 0; i < n_tph; i++, e += 2) {
+                const uint4 h = e[0];
+                const uint64_t om = ((uint64_t)h.w << 32) | h.z;
+                if ((src_outer & om) != om) continue;          /* uniform */
+                S pr, pi; T::tph(e[1], pr, pi);
+                if ((tid & h.x) != h.x) { pr = S(1); pi = S(0); }
+                const S nr = psr * pr - psi * pi;
                 psi = psr * pi + psi * pr; psr = nr;
-                break;
-            }
-            default: break;
             }
         }
         if (RD.flags & 1u) {
-            if (!(psr == R(1) && psi == R(0))) {
-                const V pr = T::bc(psr), pi = T::bc(psi), npi = T::bc(-psi);
+            if (psi != S(0)) {
+                const V pr = T::bc(psr), pi = T::bc(psi);
 #pragma unroll
-                for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi, npi);
+                for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi);
+            } else if (psr != S(1)) {
+                const V pr = T::bc(psr);
+#pragma unroll
+                for (int v = 0; v < NV; v++) { re[v] = T::mul(pr, re[v]); im[v] = T::mul(pr, im[v]); }
             }
         }
 
-        if (rd == n_rounds - 1) {
-            uint64_t dthr = outer | P.dst_fixed;
+        if (rd < n_rounds - 1) {
+            uint32_t ss = sb >> 16;
+            /* deferred X: register v holds logical vector v ^ xm; the slot map is GF(2)-linear */
 #pragma unroll
-            for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) dthr |= P.dst_thr[j];
-            uint64_t gv[QSB_NVB];
+            for (int b = 0; b < QSB_NVB; b++) if ((xm >> b) & 1) ss ^= RD.vst_x[1 << b];
+            xm = 0;
 #pragma unroll
-            for (int b = 0; b < QSB_NVB; b++) gv[b] = P.dst_vec[b];
-#pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const uint64_t gi = dthr | vcomb_or(v, gv);
-                IO<R>::gstore(dst, gi & loc_mask, re[v], im[v]);
-            }
-        } else {
-            const uint32_t ss = sb >> 16;
-            uint32_t sv[QSB_NVB];
-#pragma unroll
-            for (int b = 0; b < QSB_NVB; b++) sv[b] = RD.vec[b].st;
-#pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const uint32_t slot = ss ^ vcomb_xor(v, sv);
-                IO<R>::sstore(smem, slot, re[v], im[v]);
-            }
+            for (int v = 0; v < NV; v++) IO<R>::sstore(smem, ss ^ RD.vst_x[v], re[v], im[v]);
             __syncthreads();
         }
+    }
+
+    /* ---- scatter ---- */
+    {
+        uint64_t off = outer * AMP, xoff = 0;
+#pragma unroll
+        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) off += P.st_thr[j];
+#pragma unroll
+        for (int b = 0; b < QSB_NVB; b++) if ((xm >> b) & 1) xoff ^= P.st_vec[1 << b];
+        char *p = dst + off;
+#pragma unroll
+        for (int v = 0; v < NV; v++) IO<R>::gstore(p + (P.st_vec[v] ^ xoff), re[v], im[v]);
     }
 }
 
 /* ------------------------------------------------------------------ launching */
-template <typename R, int BLOB, bool PEER>
-static int launch_one(qsb_sim *s, const HostPass &hp, const PtrTab &src, void *dst)
+template <typename R, int BLOB>
+static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         attr_set = true;
     }
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
     const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
-    k_tile_pass<R, BLOB, PEER><<<(unsigned)hp.hdr.n_tiles, QSB_THREADS, 65536, s->stream>>>(*blob, src, dst);
+    k_tile_pass<R, BLOB><<<(unsigned)hp.hdr.n_tiles, QSB_THREADS, 65536, s->stream>>>(*blob, (const char *)src, (char *)dst);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
 }
 
 template <typename R>
-static int launch_pass(qsb_sim *s, const HostPass &hp, const PtrTab &src, void *dst, bool peer)
+static int launch_pass(qsb_sim *s, const HostPass &hp, const void *src, void *dst)
 {
-    const bool small = hp.blob.size() <= QSB_BLOB_SMALL;
-    if (peer) return small ? launch_one<R, QSB_BLOB_SMALL, true>(s, hp, src, dst) : launch_one<R, QSB_BLOB_LARGE, true>(s, hp, src, dst);
-    return small ? launch_one<R, QSB_BLOB_SMALL, false>(s, hp, src, dst) : launch_one<R, QSB_BLOB_LARGE, false>(s, hp, src, dst);
+    if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL>(s, hp, src, dst);
+    if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM>(s, hp, src, dst);
+    return launch_one<R, QSB_BLOB_LARGE>(s, hp, src, dst);
 }
 
-int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, void *const *src_ptrs, void *dst, bool peer)
+int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst)
 {
-    PtrTab t;
-    for (int i = 0; i < 8; i++) t.p[i] = src_ptrs[i];
     const HostPass &hp = p->passes[k];
-    return s->prec == QSB_F32 ? launch_pass<float>(s, hp, t, dst, peer) : launch_pass<double>(s, hp, t, dst, peer);
+    return s->prec == QSB_F32 ? launch_pass<float>(s, hp, src, dst) : launch_pass<double>(s, hp, src, dst);
 }

@@ -78,7 +78,9 @@ int tiled_min_local_bits(int prec, const qsb_options_t *) { return prec == QSB_F
 
 namespace {
 
-const int MAX_PASS_OPS = 150;   /* keeps a pass descriptor below QSB_BLOB_LARGE */
+/* keeps a pass descriptor below QSB_BLOB_LARGE: in the worst case (every op on the same vector bit)
+ * each op occupies a whole group, 160 bytes in f32 and 288 bytes in f64 */
+inline int max_pass_ops(bool f32) { return f32 ? 120 : 72; }
 const int MAX_PASS_ROUNDS = 32;
 
 struct Machine {
@@ -339,7 +341,16 @@ struct PassBuilder {
         std::vector<std::vector<HostOp>> rops(nrounds);
         int flagged = -1;
         for (int r = 0; r < nrounds; r++) {
-            for (int i : round_ops[r]) emit(ops[i], r);
+            for (size_t k = 0; k < round_ops[r].size(); k++) {
+                const COp &o = ops[round_ops[r][k]];
+                /* is this the last op of the round that involves its target qubit?  (an X can then be deferred) */
+                bool last_on_target = o.target >= 0;
+                for (size_t k2 = k + 1; k2 < round_ops[r].size() && last_on_target; k2++) {
+                    const COp &o2 = ops[round_ops[r][k2]];
+                    if (o2.target == o.target || ((o2.ctrl >> o.target) & 1)) last_on_target = false;
+                }
+                emit(o, r, last_on_target);
+            }
             rops[r].swap(hp.ops);
             bool need = false;
             for (HostOp &h : rops[r]) {
@@ -423,7 +434,7 @@ struct PassBuilder {
         else { set_c(h, set, 0, m[0], m[6]); set_c(h, set, 1, m[1], m[7]); set_c(h, set, 2, m[2], m[4]); set_c(h, set, 3, m[3], m[5]); }
     }
 
-    void emit(const COp &o, int r)
+    void emit(const COp &o, int r, bool last_on_target)
     {
         const int P = M.f32 ? 0 : -1;
         HostOp h; memset(&h, 0, sizeof h);
@@ -455,6 +466,13 @@ struct PassBuilder {
         const int tb = tile_of_qubit[o.target];
         int vb = -1;
         for (int j = 0; j < QSB_NVB; j++) if (hp.round_vec[r][j] == tb) vb = j;
+        /* X / CX whose target is a vector bit and that nothing else in this round touches afterwards:
+         * the swap of the two register halves is deferred into the next store address (free). */
+        if (o.kind == C_X && tb != P && !pack_ctrl && vmask == 0 && last_on_target) {
+            h.kind = OPK(OP_XDEF, vb, 0, 0); h.n_coef = 0;
+            hp.ops.push_back(h);
+            return;
+        }
         double m0[8], m1[8]; /* m0: controls not satisfied, m1: satisfied */
         /* X / CX that could not be absorbed: the swap is issued as the real matrix [[0,1],[1,0]] --
          * 0*x + y is exact, costs fewer instructions than register moves and keeps every update in place */
@@ -528,49 +546,257 @@ struct PassBuilder {
         }
     }
 
-    /* serialise header + rounds + op stream into the kernel-parameter blob */
+    /* Lower the logical tables (hdr / rounds / ops) to the device encoding of tiled.h (GPass, GRound,
+     * op stream, GTPhase lists) and serialise it into the kernel-parameter blob. */
     int serialise()
     {
         const bool f32 = M.f32;
-        std::vector<uint8_t> &b = hp.blob;
+        const size_t SS = f32 ? 4 : 8;                 /* scalar size */
+        const uint64_t AMP = f32 ? 8 : 16;             /* bytes per amplitude */
+        const uint64_t loc_mask = (1ULL << M.nloc) - 1;
         auto al16 = [](size_t x) { return (x + 15) / 16 * 16; };
-        size_t off = al16(sizeof(DevPass));
-        hp.hdr.rounds_off16 = (uint32_t)(off / 16);
-        off += al16(sizeof(DevRound) * hp.rounds.size());
-        std::vector<uint8_t> stream;
-        for (size_t r = 0; r < hp.rounds.size(); r++) {
-            hp.rounds[r].op_off16 = (uint32_t)((off + stream.size()) / 16);
-            hp.rounds[r].n_ops = hp.round_op_count[r];
+        const int nrounds = (int)hp.rounds.size();
+        auto put_s = [&](std::vector<uint8_t> &o, double v) {
+            if (f32) { float x = (float)v; const uint8_t *q = (const uint8_t *)&x; o.insert(o.end(), q, q + 4); }
+            else { const uint8_t *q = (const uint8_t *)&v; o.insert(o.end(), q, q + 8); }
+        };
+        auto put_v = [&](std::vector<uint8_t> &o, const double lane[2]) {   /* (lo, hi) floats or one double */
+            if (f32) { float x[2] = {(float)lane[0], (float)lane[1]}; const uint8_t *q = (const uint8_t *)x; o.insert(o.end(), q, q + 8); }
+            else { const uint8_t *q = (const uint8_t *)&lane[1]; o.insert(o.end(), q, q + 8); }
+        };
+        auto pad16 = [&](std::vector<uint8_t> &o) { o.resize(al16(o.size()), 0); };
+
+        GPass gp; memset(&gp, 0, sizeof gp);
+        gp.n_rounds = hp.hdr.n_rounds; gp.n_runs = hp.hdr.n_runs;
+        memcpy(gp.run_start, hp.hdr.run_start, sizeof gp.run_start);
+        memcpy(gp.run_len, hp.hdr.run_len, sizeof gp.run_len);
+        gp.src_fixed = hp.hdr.src_fixed; gp.n_tiles = hp.hdr.n_tiles; gp.nloc = hp.hdr.nloc;
+        for (int j = 0; j < QSB_TB; j++) {
+            gp.ld_thr[j] = (hp.rounds[0].thr[j].gidx & loc_mask) * AMP;
+            gp.st_thr[j] = (hp.hdr.dst_thr[j] & loc_mask) * AMP;
+        }
+        for (int v = 0; v < QSB_NV; v++) {
+            uint64_t l = 0, t = 0;
+            for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) { l |= hp.rounds[0].vec[b].gidx; t |= hp.hdr.dst_vec[b]; }
+            gp.ld_vec[v] = (l & loc_mask) * AMP; gp.st_vec[v] = (t & loc_mask) * AMP;
+        }
+
+        std::vector<GRound> gr(nrounds);
+        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds);
+        /* body offsets inside segstream entries are relative to the round's body; fixed up below */
+        struct SegRec { uint32_t n_special, special_rel, n_groups, group_rel; };
+        std::vector<std::vector<SegRec>> segrec(nrounds);
+        const int SET16 = QSB_SET16(f32), GROUP16 = QSB_GROUP16(f32);
+        uint32_t n_cond = 0;
+        for (int r = 0; r < nrounds; r++) {
+            const DevRound &D = hp.rounds[r];
+            GRound &G = gr[r]; memset(&G, 0, sizeof G);
+            G.flags = D.flags;
+            for (int j = 0; j < QSB_TB; j++) G.thr_x[j] = ((uint32_t)D.thr[j].ld * 16u) | (((uint32_t)D.thr[j].st * 16u) << 16);
+            for (int v = 0; v < QSB_NV; v++) {
+                uint32_t l = 0, t = 0;
+                for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) { l ^= D.vec[b].ld; t ^= D.vec[b].st; }
+                G.vld_x[v] = l * 16u; G.vst_x[v] = t * 16u;
+            }
+            /* predicate masks: source index bit -> thread bit of this round, or outer */
+            auto split_mask = [&](uint64_t tmask, uint32_t &tm8, uint64_t &om) {
+                tm8 = 0; om = 0;
+                for (uint64_t m = tmask; m; m &= m - 1) {
+                    const uint64_t bit = m & (~m + 1);
+                    int j = -1;
+                    for (int k = 0; k < QSB_TB; k++) if (D.thr[k].gidx == bit) j = k;
+                    if (j >= 0) tm8 |= 1u << j; else om |= bit;
+                }
+            };
+            /* outer condition -> bit of W (pass-wide table); false if the table is full */
+            auto cond_bit = [&](uint64_t om, uint32_t &wbits) {
+                wbits = 0;
+                if (!om) return true;
+                for (uint32_t i = 0; i < n_cond; i++) if (gp.cond[i] == om) { wbits = 1u << i; return true; }
+                if (n_cond >= QSB_MAX_COND) return false;
+                gp.cond[n_cond] = om; wbits = 1u << n_cond; n_cond++;
+                return true;
+            };
+            std::vector<uint8_t> &ts = tphstream[r];
+            uint32_t n_tph = 0;
+
+            /* segment under construction */
+            std::vector<uint8_t> specials; uint32_t n_special = 0;
+            std::vector<std::vector<uint8_t>> groups;       /* each QSB_GROUP16 * 16 bytes */
+            int next_group[QSB_NVB] = {0, 0, 0, 0};
+            auto close_segment = [&]() {
+                if (!n_special && groups.empty()) return;
+                SegRec sr; sr.n_special = n_special; sr.special_rel = (uint32_t)bodystream[r].size();
+                bodystream[r].insert(bodystream[r].end(), specials.begin(), specials.end());
+                sr.n_groups = (uint32_t)groups.size(); sr.group_rel = (uint32_t)bodystream[r].size();
+                for (auto &g : groups) bodystream[r].insert(bodystream[r].end(), g.begin(), g.end());
+                segrec[r].push_back(sr);
+                specials.clear(); n_special = 0; groups.clear();
+                for (int b = 0; b < QSB_NVB; b++) next_group[b] = 0;
+            };
+
             for (uint32_t k = hp.round_op_begin[r]; k < hp.round_op_begin[r] + hp.round_op_count[r]; k++) {
                 const HostOp &h = hp.ops[k];
-                const int code = h.kind & 0xff;
+                const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf, vmask = (h.kind >> 20) & 0xf;
                 const bool mux = (h.kind >> 16) & 1;
-                const int sets = mux ? 2 : 1;
-                size_t payload = (code == OP_TPHASE) ? 16 : al16((size_t)h.n_coef * 8 * sets);
-                OpHdr oh; oh.kind = h.kind; oh.size16 = (uint32_t)((16 + payload) / 16); oh.tmask = h.tmask;
-                size_t at = stream.size();
-                stream.resize(at + 16 + payload, 0);
-                memcpy(&stream[at], &oh, 16);
-                uint8_t *p = &stream[at + 16];
+                uint32_t tm8; uint64_t om;
+                split_mask(h.tmask, tm8, om);
                 if (code == OP_TPHASE) {
-                    if (f32) { float v[2] = {(float)h.tph[0], (float)h.tph[1]}; memcpy(p, v, 8); }
-                    else memcpy(p, h.tph, 16);
-                } else {
-                    for (int s = 0; s < sets; s++) for (int k = 0; k < h.n_coef; k++) {
-                        if (f32) { float v[2] = {(float)h.c[s][k][0], (float)h.c[s][k][1]}; memcpy(p, v, 8); }
-                        else memcpy(p, &h.c[s][k][1], 8); /* f64 has no pack lanes: the "hi" entry is the value */
-                        p += 8;
-                    }
+                    GTPhase e; memset(&e, 0, sizeof e);
+                    e.tmask = tm8; e.omask = om;
+                    if (f32) { float v[2] = {(float)h.tph[0], (float)h.tph[1]}; memcpy(e.val, v, 8); }
+                    else memcpy(e.val, h.tph, 16);
+                    const uint8_t *q = (const uint8_t *)&e; ts.insert(ts.end(), q, q + sizeof e);
+                    n_tph++;
+                    continue;
                 }
+                const bool cond = (tm8 | om) != 0;
+                /* lanes differ (a control on the pack qubit): scalar-coefficient forms cannot express it */
+                auto lanes_equal = [&](int set) { for (int c = 0; c < h.n_coef; c++) if (h.c[set][c][0] != h.c[set][c][1]) return false; return true; };
+                const bool leq = lanes_equal(0) && (!mux || lanes_equal(1));
+
+                /* ---- slot forms ---- */
+                int sform = S_SKIP;
+                if (leq) switch (code) {
+                    case OP_MAT_U: sform = S_UNIT_R; break;
+                    case OP_MAT_UI: sform = S_UNIT_I; break;
+                    case OP_MAT_R: sform = S_FULL_R; break;
+                    case OP_MAT_I: sform = S_FULL_I; break;
+                    case OP_DIAG_V: sform = S_DIAG; break;
+                    case OP_XDEF: sform = S_XDEF; break;
+                    default: break;
+                }
+                uint32_t wbits = 0;
+                if (sform != S_SKIP && cond_bit(om, wbits)) {
+                    std::vector<uint8_t> slot;
+                    auto slot_set = [&](int set, bool identity) {
+                        auto C = [&](int c) { return h.c[set][c][1]; };
+                        std::vector<uint8_t> o;
+                        switch (sform) {
+                        case S_UNIT_R: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(0)); put_s(o, C(1)); put_s(o, C(2)); put_s(o, C(3)); } break;
+                        case S_UNIT_I: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(0)); put_s(o, C(2)); put_s(o, C(4)); put_s(o, C(5)); } break;
+                        case S_FULL_R: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 1); } else { put_s(o, C(2)); put_s(o, C(0)); put_s(o, C(1)); put_s(o, C(3)); } break;
+                        case S_FULL_I: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 1); } else { put_s(o, C(4)); put_s(o, C(1)); put_s(o, C(3)); put_s(o, C(5)); } break;
+                        case S_DIAG: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 0); } else { put_s(o, C(0)); put_s(o, C(1)); put_s(o, 0); put_s(o, 0); } break;
+                        default: put_s(o, 0); put_s(o, 0); put_s(o, 0); put_s(o, 0); break;
+                        }
+                        slot.insert(slot.end(), o.begin(), o.end());
+                    };
+                    if (mux) { slot_set(0, false); slot_set(1, false); }
+                    else { slot_set(0, true); slot_set(0, false); }
+                    if ((int)slot.size() != 2 * SET16 * 16) { qsb_set_error("internal: slot of %zu bytes", slot.size()); return QSB_ERR_ARG; }
+                    const int g = next_group[vb]++;
+                    if (g == (int)groups.size()) groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0));
+                    uint8_t *G0 = groups[g].data();
+                    G0[vb] = (uint8_t)sform;                                   /* form byte of slot vb */
+                    const uint32_t pm = tm8 | (wbits << 8);
+                    memcpy(G0 + 16 + 4 * vb, &pm, 4);                          /* predicate mask */
+                    memcpy(G0 + 32 + (size_t)vb * 2 * SET16 * 16, slot.data(), slot.size());
+                    continue;
+                }
+
+                /* ---- specials (generic interpreter) ---- */
+                if (!groups.empty()) close_segment();     /* a special runs before the groups of its segment */
+                const int two = mux ? 1 : 0, skip = (!mux && cond) ? 1 : 0;
+                std::vector<uint8_t> sets[2];
+                int gcode = -1;
+                auto write_set = [&](std::vector<uint8_t> &o, int set) {
+                    const double zero[2] = {0.0, 0.0};
+                    auto L = [&](int c) { return h.c[set][c]; };
+                    /* complex 2x2 with lane pairs: m00r m00i m01r m01i m10r m10i m11r m11i */
+                    auto put_gen = [&](const double (*m)[2]) { for (int c = 0; c < 8; c++) put_v(o, m[c]); };
+                    double m[8][2];
+                    for (int c = 0; c < 8; c++) m[c][0] = m[c][1] = 0.0;
+                    switch (code) {
+                    case OP_MAT_U: case OP_MAT_UI: {   /* only when the outer-condition table is full */
+                        gcode = G_FULL_G + vb;
+                        for (int l = 0; l < 2; l++) {
+                            if (code == OP_MAT_U) {
+                                const double pp = h.c[set][0][l], q = h.c[set][1][l], kk = h.c[set][2][l], a = h.c[set][3][l];
+                                m[0][l] = a; m[2][l] = a * pp; m[4][l] = a * q; m[6][l] = a * (kk + q * pp);
+                            } else {
+                                const double pp = h.c[set][0][l], q = h.c[set][2][l], kk = h.c[set][4][l], a = h.c[set][5][l];
+                                m[0][l] = a; m[3][l] = a * pp; m[5][l] = a * q; m[6][l] = a * (kk - q * pp);
+                            }
+                        }
+                        put_gen(m);
+                        break;
+                    }
+                    case OP_XDEF:
+                        gcode = G_FULL_G + vb;
+                        m[2][0] = m[2][1] = 1.0; m[4][0] = m[4][1] = 1.0;
+                        put_gen(m);
+                        break;
+                    case OP_MAT_R:
+                        gcode = G_FULL_G + vb;
+                        put_v(o, L(2)); put_v(o, zero); put_v(o, L(0)); put_v(o, zero); put_v(o, L(1)); put_v(o, zero); put_v(o, L(3)); put_v(o, zero);
+                        break;
+                    case OP_MAT_I:
+                        gcode = G_FULL_G + vb;
+                        put_v(o, L(4)); put_v(o, zero); put_v(o, zero); put_v(o, L(1)); put_v(o, zero); put_v(o, L(3)); put_v(o, L(5)); put_v(o, zero);
+                        break;
+                    case OP_MAT_G:
+                        gcode = G_FULL_G + vb;
+                        put_v(o, L(6)); put_v(o, L(0)); put_v(o, L(1)); put_v(o, L(2)); put_v(o, L(3)); put_v(o, L(4)); put_v(o, L(7)); put_v(o, L(5));
+                        break;
+                    case OP_MATP_R:
+                        gcode = G_MATP_R; put_v(o, L(0)); put_v(o, L(1));
+                        break;
+                    case OP_MATP_G:
+                        gcode = G_MATP_G; put_v(o, L(0)); put_v(o, L(1)); put_v(o, L(2)); put_v(o, L(3));
+                        break;
+                    case OP_DIAG_V: case OP_DIAG_ALL: case OP_DIAG_GEN:
+                        gcode = code == OP_DIAG_V ? G_DIAG_V + vb : code == OP_DIAG_ALL ? G_DIAG_ALL : G_DIAG_GEN;
+                        put_v(o, L(0)); put_v(o, L(1));
+                        break;
+                    default: break;
+                    }
+                    pad16(o);
+                };
+                write_set(sets[0], 0);
+                if (mux) write_set(sets[1], 1);
+                if (gcode < 0) { qsb_set_error("internal: op code %d cannot be lowered", code); return QSB_ERR_ARG; }
+                /* an unconditional unit-form op that fell through keeps its scale in the matrix: nothing else to do.
+                 * A conditional XDEF / unit op lowered to FULL_G is a plain controlled gate (skip when the predicate fails). */
+                const size_t bytes = 16 + sets[0].size() + sets[1].size();
+                uint32_t hdr[4] = {GOPK(gcode, two, skip, vmask, bytes / 16), tm8, (uint32_t)om, (uint32_t)(om >> 32)};
+                const uint8_t *q = (const uint8_t *)hdr; specials.insert(specials.end(), q, q + 16);
+                specials.insert(specials.end(), sets[0].begin(), sets[0].end());
+                specials.insert(specials.end(), sets[1].begin(), sets[1].end());
+                n_special++;
             }
+            close_segment();
+            G.n_tph = n_tph; G.n_seg = (uint32_t)segrec[r].size();
         }
-        const size_t total = off + stream.size() + 96;   /* slack: the kernel prefetches one op ahead */
+        gp.n_cond = n_cond;
+        size_t off = al16(sizeof(GPass));
+        gp.rounds_off16 = (uint32_t)(off / 16);
+        off += al16(sizeof(GRound) * nrounds);
+        for (int r = 0; r < nrounds; r++) {
+            gr[r].seg_off16 = (uint32_t)(off / 16);
+            const size_t body0 = off + segrec[r].size() * sizeof(GSegment);
+            for (const SegRec &sr : segrec[r]) {
+                GSegment gs; gs.n_special = sr.n_special; gs.special_off16 = (uint32_t)((body0 + sr.special_rel) / 16);
+                gs.n_groups = sr.n_groups; gs.group_off16 = (uint32_t)((body0 + sr.group_rel) / 16);
+                const uint8_t *q = (const uint8_t *)&gs; segstream[r].insert(segstream[r].end(), q, q + sizeof gs);
+            }
+            off = body0 + bodystream[r].size();
+            gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size();
+        }
+        const size_t total = off + 64;   /* slack: the group loop prefetches one group header past the last group */
         if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_ERR_ARG; }
         hp.hdr.blob_bytes = (uint32_t)total;
-        b.assign(total <= QSB_BLOB_SMALL ? QSB_BLOB_SMALL : QSB_BLOB_LARGE, 0);
-        memcpy(&b[0], &hp.hdr, sizeof(DevPass));
-        memcpy(&b[(size_t)hp.hdr.rounds_off16 * 16], hp.rounds.data(), sizeof(DevRound) * hp.rounds.size());
-        memcpy(&b[off], stream.data(), stream.size());
+        std::vector<uint8_t> &b = hp.blob;
+        b.assign(total <= QSB_BLOB_SMALL ? QSB_BLOB_SMALL : total <= QSB_BLOB_MEDIUM ? QSB_BLOB_MEDIUM : QSB_BLOB_LARGE, 0);
+        memcpy(&b[0], &gp, sizeof gp);
+        memcpy(&b[(size_t)gp.rounds_off16 * 16], gr.data(), sizeof(GRound) * nrounds);
+        for (int r = 0; r < nrounds; r++) {
+            size_t at = (size_t)gr[r].seg_off16 * 16;
+            if (!segstream[r].empty()) memcpy(&b[at], segstream[r].data(), segstream[r].size());
+            at += segstream[r].size();
+            if (!bodystream[r].empty()) memcpy(&b[at], bodystream[r].data(), bodystream[r].size());
+            if (!tphstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16], tphstream[r].data(), tphstream[r].size());
+        }
         return QSB_OK;
     }
 };
@@ -583,7 +809,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.n = n; M.prec = prec; M.g = g; M.nloc = nloc; M.rank = rank;
     M.f32 = (prec == QSB_F32);
     M.T = M.f32 ? QSB_T_F32 : QSB_T_F64;
-    M.nb = M.f32 ? 4 : 3;
+    M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
     if (M.a < (M.f32 ? 3 : 2) || M.a > (M.f32 ? 6 : 5)) { qsb_set_error("low_bits %d unsupported for this precision", M.a); return QSB_ERR_ARG; }
     if (nloc < M.T) { qsb_set_error("internal: local register smaller than a tile"); return QSB_ERR_ARG; }
@@ -610,7 +836,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         uint64_t S = S0; int nS = n0;
         Blocker B; B.clear();
         mine.clear(); mine_idx.clear();
-        for (size_t i = first_open; i < N && (int)mine.size() < MAX_PASS_OPS; i++) {
+        for (size_t i = first_open; i < N && (int)mine.size() < max_pass_ops(M.f32); i++) {
             if (done[i]) continue;
             const COp &o = cops[i];
             bool can = B.ok(o);

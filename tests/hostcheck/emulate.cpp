@@ -5,7 +5,7 @@
  * verify the planner's tables (index maps, slot maps, op encodings) against the
  * oracle without a GPU, and it checks what the kernel relies on:
  *   - every smem slot is written exactly once per exchange,
- *   - every 64-bit (f32) / 128-bit (f64) shared access phase is bank-conflict free,
+ *   - every 128-bit shared access phase (16-byte slots, both precisions) is bank-conflict free,
  *   - first-round loads / last-round stores of a warp are contiguous.
  * It is linked only into tests/hostcheck/libqsb_hostcheck.so.
  */
@@ -25,8 +25,8 @@ struct Report { int max_conflict; int bad_slots; int noncontig; int passes; int 
 static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, Report &rep)
 {
     const int L = f32 ? 2 : 1;                  /* pack lanes */
-    const int nb = f32 ? 4 : 3;
-    const int phase_lanes = f32 ? 16 : 8;       /* lanes per shared-memory phase */
+    const int nb = 3;
+    const int phase_lanes = 8;                  /* lanes per 128-bit shared-memory phase (16-byte slots) */
     const uint64_t loc_mask = (1ULL << nloc) - 1;
     std::vector<cd> regs((size_t)QSB_THREADS * QSB_NV * L);
     std::vector<cd> smem((size_t)4096 * L);
@@ -100,6 +100,11 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                     const int set = (mux && pred) ? 1 : 0;
                     auto C = [&](int k, int l) { return op.c[set][k][f32 ? l : 1]; };
                     if (code == OP_TPHASE) { pend *= cd(op.tph[0], op.tph[1]); continue; }
+                    if (code == OP_XDEF) {   /* the kernel defers this swap into its next store address: same result */
+                        for (int v = 0; v < QSB_NV; v++) if (!((v >> vb) & 1))
+                            for (int l = 0; l < L; l++) std::swap(R[v * L + l], R[(v | (1 << vb)) * L + l]);
+                        continue;
+                    }
                     for (int v = 0; v < QSB_NV; v++) {
                         if (code == OP_MAT_U || code == OP_MAT_UI) {
                             if ((v >> vb) & 1) continue;
@@ -261,7 +266,7 @@ extern "C" void qsb_hostcheck_finish(void *hv, int *report5, int8_t *perm_out)
 extern "C" void qsb_hostcheck_describe(void *hv)
 {
     HcPlan *h = (HcPlan *)hv;
-    static const char *nm[16] = {"?", "MAT_R", "MAT_I", "MAT_G", "MATP_R", "MATP_G", "U", "UI", "?", "DIAG_V", "DIAG_ALL", "DIAG_GEN", "TPHASE", "?", "?", "?"};
+    static const char *nm[16] = {"?", "MAT_R", "MAT_I", "MAT_G", "MATP_R", "MATP_G", "U", "UI", "?", "DIAG_V", "DIAG_ALL", "DIAG_GEN", "TPHASE", "XDEF", "?", "?"};
     int tot[16] = {0}, totmux = 0, k = 0;
     for (const HostPass &hp : h->plan.passes) {
         if (hp.is_swap) { printf("pass %d: SWAP\n", k++); continue; }
