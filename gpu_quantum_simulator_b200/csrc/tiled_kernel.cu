@@ -269,7 +269,6 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     extern __shared__ __align__(16) uint8_t smem[];
     const uint4 *B = blob.q;
     const GPass &P = *reinterpret_cast<const GPass *>(B);
-    const GRound *rounds = reinterpret_cast<const GRound *>(B + P.rounds_off16);
     const uint32_t tid = threadIdx.x;
     const uint64_t AMP = sizeof(R) * 2;
 
@@ -305,8 +304,9 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     }
 
     uint32_t xm = 0;   /* deferred X: this thread's register v holds logical vector v ^ xm */
-    for (int rd = 0; rd < n_rounds; rd++) {
-        const GRound &RD = rounds[rd];
+    const uint4 *rp = B + P.rounds_off16;
+    for (int rd = 0; rd < n_rounds; rd++, rp += sizeof(GRound) / 16) {
+        const GRound &RD = *reinterpret_cast<const GRound *>(rp);
         uint32_t sb = 0; /* this thread's smem byte offset: load side in the low half, store side in the high half */
 #pragma unroll
         for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr_x[j];

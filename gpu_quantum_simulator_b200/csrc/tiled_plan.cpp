@@ -267,12 +267,15 @@ struct PassBuilder {
             if ((int)roundR.size() >= MAX_PASS_ROUNDS - 1) break;
             const bool is_first = roundR.empty();
             uint32_t R = 0, ctrl_used = 0; int nR = 0;
+            uint64_t closed = 0;   /* qubits that took a bare X / CX in this round: nothing may follow on them here,
+                                      so that the X is deferred into the store address instead of being computed */
             Blocker B; B.clear();
             std::vector<int> mine;
             for (size_t i = first_open; i < n; i++) {
                 if (done[i]) continue;
                 const COp &o = ops[i];
                 bool can = B.ok(o);
+                if (can && ((o.ctrl & closed) || (o.target >= 0 && ((closed >> o.target) & 1)))) can = false;
                 uint32_t cbits = 0; /* tile bits this op uses as (non-diagonal-gate) controls */
                 if (can && o.kind != C_PHASE) {
                     for (uint64_t m = o.ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) cbits |= 1u << tb; }
@@ -286,7 +289,10 @@ struct PassBuilder {
                     else if (nR < QSB_NVB && !((ctrl_used >> tb) & 1)) { R |= 1u << tb; nR++; }
                     else can = false;
                 }
-                if (can) { mine.push_back((int)i); done[i] = 1; left--; ctrl_used |= cbits; }
+                if (can) {
+                    mine.push_back((int)i); done[i] = 1; left--; ctrl_used |= cbits;
+                    if (o.kind == C_X && tile_of_qubit[o.target] != P) closed |= 1ULL << o.target;
+                }
                 else { B.block(o); if (B.full >= M.n) break; }
             }
             while (first_open < n && done[first_open]) first_open++;
@@ -481,6 +487,103 @@ struct PassBuilder {
         else if (o.kind == C_X) { memcpy(m0, IDENT, sizeof m0); memcpy(m1, XMAT, sizeof m1); }
         else { memcpy(m0, IDENT, sizeof m0); snap_mat(o.m, m1); }
         const bool is_mux = (o.kind == C_MUX);
+        /* ---- unit forms completed by a deferred X -------------------------------------------------
+         * Nothing else in this round touches the target afterwards, so an X on it costs nothing (OP_XDEF).
+         * That removes the need for full-form arithmetic: a matrix with a small m00 is X . M' with M'
+         * in unit form, and the multiplexer (U | X.U) of an absorbed CX is U for every thread followed
+         * by the deferred CX, with one uniform coefficient set and no per-thread scale. */
+        if (tb != P && !pack_ctrl && last_on_target && (!is_mux || h.tmask)) {
+            auto u_ok = [](const double *m) { return fabs(m[0]) >= 0.3; };
+            /* M = (times_i ? i : 1) * out with out real or rx form and a usable m00; returns the class or 0 */
+            auto cand = [&](const double *Mx, double *out, bool &times_i) -> int {
+                const int c = classify(Mx);
+                times_i = false;
+                if (c == 1 || c == 2) { memcpy(out, Mx, 8 * sizeof(double)); return u_ok(out) ? c : 0; }
+                if (is_jform(Mx)) {
+                    for (int k = 0; k < 4; k++) { out[2 * k] = Mx[2 * k + 1]; out[2 * k + 1] = -Mx[2 * k]; }
+                    times_i = true;
+                    const int c2 = classify(out);
+                    return ((c2 == 1 || c2 == 2) && u_ok(out)) ? c2 : 0;
+                }
+                return 0;
+            };
+            auto rowswap = [](const double *Mx, double *out) { for (int k = 0; k < 4; k++) { out[k] = Mx[4 + k]; out[4 + k] = Mx[k]; } };
+            auto fill_u = [&](HostOp &hh, int set, int cls, const double *m) {
+                const double a = m[0];
+                if (cls == 1) {
+                    const double pp = m[2] / a, q = m[4] / a, rr = m[6] / a;
+                    set_c(hh, set, 0, pp, pp); set_c(hh, set, 1, q, q); set_c(hh, set, 2, rr - q * pp, rr - q * pp); set_c(hh, set, 3, a, a);
+                } else {
+                    const double pp = m[3] / a, q = m[5] / a, rr = m[6] / a;
+                    set_c(hh, set, 0, pp, pp); set_c(hh, set, 1, -pp, -pp); set_c(hh, set, 2, q, q); set_c(hh, set, 3, -q, -q);
+                    set_c(hh, set, 4, rr + q * pp, rr + q * pp); set_c(hh, set, 5, a, a);
+                }
+            };
+            auto push_tph = [&](uint64_t tmask, double pr, double pi) {
+                HostOp t; memset(&t, 0, sizeof t);
+                t.kind = OPK(OP_TPHASE, 0, 0, 0); t.tmask = tmask; t.tph[0] = pr; t.tph[1] = pi;
+                hp.ops.push_back(t);
+            };
+            auto push_xdef = [&](uint64_t tmask) {
+                HostOp x; memset(&x, 0, sizeof x);
+                x.kind = OPK(OP_XDEF, vb, 0, 0); x.tmask = tmask; x.n_coef = 0;
+                hp.ops.push_back(x);
+            };
+            double d0[8], d1[8], s0[8], s1[8], u0[8], u1[8];
+            bool t0 = false, t1 = false;
+            if (is_mux) {
+                rowswap(m1, s1);
+                bool same = true;
+                for (int k = 0; k < 8; k++) if (s1[k] != m0[k]) same = false;
+                const int c0 = cand(m0, u0, t0);
+                if (same && c0) {
+                    /* U for everyone, then the CX: uniform coefficients, scale folded into the pass scale */
+                    HostOp g; memset(&g, 0, sizeof g);
+                    g.kind = OPK(c0 == 1 ? OP_MAT_U : OP_MAT_UI, vb, 0, 0); g.tmask = 0; g.n_coef = c0 == 1 ? 4 : 6;
+                    fill_u(g, 0, c0, u0);
+                    hp.ops.push_back(g);
+                    if (t0) push_tph(0, 0.0, 1.0);
+                    push_xdef(h.tmask);
+                    return;
+                }
+                /* both variants in unit form, each possibly through a pivot */
+                bool p0 = false, p1 = false, ok = true;
+                int k0 = cand(m0, d0, t0), k1 = cand(m1, d1, t1);
+                if (!(k0 && k1 && k0 == k1)) {
+                    if (!k0) { rowswap(m0, s0); k0 = cand(s0, d0, t0); p0 = true; }
+                    if (!k1) { k1 = cand(s1, d1, t1); p1 = true; }
+                    if (!(k0 && k1 && k0 == k1)) ok = false;
+                    if (ok) {
+                        HostOp g; memset(&g, 0, sizeof g);
+                        g.kind = OPK(k0 == 1 ? OP_MAT_U : OP_MAT_UI, vb, 1, 0); g.tmask = h.tmask; g.n_coef = k0 == 1 ? 4 : 6;
+                        fill_u(g, 0, k0, d0); fill_u(g, 1, k1, d1);
+                        hp.ops.push_back(g);
+                        /* factors of i: set 0 only -> i everywhere and -i where the predicate holds */
+                        if (t0 && t1) push_tph(0, 0.0, 1.0);
+                        else if (t1) push_tph(h.tmask, 0.0, 1.0);
+                        else if (t0) { push_tph(0, 0.0, 1.0); push_tph(h.tmask, 0.0, -1.0); }
+                        if (p0) push_xdef(0);                 /* X for everyone ... */
+                        if (p0 != p1) push_xdef(h.tmask);     /* ... toggled back (or on) where the predicate holds */
+                        return;
+                    }
+                }
+            } else if (o.kind != C_X) {
+                const int k1 = cand(m1, d1, t1);
+                if (!k1) {
+                    rowswap(m1, s1);
+                    const int kp = cand(s1, d1, t1);
+                    if (kp) {
+                        HostOp g; memset(&g, 0, sizeof g);
+                        g.kind = OPK(kp == 1 ? OP_MAT_U : OP_MAT_UI, vb, 0, 0); g.tmask = h.tmask; g.n_coef = kp == 1 ? 4 : 6;
+                        fill_u(g, 0, kp, d1);
+                        hp.ops.push_back(g);
+                        if (t1) push_tph(h.tmask, 0.0, 1.0);
+                        push_xdef(h.tmask);
+                        return;
+                    }
+                }
+            }
+        }
         /* rx-form multiplexer: m1 = i * m1' with m1' in rx form; the i becomes a thread phase */
         bool extra_i = false;
         if (is_mux && classify(m0) == 2 && classify(m1) == 3 && is_jform(m1) && !pack_ctrl && h.tmask && tile_of_qubit[o.target] != P) {

@@ -283,3 +283,17 @@ extern "C" void qsb_hostcheck_describe(void *hv)
     for (int c = 0; c < 16; c++) if (tot[c]) printf(" %s:%d", nm[c], tot[c]);
     printf(" mux:%d\n", totmux);
 }
+
+/* tuning aid: classify the full-form real ops of a plan (bare X / multiplexer / other) */
+extern "C" void qsb_hostcheck_describe_full(void *hv)
+{
+    HcPlan *h = (HcPlan *)hv;
+    int nx = 0, nmux = 0, nother = 0, nx_cond = 0;
+    for (const HostPass &hp : h->plan.passes) for (const HostOp &o : hp.ops) {
+        const int code = o.kind & 0xff; const bool mux = (o.kind >> 16) & 1;
+        if (code != OP_MAT_R) continue;
+        const bool isx = o.c[0][0][1] == 1 && o.c[0][1][1] == 1 && o.c[0][2][1] == 0 && o.c[0][3][1] == 0;
+        if (mux) nmux++; else if (isx) { nx++; if (o.tmask) nx_cond++; } else nother++;
+    }
+    printf("MAT_R: bare X %d (conditional %d), mux %d, other %d\n", nx, nx_cond, nmux, nother);
+}
