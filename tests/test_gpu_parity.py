@@ -157,3 +157,30 @@ def test_ref_shim_and_cli(tmp_path):
     assert any(l.startswith("MOST LIKELY MEASUREMENT: ") for l in out)
     bad = subprocess.run([exe], capture_output=True, text=True)
     assert bad.returncode == 1 and "Usage:" in bad.stdout
+
+
+def test_reference_main_links_against_gpu_library(tmp_path):
+    """the UNMODIFIED reference program (oracle/_ref/libqsim_ref.so = quantum_simulator.c
+    built -fPIC -Dmain=ref_main) runs its own main() while compute_state_vector / the CDF resolve to
+    libqsim_b200_refcompat.so, i.e. run on the GPU."""
+    ref_so = os.path.join(helpers.ROOT, "oracle", "_ref", "libqsim_ref.so")
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    lib_dir = os.path.join(helpers.ROOT, "gpu_quantum_simulator_b200")
+    launcher = tmp_path / "launcher.c"
+    launcher.write_text("int ref_main(int, char **); int main(int c, char **v) { return ref_main(c, v); }\n")
+    exe = tmp_path / "CExe_gpu"
+    subprocess.run(["gcc", str(launcher), "-o", str(exe), "-Wl,--no-as-needed", "-L" + lib_dir, "-lqsim_b200_refcompat",
+                    "-L" + os.path.dirname(ref_so), "-lqsim_ref", "-lqsim_b200", "-lm",
+                    "-Wl,-rpath," + lib_dir, "-Wl,-rpath," + os.path.dirname(ref_so)], check=True)
+    circ, n, amps, _ = helpers.load_case(os.path.join(helpers.GOLDEN, "grover_3_18.npz"))
+    path = tmp_path / "grover.qasm"
+    path.write_text(circuits.to_qasm(circ, n))
+    env = dict(os.environ, LD_DEBUG="bindings")
+    r = subprocess.run([str(exe), str(path), "1"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0
+    float(r.stdout.split()[0])                                  # the reference's only output: "%lf" seconds
+    bound = [l for l in r.stderr.splitlines() if "`compute_state_vector'" in l and "normal symbol" in l]
+    assert bound and all("libqsim_b200_refcompat" in l.split(" to ")[1] for l in bound), bound[:3]
+    bad = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Usage:" in bad.stdout          # quantum_simulator.c:39-43
