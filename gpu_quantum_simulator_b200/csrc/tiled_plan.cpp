@@ -85,7 +85,7 @@ const int MAX_PASS_ROUNDS = 32;
 
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
-    bool f32;
+    bool f32, lazy_diag;
 };
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
@@ -261,12 +261,17 @@ struct PassBuilder {
         const size_t n = ops.size();
         done.assign(n, 0);
         size_t left = n, first_open = 0;
+        const bool lazy_diag = M.lazy_diag;
         std::vector<uint32_t> roundR;             /* vector-bit set (tile-bit mask) per round */
         std::vector<std::vector<int>> round_ops;
         while (left || roundR.empty()) {
             if ((int)roundR.size() >= MAX_PASS_ROUNDS - 1) break;
             const bool is_first = roundR.empty();
-            uint32_t R = 0, ctrl_used = 0; int nR = 0;
+            uint32_t R = 0, ctrl_used = 0, ctrl_real = 0; int nR = 0;
+            uint32_t nonpack = 0;
+            for (int tb = 0; tb < M.T; tb++) if (tb != P) nonpack |= 1u << tb;
+            /* every round needs QSB_NVB vector bits that are neither controls of its gates nor (edge rounds) lane bits */
+            auto paddable = [&](uint32_t R_, uint32_t creal) { return popc(nonpack & ~F & ~(creal | R_)) + popc(R_) >= QSB_NVB; };
             uint64_t closed = 0;   /* qubits that took a bare X / CX in this round: nothing may follow on them here,
                                       so that the X is deferred into the store address instead of being computed */
             Blocker B; B.clear();
@@ -277,20 +282,23 @@ struct PassBuilder {
                 bool can = B.ok(o);
                 if (can && ((o.ctrl & closed) || (o.target >= 0 && ((closed >> o.target) & 1)))) can = false;
                 uint32_t cbits = 0; /* tile bits this op uses as (non-diagonal-gate) controls */
-                if (can && o.kind != C_PHASE) {
+                if (can && (o.kind != C_PHASE || lazy_diag)) {
+                    /* controls must stay thread-level; with lazy diagonals so must the qubits of a phase gate: it
+                     * then costs one entry of the per-thread phase list instead of arithmetic on the vectors */
                     for (uint64_t m = o.ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) cbits |= 1u << tb; }
-                    if (cbits & R) can = false;           /* controls must stay thread-level */
+                    if (cbits & R) can = false;
                 }
+                const uint32_t creal = (o.kind != C_PHASE) ? cbits : 0u;
                 if (can && o.target >= 0) {
                     int tb = tile_of_qubit[o.target];
-                    if (tb == P) { /* pack variants */ }
+                    if (tb == P) { if (!paddable(R, ctrl_real | creal)) can = false; }
                     else if (is_first && ((F >> tb) & 1)) can = false;
-                    else if ((R >> tb) & 1) {}
-                    else if (nR < QSB_NVB && !((ctrl_used >> tb) & 1)) { R |= 1u << tb; nR++; }
+                    else if ((R >> tb) & 1) { if (!paddable(R, ctrl_real | creal)) can = false; }
+                    else if (nR < QSB_NVB && !((ctrl_used >> tb) & 1) && paddable(R | (1u << tb), ctrl_real | creal)) { R |= 1u << tb; nR++; }
                     else can = false;
                 }
                 if (can) {
-                    mine.push_back((int)i); done[i] = 1; left--; ctrl_used |= cbits;
+                    mine.push_back((int)i); done[i] = 1; left--; ctrl_used |= cbits; ctrl_real |= creal;
                     if (o.kind == C_X && tile_of_qubit[o.target] != P) closed |= 1ULL << o.target;
                 }
                 else { B.block(o); if (B.full >= M.n) break; }
@@ -305,24 +313,26 @@ struct PassBuilder {
         const int nrounds = (int)roundR.size();
         hp.rounds.assign(nrounds, DevRound());
         hp.round_thr.assign(nrounds, {}); hp.round_vec.assign(nrounds, {});
-        std::vector<uint32_t> ctrl_of_round(nrounds, 0);
+        std::vector<uint32_t> ctrl_of_round(nrounds, 0), phase_of_round(nrounds, 0);
         for (int r = 0; r < nrounds; r++)
-            for (int i : round_ops[r]) if (ops[i].kind != C_PHASE)
-                for (uint64_t m = ops[i].ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) ctrl_of_round[r] |= 1u << tb; }
+            for (int i : round_ops[r])
+                for (uint64_t m = ops[i].ctrl; m; m &= m - 1) {
+                    int tb = tile_of_qubit[__builtin_ctzll(m)];
+                    if (tb >= 0 && tb != P) (ops[i].kind != C_PHASE ? ctrl_of_round[r] : phase_of_round[r]) |= 1u << tb;
+                }
         for (int r = 0; r < nrounds; r++) {
             uint32_t R = roundR[r];
             const bool edge = (r == 0 || r == nrounds - 1);
-            /* pad R with the highest free tile bits (never a control of this round) */
-            for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) {
-                if (tb == P || ((R >> tb) & 1) || ((ctrl_of_round[r] >> tb) & 1)) continue;
-                if (edge && ((F >> tb) & 1)) continue;
-                R |= 1u << tb;
-            }
-            for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) { /* cannot happen in practice: relax the control rule */
-                if (tb == P || ((R >> tb) & 1)) continue;
-                if (edge && ((F >> tb) & 1)) continue;
-                R |= 1u << tb;
-            }
+            /* pad R with the highest free tile bits: never a control of this round; the qubits of its phase
+             * gates only if nothing else is left (they then cost vector arithmetic instead of a thread phase) */
+            for (int tier = 0; tier < 2; tier++)
+                for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) {
+                    if (tb == P || ((R >> tb) & 1) || ((ctrl_of_round[r] >> tb) & 1)) continue;
+                    if (tier == 0 && lazy_diag && ((phase_of_round[r] >> tb) & 1)) continue;
+                    if (edge && ((F >> tb) & 1)) continue;
+                    R |= 1u << tb;
+                }
+            if (popc(R) < QSB_NVB) { qsb_set_error("internal: round %d cannot be padded to %d vector bits", r, QSB_NVB); return QSB_ERR_ARG; }
             std::vector<int8_t> vec, thr;
             for (int tb = 0; tb < M.T; tb++) if ((R >> tb) & 1) vec.push_back((int8_t)tb);
             /* thread bits: ascending; on edge rounds this puts the low physical bits on the lanes */
@@ -912,6 +922,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.n = n; M.prec = prec; M.g = g; M.nloc = nloc; M.rank = rank;
     M.f32 = (prec == QSB_F32);
     M.T = M.f32 ? QSB_T_F32 : QSB_T_F64;
+    M.lazy_diag = !(opt && opt->reserved[1] == 1);   /* reserved[1] = 1 switches lazy diagonals off (A/B runs) */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
     if (M.a < (M.f32 ? 3 : 2) || M.a > (M.f32 ? 6 : 5)) { qsb_set_error("low_bits %d unsupported for this precision", M.a); return QSB_ERR_ARG; }
