@@ -181,7 +181,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def make_sim(n):
-        sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local_rank, low_bits=args.low_bits)
+        sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local_rank, low_bits=args.low_bits,
+                          reserved=[0, args.no_lazy_diag, args.trim, args.cost_cap])
         if world > 1:
             from gpu_quantum_simulator_b200 import dist as qdist
             qdist.init_comm(sim, dist)
@@ -189,7 +190,7 @@ def run_ours(args):
 
     def measure(n, steps, warmup, with_clocks):
         """-> dict with the device-timed numbers of random_layered(n) and the live objects (sim, plan, circ)."""
-        circ = circuits.random_layered(n, DEPTH, SEED)
+        circ = circuits.random_layered(n, DEPTH, SEED) if args.workload == "layered" else circuits.qft(n)
         gates = q.gates_from_circuit(circ)
         sim = make_sim(n)
         plan = sim.plan(gates)
@@ -288,6 +289,15 @@ def run_ours(args):
                   "ms_per_step": m30["ms_per_step"], "passes": m30["pst"]["passes"], "rounds": m30["pst"]["rounds"],
                   "roofline": m30["roofline"]}
         plan, sim = m30["plan"], m30["sim"]
+        # the same circuit with the fusion depth capped (more, lighter passes): the HBM-bound regime of the kernel
+        if not args.cost_cap:
+            plan.close(); sim.close()
+            args.cost_cap = 12
+            ms = measure(30, max(3, min(args.steps, 10)), 3, False)
+            args.cost_cap = 0
+            at_30q["shallow_fusion"] = {"cost_cap": 12, "value": ms["value"], "unit": "gates/s", "ms_per_step": ms["ms_per_step"],
+                                        "passes": ms["pst"]["passes"], "rounds": ms["pst"]["rounds"], "roofline": ms["roofline"]}
+            plan, sim = ms["plan"], ms["sim"]
 
     line = None
     if rank == 0:
@@ -300,8 +310,8 @@ def run_ours(args):
         line = {"metric": "gates_per_sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if prec == q.F32 else "f64", "data": "synthetic",
-                "config": {"workload": f"random_layered_{n}q_d{DEPTH}", "qubits": n, "depth": DEPTH, "seed": SEED,
-                           "source_gates": len(circ), "passes": pst["passes"], "rounds": pst["rounds"], "swaps": pst["swaps"],
+                "config": {"workload": f"random_layered_{n}q_d{DEPTH}" if args.workload == "layered" else f"qft_{n}q_after_h_layer",
+                           "qubits": n, "depth": DEPTH, "seed": SEED, "source_gates": len(circ), "passes": pst["passes"], "rounds": pst["rounds"], "swaps": pst["swaps"],
                            "l2": "inputs larger than L2 (state = %d MiB per GPU)" % (n_loc_amps * amp_bytes >> 20),
                            "parallelism": f"shard{world}" if world > 1 else "single"},
                 "effective_gate_GBps": len(circ) * 2 * (1 << n) * amp_bytes / (ms_per_step * 1e-3) / 1e9,
@@ -327,6 +337,10 @@ def main():
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-30q", action="store_true")
+    ap.add_argument("--no-lazy-diag", type=int, default=0, help="planner A/B: 1 = lazy diagonals off")
+    ap.add_argument("--trim", type=int, default=0, help="planner A/B: k+1 = trim tail rounds with < k gates (1 = off)")
+    ap.add_argument("--cost-cap", type=int, default=0, help="fusion-depth sweep: SM cost cap per pass in gate units")
+    ap.add_argument("--workload", default="layered", choices=["layered", "qft"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

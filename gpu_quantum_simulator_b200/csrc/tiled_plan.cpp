@@ -86,6 +86,7 @@ const int MAX_PASS_ROUNDS = 32;
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
     bool f32, lazy_diag;
+    int trim_thin, cost_cap;
 };
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
@@ -254,7 +255,7 @@ struct PassBuilder {
 
     /* Build rounds for the ordered op list `ops` (all targets resident).  done[i] tells the
      * caller which ops were consumed (a pass is cut at MAX_PASS_ROUNDS). */
-    int build_rounds(const std::vector<COp> &ops, std::vector<char> &done)
+    int build_rounds(const std::vector<COp> &ops, std::vector<char> &done, bool more_passes_follow = false)
     {
         const int P = M.f32 ? 0 : -1;             /* pack tile bit */
         const uint32_t F = lane_forbidden();
@@ -262,10 +263,13 @@ struct PassBuilder {
         done.assign(n, 0);
         size_t left = n, first_open = 0;
         const bool lazy_diag = M.lazy_diag;
+        const int trim_thin = M.trim_thin;
+        double sm_cost = 0.0;
         std::vector<uint32_t> roundR;             /* vector-bit set (tile-bit mask) per round */
         std::vector<std::vector<int>> round_ops;
         while (left || roundR.empty()) {
             if ((int)roundR.size() >= MAX_PASS_ROUNDS - 1) break;
+            if (M.cost_cap > 0 && !roundR.empty() && more_passes_follow && sm_cost >= M.cost_cap) break;   /* fusion-depth limit (sweeps) */
             const bool is_first = roundR.empty();
             uint32_t R = 0, ctrl_used = 0, ctrl_real = 0; int nR = 0;
             uint32_t nonpack = 0;
@@ -302,6 +306,20 @@ struct PassBuilder {
                     if (o.kind == C_X && tile_of_qubit[o.target] != P) closed |= 1ULL << o.target;
                 }
                 else { B.block(o); if (B.full >= M.n) break; }
+            }
+            /* A heavy pass is bound by the SM, not by HBM: a thin tail round (fewer than `trim` gates with
+             * arithmetic) costs a full shared-memory exchange for almost no work.  Leave its ops to the
+             * next pass, whose tile is chosen around them. */
+            {
+                int useful = 0;
+                for (int i : mine) if (ops[i].kind != C_PHASE) useful++;
+                /* cost in units of one unit-form gate: ~5 for the exchange, the round tables and the pending scalar;
+                 * one HBM sweep hides roughly 17 such units (measured) */
+                if (trim_thin > 0 && sm_cost >= 34.0 && more_passes_follow && !roundR.empty() && useful < trim_thin) {
+                    for (int i : mine) { done[i] = 0; left++; }
+                    break;
+                }
+                sm_cost += 5.0 + useful;
             }
             while (first_open < n && done[first_open]) first_open++;
             roundR.push_back(R); round_ops.push_back(mine);
@@ -923,6 +941,8 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.f32 = (prec == QSB_F32);
     M.T = M.f32 ? QSB_T_F32 : QSB_T_F64;
     M.lazy_diag = !(opt && opt->reserved[1] == 1);   /* reserved[1] = 1 switches lazy diagonals off (A/B runs) */
+    M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
+    M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
     if (M.a < (M.f32 ? 3 : 2) || M.a > (M.f32 ? 6 : 5)) { qsb_set_error("low_bits %d unsupported for this precision", M.a); return QSB_ERR_ARG; }
@@ -970,7 +990,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         PassBuilder pb(M, perm);
         pb.set_tile(S, forced_pos, pos_map);
         std::vector<char> used;
-        int rc = pb.build_rounds(mine, used);
+        int rc = pb.build_rounds(mine, used, !allow_empty && mine_idx.size() < left);
         if (rc) return rc;
         size_t consumed = 0;
         for (size_t k = 0; k < mine_idx.size(); k++) if (used[k]) { done[mine_idx[k]] = 1; left--; consumed++; }

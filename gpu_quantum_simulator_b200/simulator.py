@@ -66,9 +66,13 @@ def gates_from_circuit(circ):
     return (Gate * len(out)).from_buffer(arr) if out else (Gate * 0)()
 
 
-def _options(precision, mode, low_bits, rank, world_size, device):
+def _options(precision, mode, low_bits, rank, world_size, device, reserved=None):
+    """reserved: planner tuning knobs (qsb_options_t.reserved): [0] min gates before a qubit exchange,
+    [1] 1 = lazy diagonals off, [2] k+1 = trim tail rounds with < k gates (1 = off), [3] fusion-depth cost cap."""
     o = Options()
     lib.qsb_options_default(C.byref(o))
+    for k, v in enumerate(reserved or ()):
+        o.reserved[k] = int(v)
     o.precision = precision
     o.mode = mode
     o.low_bits = low_bits
@@ -78,10 +82,10 @@ def _options(precision, mode, low_bits, rank, world_size, device):
     return o
 
 
-def plan_dry_run(num_qubits, gates, precision=F32, low_bits=0, world_size=1, rank=0):
+def plan_dry_run(num_qubits, gates, precision=F32, low_bits=0, world_size=1, rank=0, reserved=None):
     """Host-only scheduling statistics (no GPU needed)."""
     arr, n = _gate_array(gates)
-    o = _options(precision, MODE_TILED, low_bits, rank, world_size, -1)
+    o = _options(precision, MODE_TILED, low_bits, rank, world_size, -1, reserved)
     st = RunStats()
     check(lib.qsb_plan_dry_run(num_qubits, C.byref(o), arr, n, C.byref(st)))
     return st.as_dict()
@@ -105,9 +109,9 @@ class Plan:
 
 
 class Simulator:
-    def __init__(self, num_qubits, precision=F32, mode=MODE_TILED, low_bits=0, rank=0, world_size=1, device=-1):
+    def __init__(self, num_qubits, precision=F32, mode=MODE_TILED, low_bits=0, rank=0, world_size=1, device=-1, reserved=None):
         self._h = C.c_void_p()
-        o = _options(precision, mode, low_bits, rank, world_size, device)
+        o = _options(precision, mode, low_bits, rank, world_size, device, reserved)
         check(lib.qsb_create(C.byref(self._h), num_qubits, C.byref(o)))
         self.num_qubits, self.precision = num_qubits, precision
         self.rank, self.world_size = rank, world_size
