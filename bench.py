@@ -337,7 +337,7 @@ def main():
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-30q", action="store_true")
-    ap.add_argument("--no-lazy-diag", type=int, default=0, help="planner A/B: 1 = lazy diagonals off")
+    ap.add_argument("--no-lazy-diag", type=int, default=0, help="planner A/B: 2 = lazy diagonals on")
     ap.add_argument("--trim", type=int, default=0, help="planner A/B: k+1 = trim tail rounds with < k gates (1 = off)")
     ap.add_argument("--cost-cap", type=int, default=0, help="fusion-depth sweep: SM cost cap per pass in gate units")
     ap.add_argument("--workload", default="layered", choices=["layered", "qft"])

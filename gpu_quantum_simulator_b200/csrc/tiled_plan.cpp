@@ -85,7 +85,7 @@ const int MAX_PASS_ROUNDS = 32;
 
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
-    bool f32, lazy_diag;
+    bool f32, lazy_diag, defer_diag;
     int trim_thin, cost_cap;
 };
 
@@ -310,6 +310,32 @@ struct PassBuilder {
             /* A heavy pass is bound by the SM, not by HBM: a thin tail round (fewer than `trim` gates with
              * arithmetic) costs a full shared-memory exchange for almost no work.  Leave its ops to the
              * next pass, whose tile is chosen around them. */
+            /* Phase gates that touch a vector bit cost arithmetic on the vectors; as thread-level phases they are
+             * one entry of the pending-scalar list.  A phase gate that no later gate of this round depends on (no
+             * later target among its qubits) can wait for a round in which all its qubits are thread-level. */
+            if (M.defer_diag) {
+                std::vector<char> gone(mine.size(), 0);
+                bool any = false;
+                for (int k = (int)mine.size() - 1; k >= 0; k--) {
+                    const COp &o = ops[mine[k]];
+                    if (o.kind != C_PHASE) continue;
+                    uint32_t bits = 0;
+                    for (uint64_t m = o.ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) bits |= 1u << tb; }
+                    if (!(bits & R)) continue;
+                    bool needed = false;
+                    for (size_t k2 = k + 1; k2 < mine.size() && !needed; k2++) {
+                        if (gone[k2]) continue;
+                        const COp &o2 = ops[mine[k2]];
+                        if (o2.target >= 0 && ((o.ctrl >> o2.target) & 1)) needed = true;
+                    }
+                    if (!needed) { gone[k] = 1; any = true; done[mine[k]] = 0; left++; }
+                }
+                if (any) {
+                    std::vector<int> kept;
+                    for (size_t k = 0; k < mine.size(); k++) if (!gone[k]) kept.push_back(mine[k]);
+                    mine.swap(kept);
+                }
+            }
             {
                 int useful = 0;
                 for (int i : mine) if (ops[i].kind != C_PHASE) useful++;
@@ -343,13 +369,23 @@ struct PassBuilder {
             const bool edge = (r == 0 || r == nrounds - 1);
             /* pad R with the highest free tile bits: never a control of this round; the qubits of its phase
              * gates only if nothing else is left (they then cost vector arithmetic instead of a thread phase) */
-            for (int tier = 0; tier < 2; tier++)
-                for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) {
+            for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) {
+                if (tb == P || ((R >> tb) & 1) || (((ctrl_of_round[r] | phase_of_round[r]) >> tb) & 1)) continue;
+                if (edge && ((F >> tb) & 1)) continue;
+                R |= 1u << tb;
+            }
+            while (popc(R) < QSB_NVB) {   /* second choice: the phase-gate qubit with the fewest phase gates on it */
+                int best = -1, best_cnt = 1 << 30;
+                for (int tb = M.T - 1; tb >= 0; tb--) {
                     if (tb == P || ((R >> tb) & 1) || ((ctrl_of_round[r] >> tb) & 1)) continue;
-                    if (tier == 0 && lazy_diag && ((phase_of_round[r] >> tb) & 1)) continue;
                     if (edge && ((F >> tb) & 1)) continue;
-                    R |= 1u << tb;
+                    int cnt = 0;
+                    for (int i : round_ops[r]) if (ops[i].kind == C_PHASE && tile_qubit[tb] >= 0 && ((ops[i].ctrl >> tile_qubit[tb]) & 1)) cnt++;
+                    if (cnt < best_cnt) { best_cnt = cnt; best = tb; }
                 }
+                if (best < 0) break;
+                R |= 1u << best;
+            }
             if (popc(R) < QSB_NVB) { qsb_set_error("internal: round %d cannot be padded to %d vector bits", r, QSB_NVB); return QSB_ERR_ARG; }
             std::vector<int8_t> vec, thr;
             for (int tb = 0; tb < M.T; tb++) if ((R >> tb) & 1) vec.push_back((int8_t)tb);
@@ -940,8 +976,10 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.n = n; M.prec = prec; M.g = g; M.nloc = nloc; M.rank = rank;
     M.f32 = (prec == QSB_F32);
     M.T = M.f32 ? QSB_T_F32 : QSB_T_F64;
-    M.lazy_diag = !(opt && opt->reserved[1] == 1);   /* reserved[1] = 1 switches lazy diagonals off (A/B runs) */
+    M.lazy_diag = opt && opt->reserved[1] == 2;      /* reserved[1] = 2: keep the qubits of phase gates thread-level (A/B runs;
+                                                        same speed on random circuits, 2.4x more rounds on QFT) */
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
+    M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */

@@ -68,7 +68,7 @@ def gates_from_circuit(circ):
 
 def _options(precision, mode, low_bits, rank, world_size, device, reserved=None):
     """reserved: planner tuning knobs (qsb_options_t.reserved): [0] min gates before a qubit exchange,
-    [1] 1 = lazy diagonals off, [2] k+1 = trim tail rounds with < k gates (1 = off), [3] fusion-depth cost cap."""
+    [1] 2 = lazy diagonals on, [2] k+1 = trim tail rounds with < k gates (1 = off), [3] fusion-depth cost cap."""
     o = Options()
     lib.qsb_options_default(C.byref(o))
     for k, v in enumerate(reserved or ()):
