@@ -143,12 +143,11 @@ enum {              /* slot forms (one-hot bytes, so the kernel dispatches with 
     S_SKIP = 0,
     S_UNIT_R = 1,   /* real unit form  a[[1,p],[q,r]]: x0 += p x1; x1 = k x1 + q x0     S: p q k a */
     S_UNIT_I = 2,   /* rx unit form    a[[1,ip],[iq,r]]                                 S: p q k a */
-    S_FULL_R = 4,   /* real 2x2                                               S: m00 m01 m10 m11 */
     S_DIAG = 8,     /* phase on the vectors whose bit is set                           S: pr pi   */
     S_XDEF = 16,    /* X (swap of the two halves) under the predicate, DEFERRED: the thread only
                        flips bit j of its vector-index mask; the swap happens for free in the
                        address of the next shared / global store.  Last op on its bit in a round. */
-    S_FULL_I = 32,  /* [[a, ib],[ic, d]]                                               S: a b c d */
+    /* matrices that cannot take a unit form (rare after pivoting) run as G_FULL_G specials */
 };
 /* A group (16-byte units): [0] x = form of slot 0 | slot 1 << 8 | slot 2 << 16 | slot 3 << 24
  *                          [1] the four predicate masks: (tw & pmask) == pmask

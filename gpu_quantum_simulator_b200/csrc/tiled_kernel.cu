@@ -122,32 +122,6 @@ __device__ __forceinline__ void unit_v(typename VT<R>::V (&re)[NV], typename VT<
     }
 }
 
-/* full 2x2 on vector bit VB.  FORM 1: real [[a,b],[c,d]]; 2: [[a, ib],[ic, d]].
- * Cross terms go to temporaries first, then each amplitude is updated in place. */
-template <typename R, int VB, int FORM>
-__device__ __forceinline__ void full_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::S as, typename VT<R>::S bs, typename VT<R>::S cs, typename VT<R>::S ds)
-{
-    typedef VT<R> T; typedef typename T::V V;
-    const V a = T::bc(as), b = T::bc(bs), cc = T::bc(cs), d = T::bc(ds);
-    if (FORM == 1) {
-#pragma unroll
-        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
-            const int w = v | (1 << VB);
-            const V t0 = T::mul(b, re[w]), t1 = T::mul(b, im[w]), t2 = T::mul(cc, re[v]), t3 = T::mul(cc, im[v]);
-            T::updd(re[v], a, t0, t2); T::updd(im[v], a, t1, t3);
-            T::updd(re[w], d, t2, t0); T::updd(im[w], d, t3, t1);
-        }
-    } else {
-#pragma unroll
-        for (int v = 0; v < NV; v++) if (!((v >> VB) & 1)) {
-            const int w = v | (1 << VB);
-            const V t0 = T::nmul(b, im[w]), t1 = T::mul(b, re[w]), t2 = T::nmul(cc, im[v]), t3 = T::mul(cc, re[v]);
-            T::updd(re[v], a, t0, t3); T::updd(im[v], a, t1, t2);
-            T::updd(re[w], d, t2, t1); T::updd(im[w], d, t3, t0);
-        }
-    }
-}
-
 /* complex 2x2 on vector bit VB; coefficients are V-typed (lane pairs in f32) */
 template <typename R, int VB>
 __device__ __forceinline__ void gen_v(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], const typename VT<R>::V (&m)[8])
@@ -172,6 +146,12 @@ __device__ __forceinline__ void diag_v(typename VT<R>::V (&re)[NV], typename VT<
 {
 #pragma unroll
     for (int v = 0; v < NV; v++) if ((v >> VB) & 1) cmul_inplace<R>(re[v], im[v], pr, pi);
+}
+template <typename R, int MASK>
+__device__ __forceinline__ void diag_mask(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::V pr, typename VT<R>::V pi)
+{
+#pragma unroll
+    for (int v = 0; v < NV; v++) if ((v & MASK) == MASK) cmul_inplace<R>(re[v], im[v], pr, pi);
 }
 /* (pr, pi) of a diagonal op: set 0, or set 1 for the threads that pass (uniform loads + select) */
 template <typename R>
@@ -254,9 +234,7 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
     const S c0 = pred ? s.d[0] : s.c[0], c1 = pred ? s.d[1] : s.c[1], c2 = pred ? s.d[2] : s.c[2], c3 = pred ? s.d[3] : s.c[3];
     if (form & S_UNIT_R) { unit_v<R, VB, false>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
     else if (form & S_UNIT_I) { unit_v<R, VB, true>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
-    else if (form & S_FULL_R) full_v<R, VB, 1>(re, im, c0, c1, c2, c3);
     else if (form & S_DIAG) diag_v<R, VB>(re, im, T::bc(c0), T::bc(c1));
-    else if (form & S_FULL_I) full_v<R, VB, 2>(re, im, c0, c1, c2, c3);
     else xm ^= pred ? (1u << VB) : 0u;   /* S_XDEF */
 }
 
@@ -356,8 +334,12 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 case G_DIAG_GEN: {
                     const uint32_t vmask = (h.x >> 12) & 0xfu;
                     V pr, pi; load_phase<R>(c, two, s1, pr, pi);
-#pragma unroll
-                    for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) cmul_inplace<R>(re[v], im[v], pr, pi);
+                    switch (vmask) {   /* uniform: one static variant per mask, only the matching vectors are touched */
+#define DGEN(MASK) case MASK: diag_mask<R, MASK>(re, im, pr, pi); break;
+                    DGEN(3) DGEN(5) DGEN(6) DGEN(7) DGEN(9) DGEN(10) DGEN(11) DGEN(12) DGEN(13) DGEN(14) DGEN(15)
+#undef DGEN
+                    default: break;
+                    }
                     break;
                 }
                 case G_MATP_R: {

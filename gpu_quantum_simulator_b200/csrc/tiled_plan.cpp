@@ -827,8 +827,6 @@ struct PassBuilder {
                 if (leq) switch (code) {
                     case OP_MAT_U: sform = S_UNIT_R; break;
                     case OP_MAT_UI: sform = S_UNIT_I; break;
-                    case OP_MAT_R: sform = S_FULL_R; break;
-                    case OP_MAT_I: sform = S_FULL_I; break;
                     case OP_DIAG_V: sform = S_DIAG; break;
                     case OP_XDEF: sform = S_XDEF; break;
                     default: break;
@@ -842,8 +840,6 @@ struct PassBuilder {
                         switch (sform) {
                         case S_UNIT_R: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(0)); put_s(o, C(1)); put_s(o, C(2)); put_s(o, C(3)); } break;
                         case S_UNIT_I: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(0)); put_s(o, C(2)); put_s(o, C(4)); put_s(o, C(5)); } break;
-                        case S_FULL_R: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 1); } else { put_s(o, C(2)); put_s(o, C(0)); put_s(o, C(1)); put_s(o, C(3)); } break;
-                        case S_FULL_I: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 1); } else { put_s(o, C(4)); put_s(o, C(1)); put_s(o, C(3)); put_s(o, C(5)); } break;
                         case S_DIAG: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 0); } else { put_s(o, C(0)); put_s(o, C(1)); put_s(o, 0); put_s(o, 0); } break;
                         default: put_s(o, 0); put_s(o, 0); put_s(o, 0); put_s(o, 0); break;
                         }
