@@ -23,9 +23,10 @@ struct qsb_sim {
     void *d_scratch = nullptr; /* small device scratch (reductions)             */
     qsb_run_stats_t last{};
     void *comm = nullptr;    /* ncclComm_t                                      */
-    /* peer access (filled by qsb_comm_init) */
-    void *peer_state[64] = {nullptr};
-    void *peer_state2[64] = {nullptr};
+    /* peer shards mapped through CUDA IPC (filled by qsb_comm_init): a fused-exchange pass stores into them */
+    bool peers_ok = false;
+    void *peer_state[16] = {nullptr};    /* rank r's current state buffer  (own rank: == state)  */
+    void *peer_state2[16] = {nullptr};   /* rank r's second buffer         (own rank: == state2) */
 };
 
 struct qsb_plan {

@@ -45,7 +45,7 @@
 #define QSB_MAX_RUNS 16
 #define QSB_BLOB_SMALL 4000    /* pass descriptor sizes (kernel parameter)   */
 #define QSB_BLOB_MEDIUM 12000
-#define QSB_BLOB_LARGE 32000
+#define QSB_BLOB_LARGE 31744   /* + two pointers + the peer table stay below the 32764-byte parameter limit */
 
 /* ---- op codes ---------------------------------------------------------- */
 enum {
@@ -211,7 +211,15 @@ struct GPass {
     uint64_t st_thr[QSB_TB];   /*                                    last-round scatter               */
     uint64_t ld_vec[QSB_NV];   /* local BYTE offset of vector v                                       */
     uint64_t st_vec[QSB_NV];
+    uint64_t st_fixed;         /* constant part of the scatter offset (fused exchange: the writer's rank
+                                  on the top local positions)                                         */
+    /* Scatter offsets are  local byte offset | destination-rank contribution << QSB_RANK_SHIFT.  The rank
+     * field is non-zero only in a fused-exchange pass (peer stores), whose kernel variant adds the fields
+     * up and indexes the peer-pointer table with the result. */
 };
+#define QSB_RANK_SHIFT 48
+#define QSB_MAX_PEERS 16
+struct PeerTab { char *p[QSB_MAX_PEERS]; uint64_t shard_bytes; uint32_t world, pad; };
 
 /* ---- host-side plan ----------------------------------------------------- */
 struct HostOp {              /* precision-independent; lane-expanded fp64 coefficients */
@@ -234,7 +242,8 @@ struct HostPass {
     std::vector<std::vector<int8_t>> round_thr; /* per round: thread bit j -> tile bit */
     std::vector<std::vector<int8_t>> round_vec; /* per round: vector bit j -> tile bit */
     std::vector<uint32_t> round_op_begin, round_op_count; /* indices into ops */
-    bool is_swap = false;
+    bool is_swap = false;                /* exchange marker: NCCL all-to-all of contiguous chunks             */
+    bool fused_swap = false;             /* this pass scatters into the peers' shards: it IS the exchange      */
     int n_source_ops = 0;
 };
 

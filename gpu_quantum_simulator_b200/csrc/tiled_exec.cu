@@ -13,12 +13,15 @@
  * loaded at run time (dlopen) so the library has no link-time dependency on it.
  */
 #include <dlfcn.h>
+#include <stdio.h>
+#include <algorithm>
+#include <utility>
 #include <string.h>
 
 #include "sim.h"
 #include "tiled.h"
 
-int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst);
+int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst, const PeerTab *peers);
 
 int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
                      const std::vector<COp> &cops, const double gphase[2], bool /*with_device*/,
@@ -30,6 +33,7 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
     uint64_t n_ops = 0, n_rounds = 0, sweeps = 0, swaps = 0;
     for (auto &hp : p->passes) {
         if (hp.is_swap) { swaps++; continue; }
+        if (hp.fused_swap) swaps++;
         sweeps++; n_ops += hp.ops.size(); n_rounds += hp.rounds.size();
     }
     const uint64_t local_bytes = ((uint64_t)1 << nloc) * amp_bytes(prec);
@@ -57,6 +61,8 @@ struct NcclApi {
     int (*CommDestroy)(qsb_nccl_comm_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, qsb_nccl_comm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, qsb_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, qsb_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, qsb_nccl_comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -73,7 +79,7 @@ static int nccl_load()
 #define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { qsb_set_error("NCCL symbol %s missing", name); return QSB_ERR_COMM; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-    SYM(GetErrorString, "ncclGetErrorString")
+    SYM(GetErrorString, "ncclGetErrorString") SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce")
 #undef SYM
     g_nccl.lib = h;
     return QSB_OK;
@@ -106,11 +112,49 @@ extern "C" int qsb_comm_init(qsb_t *s, const void *id128)
         cudaError_t e = cudaMalloc(&s->state2, s->state_bytes);
         if (e != cudaSuccess) { qsb_set_error("Malloc error: exchange buffer of %zu bytes (%s)", s->state_bytes, cudaGetErrorString(e)); (void)cudaGetLastError(); return QSB_ERR_NOMEM; }
     }
+    /* Map every peer's two shard buffers (CUDA IPC over NVLink peer access): the fused-exchange passes store
+     * straight into them.  If the mapping is not possible the planner keeps the NCCL all-to-all. */
+    s->peers_ok = false;
+    if (s->world <= QSB_MAX_PEERS && !(s->opt.reserved[5] == 2)) {
+        struct Handles { cudaIpcMemHandle_t a, b; };
+        Handles mine; memset(&mine, 0, sizeof mine);
+        bool ok = cudaIpcGetMemHandle(&mine.a, s->state) == cudaSuccess && cudaIpcGetMemHandle(&mine.b, s->state2) == cudaSuccess;
+        (void)cudaGetLastError();
+        char *dbuf = (char *)s->d_scratch;                       /* 1 MiB scratch: [mine | all] */
+        std::vector<Handles> all(s->world);
+        QSB_CUDA(cudaMemcpyAsync(dbuf, &mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+        QSB_NCCL(g_nccl.AllGather(dbuf, dbuf + 4096, sizeof mine, 1 /* ncclUint8 */, c, s->stream));
+        QSB_CUDA(cudaMemcpyAsync(all.data(), dbuf + 4096, sizeof(Handles) * s->world, cudaMemcpyDeviceToHost, s->stream));
+        QSB_CUDA(cudaStreamSynchronize(s->stream));
+        for (int r = 0; r < s->world && ok; r++) {
+            if (r == s->rank) { s->peer_state[r] = s->state; s->peer_state2[r] = s->state2; continue; }
+            if (cudaIpcOpenMemHandle(&s->peer_state[r], all[r].a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&s->peer_state2[r], all[r].b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+        }
+        (void)cudaGetLastError();
+        /* every rank must take the same decision: the plans have to agree on where the exchanges are */
+        int *flag = (int *)(dbuf + 65536);
+        const int mine_ok = ok ? 1 : 0; int all_ok = 0;
+        QSB_CUDA(cudaMemcpyAsync(flag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        QSB_NCCL(g_nccl.AllReduce(flag, flag + 1, 1, 2 /* ncclInt32 */, 3 /* ncclMin */, c, s->stream));
+        QSB_CUDA(cudaMemcpyAsync(&all_ok, flag + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        QSB_CUDA(cudaStreamSynchronize(s->stream));
+        s->peers_ok = all_ok == 1;
+    }
+    if (s->peers_ok && s->opt.reserved[5] == 0) s->opt.reserved[5] = 1;   /* plans made from now on fuse the exchanges */
     return QSB_OK;
 }
 
 void tiled_comm_destroy(qsb_sim *s)
 {
+    if (s->peers_ok) {
+        for (int r = 0; r < s->world; r++) if (r != s->rank) {
+            /* peer_state / peer_state2 may have traded places: close both mappings whatever their current role */
+            if (s->peer_state[r]) cudaIpcCloseMemHandle(s->peer_state[r]);
+            if (s->peer_state2[r]) cudaIpcCloseMemHandle(s->peer_state2[r]);
+        }
+        s->peers_ok = false;
+    }
     if (s->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy((qsb_nccl_comm_t)s->comm); s->comm = nullptr; }
 }
 
@@ -129,6 +173,7 @@ static int exchange(qsb_sim *s)
     QSB_NCCL(g_nccl.GroupEnd());
     QSB_CUDA(cudaMemcpyAsync(dst + (size_t)s->rank * chunk, src + (size_t)s->rank * chunk, chunk, cudaMemcpyDeviceToDevice, s->stream));
     void *t = s->state; s->state = s->state2; s->state2 = t;
+    if (s->peers_ok) for (int r = 0; r < s->world; r++) std::swap(s->peer_state[r], s->peer_state2[r]);
     return QSB_OK;
 }
 
@@ -146,7 +191,27 @@ int tiled_execute(qsb_sim *s, TiledPlan *p)
             ev.push_back(a); ev.push_back(b);
             continue;
         }
-        int rc = tiled_launch_pass(s, p, k, s->state, s->state);
+        if (p->passes[k].fused_swap) {
+            /* the pass scatters into every rank's SECOND buffer; once all ranks are through (an all-reduce on the
+             * stream is the barrier) the buffers trade places everywhere */
+            if (!s->peers_ok) { qsb_set_error("plan has fused exchanges but the peer shards are not mapped"); return QSB_ERR_COMM; }
+            cudaEvent_t a, b;
+            QSB_CUDA(cudaEventCreate(&a)); QSB_CUDA(cudaEventCreate(&b));
+            PeerTab pt; memset(&pt, 0, sizeof pt);
+            for (int r = 0; r < s->world; r++) pt.p[r] = (char *)s->peer_state2[r];
+            pt.shard_bytes = s->state_bytes; pt.world = (uint32_t)s->world;
+            int rc = tiled_launch_pass(s, p, k, s->state, s->state2, &pt);
+            if (rc) return rc;
+            QSB_CUDA(cudaEventRecord(a, s->stream));
+            int *flag = (int *)((char *)s->d_scratch + 65536);
+            QSB_NCCL(g_nccl.AllReduce(flag, flag + 1, 1, 2 /* ncclInt32 */, 3 /* ncclMin */, (qsb_nccl_comm_t)s->comm, s->stream));
+            QSB_CUDA(cudaEventRecord(b, s->stream));
+            ev.push_back(a); ev.push_back(b);
+            std::swap(s->state, s->state2);
+            for (int r = 0; r < s->world; r++) std::swap(s->peer_state[r], s->peer_state2[r]);
+            continue;
+        }
+        int rc = tiled_launch_pass(s, p, k, s->state, s->state, nullptr);
         if (rc) return rc;
     }
     s->perm = p->end_perm;

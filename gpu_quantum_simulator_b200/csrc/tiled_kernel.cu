@@ -238,9 +238,11 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
     else xm ^= pred ? (1u << VB) : 0u;   /* S_XDEF */
 }
 
-template <typename R, int BLOB>
+/* PEER: the scatter of a fused-exchange pass -- every amplitude goes straight into the shard of the rank
+ * named by its victim bits (peer memory over NVLink), so the qubit exchange costs no extra sweep. */
+template <typename R, int BLOB, bool PEER>
 __global__ void __launch_bounds__(QSB_THREADS, 2)
-k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst)
+k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst, const __grid_constant__ PeerTab peers)
 {
     typedef VT<R> T; typedef typename T::V V; typedef typename T::S S;
     static_assert(QSB_NVB == 4, "the interpreter is written for 4 vector bits");
@@ -419,43 +421,67 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 
     /* ---- scatter ---- */
     {
-        uint64_t off = outer * AMP, xoff = 0;
+        uint64_t off = outer * AMP + P.st_fixed, xoff = 0;
 #pragma unroll
         for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) off += P.st_thr[j];
 #pragma unroll
         for (int b = 0; b < QSB_NVB; b++) if ((xm >> b) & 1) xoff ^= P.st_vec[1 << b];
-        char *p = dst + off;
+        if (!PEER) {
+            char *p = dst + off;
 #pragma unroll
-        for (int v = 0; v < NV; v++) IO<R>::gstore(p + (P.st_vec[v] ^ xoff), re[v], im[v]);
+            for (int v = 0; v < NV; v++) IO<R>::gstore(p + (P.st_vec[v] ^ xoff), re[v], im[v]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                const uint64_t t = off + (P.st_vec[v] ^ xoff);            /* fields add without carries */
+                char *p = peers.p[t >> QSB_RANK_SHIFT] + (t & ((1ULL << QSB_RANK_SHIFT) - 1));
+#ifdef QSB_DEBUG_PEER
+                if ((t >> QSB_RANK_SHIFT) >= peers.world || (t & ((1ULL << QSB_RANK_SHIFT) - 1)) + 16 > peers.shard_bytes || !peers.p[t >> QSB_RANK_SHIFT]) {
+                    if (threadIdx.x == 0 || true) printf("bad peer store: block %u tid %u v %d t %llx off %llx stvec %llx xoff %llx base %p\n", blockIdx.x, tid, v,
+                                               (unsigned long long)t, (unsigned long long)off, (unsigned long long)P.st_vec[v], (unsigned long long)xoff, (void *)peers.p[(t >> QSB_RANK_SHIFT) & 15]);
+                    continue;
+                }
+#endif
+                IO<R>::gstore(p, re[v], im[v]);
+            }
+        }
     }
 }
 
 /* ------------------------------------------------------------------ launching */
-template <typename R, int BLOB>
-static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst)
+template <typename R, int BLOB, bool PEER>
+static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab &peers)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         attr_set = true;
     }
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
     const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
-    k_tile_pass<R, BLOB><<<(unsigned)hp.hdr.n_tiles, QSB_THREADS, 65536, s->stream>>>(*blob, (const char *)src, (char *)dst);
+    k_tile_pass<R, BLOB, PEER><<<(unsigned)hp.hdr.n_tiles, QSB_THREADS, 65536, s->stream>>>(*blob, (const char *)src, (char *)dst, peers);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
 }
 
 template <typename R>
-static int launch_pass(qsb_sim *s, const HostPass &hp, const void *src, void *dst)
+static int launch_pass(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab *peers)
 {
-    if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL>(s, hp, src, dst);
-    if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM>(s, hp, src, dst);
-    return launch_one<R, QSB_BLOB_LARGE>(s, hp, src, dst);
+    if (peers) {
+        /* the descriptor and the peer table together must stay below the 32764-byte kernel-parameter limit */
+        if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL, true>(s, hp, src, dst, *peers);
+        if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM, true>(s, hp, src, dst, *peers);
+        return launch_one<R, QSB_BLOB_LARGE, true>(s, hp, src, dst, *peers);
+    }
+    static const PeerTab none = {};
+    if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL, false>(s, hp, src, dst, none);
+    if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM, false>(s, hp, src, dst, none);
+    return launch_one<R, QSB_BLOB_LARGE, false>(s, hp, src, dst, none);
 }
 
-int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst)
+/* peers: the destination shards of a fused-exchange pass (indexed by rank), or null */
+int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst, const PeerTab *peers)
 {
     const HostPass &hp = p->passes[k];
-    return s->prec == QSB_F32 ? launch_pass<float>(s, hp, src, dst) : launch_pass<double>(s, hp, src, dst);
+    return s->prec == QSB_F32 ? launch_pass<float>(s, hp, src, dst, peers) : launch_pass<double>(s, hp, src, dst, peers);
 }

@@ -87,6 +87,7 @@ struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
     bool f32, lazy_diag, defer_diag;
     int trim_thin, cost_cap;
+    bool fused_exchange;
 };
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
@@ -210,8 +211,13 @@ struct PassBuilder {
     /* choose the tile from the set of resident logical qubits (+ positions that must be resident);
      * pos_map, if given, relocates physical positions inside the tile (in-tile qubit permutation:
      * free, because the tile is gathered and scattered anyway). */
-    void set_tile(uint64_t resident, uint64_t forced_pos = 0, const int8_t *pos_map = nullptr)
+    void set_tile(uint64_t resident, uint64_t forced_pos = 0, const int8_t *pos_map = nullptr, bool fuse_exchange = false)
     {
+        /* fuse_exchange: the pass also performs the global <-> local qubit exchange -- after the in-tile
+         * permutation the top g local positions trade places with the rank bits, i.e. every amplitude is
+         * scattered straight into the shard of the rank named by its victim bits (peer memory over NVLink),
+         * at the local address whose top g bits are the WRITER's rank. */
+        auto exch = [&](int p) { return (fuse_exchange && p >= M.nloc - M.g && p < M.nloc) ? p + M.g : p; };
         uint64_t posmask = forced_pos;
         for (int q = 0; q < M.n; q++) if ((resident >> q) & 1) posmask |= 1ULL << perm.pos[q];
         for (int p = 0; p < M.a; p++) posmask |= 1ULL << p;              /* contiguous low segment */
@@ -224,7 +230,7 @@ struct PassBuilder {
         int j = 0;
         for (int p = 0; p < M.nloc + M.g; p++) if ((posmask >> p) & 1) {
             hp.tile_src[j] = (int8_t)p;
-            hp.tile_dst[j] = pos_map ? pos_map[p] : (int8_t)p;
+            hp.tile_dst[j] = (int8_t)exch(pos_map ? pos_map[p] : p);
             tile_qubit[j] = inv[p];
             if (inv[p] >= 0) tile_of_qubit[inv[p]] = j;
             j++;
@@ -242,6 +248,11 @@ struct PassBuilder {
         hp.hdr.src_fixed = hp.hdr.dst_fixed = (uint64_t)M.rank << M.nloc;
         hp.hdr.nloc = M.nloc;
         hp.hdr.out_of_place = 0;
+        hp.fused_swap = fuse_exchange;
+        if (fuse_exchange) {
+            hp.hdr.dst_fixed = (uint64_t)M.rank << (M.nloc - M.g);   /* the old rank bits land on the top local positions */
+            hp.hdr.out_of_place = 1;
+        }
     }
 
     /* tile bits that must be thread (lane) bits in the first / last round */
@@ -738,15 +749,19 @@ struct PassBuilder {
         memcpy(gp.run_start, hp.hdr.run_start, sizeof gp.run_start);
         memcpy(gp.run_len, hp.hdr.run_len, sizeof gp.run_len);
         gp.src_fixed = hp.hdr.src_fixed; gp.n_tiles = hp.hdr.n_tiles; gp.nloc = hp.hdr.nloc;
+        /* destination index bits -> local byte offset | rank contribution << QSB_RANK_SHIFT (fused exchange only) */
+        auto enc_dst = [&](uint64_t bits) { return ((bits & loc_mask) * AMP) | ((bits >> M.nloc) << QSB_RANK_SHIFT); };
         for (int j = 0; j < QSB_TB; j++) {
             gp.ld_thr[j] = (hp.rounds[0].thr[j].gidx & loc_mask) * AMP;
-            gp.st_thr[j] = (hp.hdr.dst_thr[j] & loc_mask) * AMP;
+            gp.st_thr[j] = hp.fused_swap ? enc_dst(hp.hdr.dst_thr[j]) : (hp.hdr.dst_thr[j] & loc_mask) * AMP;
         }
         for (int v = 0; v < QSB_NV; v++) {
             uint64_t l = 0, t = 0;
             for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) { l |= hp.rounds[0].vec[b].gidx; t |= hp.hdr.dst_vec[b]; }
-            gp.ld_vec[v] = (l & loc_mask) * AMP; gp.st_vec[v] = (t & loc_mask) * AMP;
+            gp.ld_vec[v] = (l & loc_mask) * AMP;
+            gp.st_vec[v] = hp.fused_swap ? enc_dst(t) : (t & loc_mask) * AMP;
         }
+        gp.st_fixed = hp.fused_swap ? (hp.hdr.dst_fixed & loc_mask) * AMP : 0;
 
         std::vector<GRound> gr(nrounds);
         std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds);
@@ -976,6 +991,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                                                         same speed on random circuits, 2.4x more rounds on QFT) */
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
+    M.fused_exchange = g > 0 && opt && opt->reserved[5] == 1;   /* reserved[5] = 1: exchanges fused into the preceding pass (peer stores) */
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
@@ -1000,11 +1016,12 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     const int SWAP_MIN_OPS = opt && opt->reserved[0] > 0 ? opt->reserved[0] : 10;
 
     /* greedy op collection for one pass.  S0/n0: qubits / slots already resident. */
-    auto collect = [&](uint64_t S0, int n0, std::vector<COp> &mine, std::vector<size_t> &mine_idx, uint64_t &S_out) {
+    auto collect = [&](uint64_t S0, int n0, std::vector<COp> &mine, std::vector<size_t> &mine_idx, uint64_t &S_out, int op_limit = 0) {
         uint64_t S = S0; int nS = n0;
         Blocker B; B.clear();
         mine.clear(); mine_idx.clear();
-        for (size_t i = first_open; i < N && (int)mine.size() < max_pass_ops(M.f32); i++) {
+        const int max_ops = op_limit > 0 ? op_limit : max_pass_ops(M.f32);
+        for (size_t i = first_open; i < N && (int)mine.size() < max_ops; i++) {
             if (done[i]) continue;
             const COp &o = cops[i];
             bool can = B.ok(o);
@@ -1020,9 +1037,9 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         S_out = S;
     };
     auto emit_pass = [&](uint64_t S, uint64_t forced_pos, const int8_t *pos_map, const std::vector<COp> &mine,
-                         const std::vector<size_t> &mine_idx, bool allow_empty) -> int {
+                         const std::vector<size_t> &mine_idx, bool allow_empty, bool fuse_exchange = false) -> int {
         PassBuilder pb(M, perm);
-        pb.set_tile(S, forced_pos, pos_map);
+        pb.set_tile(S, forced_pos, pos_map, fuse_exchange);
         std::vector<char> used;
         int rc = pb.build_rounds(mine, used, !allow_empty && mine_idx.size() < left);
         if (rc) return rc;
@@ -1093,19 +1110,24 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             pos_map[pv] = (int8_t)pt; pos_map[pt] = (int8_t)pv;
             forced |= (1ULL << pv) | (1ULL << pt);
         }
+        const bool fuse = M.fused_exchange;
+        if (fuse) forced |= top_pos;   /* the victim bits select the destination rank: they must be tile bits */
         if (forced) {
             /* resident set: low qubits + the qubits living on the forced positions */
             uint64_t S0 = lowS; int n0 = M.a;
             for (int q = 0; q < n; q++) if ((forced >> perm.pos[q]) & 1) { if (!((S0 >> q) & 1)) S0 |= 1ULL << q; }
             n0 += popc(forced);   /* forced positions are >= a: each takes a slot, qubit or padding */
-            collect(S0, n0, mine, mine_idx, S);
-            int rc = emit_pass(S, forced, pos_map, mine, mine_idx, true);
+            /* a fused-exchange pass also carries the peer table as a kernel parameter: keep its descriptor in the medium class */
+            collect(S0, n0, mine, mine_idx, S, fuse ? max_pass_ops(M.f32) / 3 : 0);
+            int rc = emit_pass(S, forced, pos_map, mine, mine_idx, true, fuse);
             if (rc) return rc;
         }
-        /* exchange marker: top g local positions <-> rank bits */
-        HostPass sw; memset(&sw.hdr, 0, sizeof sw.hdr);
-        sw.is_swap = true; sw.hdr.nloc = nloc;
-        plan->passes.push_back(std::move(sw));
+        if (!fuse) {
+            /* exchange marker: top g local positions <-> rank bits (NCCL all-to-all of contiguous chunks) */
+            HostPass sw; memset(&sw.hdr, 0, sizeof sw.hdr);
+            sw.is_swap = true; sw.hdr.nloc = nloc;
+            plan->passes.push_back(std::move(sw));
+        }
         for (int q = 0; q < n; q++) {
             int p = perm.pos[q];
             if (p >= nloc) perm.pos[q] = (int8_t)(p - g);

@@ -197,6 +197,10 @@ def _hc():
     L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck")))
     L.qsb_hostcheck_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Gate), C.c_size_t]
     L.qsb_hostcheck_plan.restype = C.c_void_p
+    L.qsb_hostcheck_plan_fused.argtypes = L.qsb_hostcheck_plan.argtypes
+    L.qsb_hostcheck_plan_fused.restype = C.c_void_p
+    L.qsb_hostcheck_step_kind.argtypes = [C.c_void_p, C.c_int]
+    L.qsb_hostcheck_run_step_fused.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     L.qsb_hostcheck_num_steps.argtypes = [C.c_void_p]
     L.qsb_hostcheck_step_is_swap.argtypes = [C.c_void_p, C.c_int]
     L.qsb_hostcheck_nloc.argtypes = [C.c_void_p]
@@ -208,9 +212,10 @@ def _hc():
 class ShardedHostRun:
     """One rank of a sharded schedule, interpreted on the host.  Exchanges are the caller's job."""
 
-    def __init__(self, gates, n, world, rank, precision=32, low_bits=0, swap_min_ops=0):
+    def __init__(self, gates, n, world, rank, precision=32, low_bits=0, swap_min_ops=0, fused=False):
         self.L = _hc()
-        self.h = self.L.qsb_hostcheck_plan(n, precision, low_bits, world, rank, swap_min_ops, gates, len(gates))
+        plan = self.L.qsb_hostcheck_plan_fused if fused else self.L.qsb_hostcheck_plan
+        self.h = plan(n, precision, low_bits, world, rank, swap_min_ops, gates, len(gates))
         if not self.h:
             raise RuntimeError("hostcheck planning failed")
         self.n, self.world, self.rank = n, world, rank
@@ -223,8 +228,17 @@ class ShardedHostRun:
     def is_swap(self, i):
         return bool(self.L.qsb_hostcheck_step_is_swap(self.h, i))
 
+    def kind(self, i):
+        """0 ordinary pass, 1 exchange marker, 2 fused-exchange pass"""
+        return self.L.qsb_hostcheck_step_kind(self.h, i)
+
     def run(self, i):
         assert self.L.qsb_hostcheck_run_step(self.h, i, self.shard.ctypes.data) == 0
+
+    def run_fused(self, i, new_shards):
+        """new_shards: list of the P destination shards (complex128 arrays), written in place"""
+        ptrs = (C.c_void_p * len(new_shards))(*[a.ctypes.data for a in new_shards])
+        assert self.L.qsb_hostcheck_run_step_fused(self.h, i, self.shard.ctypes.data, ptrs) == 0
 
     def chunks(self):
         return self.shard.reshape(self.world, -1)
@@ -247,11 +261,18 @@ def gather_logical(shards, perm, n, nloc):
     return full[phys]
 
 
-def sharded_host_run(circ_gates, n, world, precision=32, low_bits=0, swap_min_ops=0):
-    """All ranks in one process; the exchange is the chunk transpose the NCCL path performs."""
-    ranks = [ShardedHostRun(circ_gates, n, world, r, precision, low_bits, swap_min_ops) for r in range(world)]
+def sharded_host_run(circ_gates, n, world, precision=32, low_bits=0, swap_min_ops=0, fused=False):
+    """All ranks in one process; the exchange is the chunk transpose the NCCL path performs, or (fused) the
+    peer scatter of the pass itself."""
+    ranks = [ShardedHostRun(circ_gates, n, world, r, precision, low_bits, swap_min_ops, fused) for r in range(world)]
     for i in range(ranks[0].steps):
-        if ranks[0].is_swap(i):
+        if ranks[0].kind(i) == 2:
+            new = [np.zeros_like(r.shard) for r in ranks]
+            for r in ranks:
+                r.run_fused(i, new)
+            for r in ranks:
+                r.shard = new[r.rank]
+        elif ranks[0].is_swap(i):
             ch = [r.chunks().copy() for r in ranks]
             for r in ranks:
                 for j in range(world):

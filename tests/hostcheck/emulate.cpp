@@ -22,7 +22,9 @@ typedef std::complex<double> cd;
 
 struct Report { int max_conflict; int bad_slots; int noncontig; int passes; int rounds; };
 
-static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, Report &rep)
+/* outs: fused-exchange passes scatter into the shard of the rank named by the index bits above nloc
+ * (outs[rank] = that rank's NEW shard); null for ordinary in-place passes */
+static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, Report &rep, cd *const *outs = nullptr)
 {
     const int L = f32 ? 2 : 1;                  /* pack lanes */
     const int nb = 3;
@@ -155,7 +157,11 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                     for (int v = 0; v < QSB_NV; v++) {
                         uint64_t gi = d;
                         for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) gi |= hp.hdr.dst_vec[b];
-                        for (int l = 0; l < L; l++) st[(gi & loc_mask) | (uint64_t)l] = regs[((size_t)tid * QSB_NV + v) * L + l];
+                        for (int l = 0; l < L; l++) {
+                            const cd val = regs[((size_t)tid * QSB_NV + v) * L + l];
+                            if (hp.fused_swap) { if (!outs) { rep.bad_slots++; continue; } outs[gi >> nloc][(gi & loc_mask) | (uint64_t)l] = val; }
+                            else st[(gi & loc_mask) | (uint64_t)l] = val;
+                        }
                     }
                 }
             } else {
@@ -238,6 +244,41 @@ extern "C" void *qsb_hostcheck_plan(int num_q, int prec, int low_bits, int world
     if (tiled_schedule(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan)) { delete h; return nullptr; }
     return h;
 }
+/* like qsb_hostcheck_plan, with the exchanges fused into the preceding pass (peer scatter) */
+extern "C" void *qsb_hostcheck_plan_fused(int num_q, int prec, int low_bits, int world, int rank, int swap_min_ops,
+                                          const qsb_gate_t *gates, size_t n)
+{
+    qsb_options_t opt; memset(&opt, 0, sizeof opt);
+    opt.precision = prec; opt.low_bits = low_bits; opt.world_size = world; opt.rank = rank; opt.reserved[0] = swap_min_ops;
+    opt.reserved[5] = 1;
+    int g = 0; while ((1 << g) < world) g++;
+    const int T = tiled_min_local_bits(prec, &opt);
+    const int nloc = std::max(num_q - g, T);
+    std::vector<COp> cops; double gph[2];
+    if (qsb_canonicalise(gates, n, num_q, cops, gph)) return nullptr;
+    BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
+    HcPlan *h = new HcPlan();
+    h->prec = prec; h->nloc = nloc; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
+    if (tiled_schedule(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan)) { delete h; return nullptr; }
+    return h;
+}
+/* 0 ordinary pass, 1 exchange marker (all-to-all of chunks), 2 fused-exchange pass */
+extern "C" int qsb_hostcheck_step_kind(void *h, int i)
+{
+    const HostPass &hp = ((HcPlan *)h)->plan.passes[i];
+    return hp.is_swap ? 1 : hp.fused_swap ? 2 : 0;
+}
+/* fused-exchange pass of one rank: reads `state` (this rank's shard), writes into outs[r] (rank r's NEW shard) */
+extern "C" int qsb_hostcheck_run_step_fused(void *hv, int i, const double *state, double *const *outs)
+{
+    HcPlan *h = (HcPlan *)hv;
+    const HostPass &hp = h->plan.passes[i];
+    if (!hp.fused_swap) return 1;
+    std::vector<cd> st((size_t)1 << h->nloc);
+    memcpy((void *)st.data(), state, sizeof(cd) * st.size());
+    run_pass(hp, h->prec == QSB_F32, h->nloc, st, h->rep, (cd *const *)outs);
+    return 0;
+}
 extern "C" int qsb_hostcheck_num_steps(void *h) { return (int)((HcPlan *)h)->plan.passes.size(); }
 extern "C" int qsb_hostcheck_step_is_swap(void *h, int i) { return ((HcPlan *)h)->plan.passes[i].is_swap ? 1 : 0; }
 extern "C" int qsb_hostcheck_nloc(void *h) { return ((HcPlan *)h)->nloc; }
@@ -256,8 +297,8 @@ extern "C" void qsb_hostcheck_finish(void *hv, int *report5, int8_t *perm_out)
 {
     HcPlan *h = (HcPlan *)hv;
     report5[0] = h->rep.max_conflict; report5[1] = h->rep.bad_slots; report5[2] = h->rep.noncontig;
-    int sw = 0; for (auto &p : h->plan.passes) sw += p.is_swap;
-    report5[3] = (int)h->plan.passes.size() - sw; report5[4] = sw;
+    int sw = 0, fs = 0; for (auto &p : h->plan.passes) { sw += p.is_swap; fs += p.fused_swap; }
+    report5[3] = (int)h->plan.passes.size() - sw; report5[4] = sw + fs;
     for (int q = 0; q < 64; q++) perm_out[q] = h->plan.end_perm.pos[q];
     delete h;
 }

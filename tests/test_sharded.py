@@ -23,12 +23,24 @@ def test_sharded_schedule_reproduces_oracle(n, world, depth, seed, precision):
     assert np.max(np.abs(got - want)) < 1e-12
 
 
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("n,world,depth,seed", [(19, 2, 6, 1), (20, 4, 5, 2), (21, 8, 4, 3)])
+def test_fused_exchange_schedule_reproduces_oracle(n, world, depth, seed, precision):
+    """Exchanges fused into the preceding pass: every rank scatters straight into its peers' shards."""
+    circ = circuits.random_layered(n, depth=depth, seed=seed)
+    got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, precision, fused=True)
+    want = helpers.oracle_run_circuit(circ, n)
+    assert rep["swaps"] >= 1 and rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
 def test_sharded_superset_and_qft():
     for circ, n, world in ((circuits.random_superset(19, 150, 9), 19, 4), (circuits.qft(19), 19, 2)):
-        got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, 32, swap_min_ops=4)
         want = helpers.oracle_run_circuit(circ, n)
-        assert rep["bad_slots"] == 0
-        assert np.max(np.abs(got - want)) < 1e-12
+        for fused in (False, True):
+            got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, 32, swap_min_ops=4, fused=fused)
+            assert rep["bad_slots"] == 0
+            assert np.max(np.abs(got - want)) < 1e-12
 
 
 def test_exchange_count_on_the_34_qubit_workload():
