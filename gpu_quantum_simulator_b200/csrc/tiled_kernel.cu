@@ -235,7 +235,8 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
     if (form & S_UNIT_R) { unit_v<R, VB, false>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
     else if (form & S_UNIT_I) { unit_v<R, VB, true>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
     else if (form & S_DIAG) diag_v<R, VB>(re, im, T::bc(c0), T::bc(c1));
-    else xm ^= pred ? (1u << VB) : 0u;   /* S_XDEF */
+    /* S_XDEF alone, or merged into the gate it follows (the planner then gives both the same predicate) */
+    if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;
 }
 
 /* PEER: the scatter of a fused-exchange pass -- every amplitude goes straight into the shard of the rank

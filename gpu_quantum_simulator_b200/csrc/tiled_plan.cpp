@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 
 #include "sim.h"
 #include "tiled.h"
@@ -805,6 +806,7 @@ struct PassBuilder {
             /* segment under construction */
             std::vector<uint8_t> specials; uint32_t n_special = 0;
             std::vector<std::vector<uint8_t>> groups;       /* each QSB_GROUP16 * 16 bytes */
+            std::vector<std::array<bool, QSB_NVB>> slot_single;   /* slot holds an unconditional single-set gate */
             int next_group[QSB_NVB] = {0, 0, 0, 0};
             auto close_segment = [&]() {
                 if (!n_special && groups.empty()) return;
@@ -813,7 +815,7 @@ struct PassBuilder {
                 sr.n_groups = (uint32_t)groups.size(); sr.group_rel = (uint32_t)bodystream[r].size();
                 for (auto &g : groups) bodystream[r].insert(bodystream[r].end(), g.begin(), g.end());
                 segrec[r].push_back(sr);
-                specials.clear(); n_special = 0; groups.clear();
+                specials.clear(); n_special = 0; groups.clear(); slot_single.clear();
                 for (int b = 0; b < QSB_NVB; b++) next_group[b] = 0;
             };
 
@@ -863,12 +865,27 @@ struct PassBuilder {
                     if (mux) { slot_set(0, false); slot_set(1, false); }
                     else { slot_set(0, true); slot_set(0, false); }
                     if ((int)slot.size() != 2 * SET16 * 16) { qsb_set_error("internal: slot of %zu bytes", slot.size()); return QSB_ERR_ARG; }
+                    const uint32_t pm_new = tm8 | (wbits << 8);
+                    if (sform == S_XDEF && next_group[vb] > 0) {
+                        /* merge a deferred X into the gate it follows on the same vector bit: same slot, same predicate.
+                         * An unconditional single-set gate takes the X's predicate (both coefficient sets identical). */
+                        uint8_t *Gp = groups[next_group[vb] - 1].data();
+                        const uint8_t pf = Gp[vb];
+                        uint32_t ppm; memcpy(&ppm, Gp + 16 + 4 * vb, 4);
+                        uint8_t *sets = Gp + 32 + (size_t)vb * 2 * SET16 * 16;
+                        const bool prev_uncond = ppm == 0 && slot_single[next_group[vb] - 1][vb];
+                        if ((pf & (S_UNIT_R | S_UNIT_I | S_DIAG)) && !(pf & S_XDEF) && (ppm == pm_new || prev_uncond)) {
+                            if (ppm != pm_new) { memcpy(sets, sets + (size_t)SET16 * 16, (size_t)SET16 * 16); memcpy(Gp + 16 + 4 * vb, &pm_new, 4); }
+                            Gp[vb] = (uint8_t)(pf | S_XDEF);
+                            continue;
+                        }
+                    }
                     const int g = next_group[vb]++;
-                    if (g == (int)groups.size()) groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0));
+                    if (g == (int)groups.size()) { groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0)); slot_single.push_back({{false, false, false, false}}); }
+                    slot_single[g][vb] = !mux && !cond;
                     uint8_t *G0 = groups[g].data();
                     G0[vb] = (uint8_t)sform;                                   /* form byte of slot vb */
-                    const uint32_t pm = tm8 | (wbits << 8);
-                    memcpy(G0 + 16 + 4 * vb, &pm, 4);                          /* predicate mask */
+                    memcpy(G0 + 16 + 4 * vb, &pm_new, 4);                      /* predicate mask */
                     memcpy(G0 + 32 + (size_t)vb * 2 * SET16 * 16, slot.data(), slot.size());
                     continue;
                 }
