@@ -86,7 +86,7 @@ const int MAX_PASS_ROUNDS = 32;
 
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
-    bool f32, lazy_diag, defer_diag;
+    bool f32, lazy_diag, defer_diag, sink_phases;
     int trim_thin, cost_cap;
     bool fused_exchange;
 };
@@ -367,6 +367,29 @@ struct PassBuilder {
         if (roundR.back() & F) { roundR.push_back(0); round_ops.push_back({}); }
 
         const int nrounds = (int)roundR.size();
+        /* Sink thread-level phase gates to the latest round that can take them: a phase whose qubits are
+         * thread-level in this round AND the next one commutes with everything in between, so it can ride
+         * with the next round's pending scalar.  Rounds left without any phase skip the scalar multiply. */
+        if (M.sink_phases) for (int r = 0; r + 1 < nrounds; r++) {
+            std::vector<int> keep, moved;
+            for (int i : round_ops[r]) {
+                const COp &o = ops[i];
+                bool move = false;
+                if (o.kind == C_PHASE) {
+                    uint32_t bits = 0; bool pack = false;
+                    for (uint64_t m = o.ctrl; m; m &= m - 1) {
+                        int tb = tile_of_qubit[__builtin_ctzll(m)];
+                        if (tb == P && tb >= 0) pack = true; else if (tb >= 0) bits |= 1u << tb;
+                    }
+                    move = !pack && !(bits & roundR[r]) && !(bits & roundR[r + 1]);
+                }
+                (move ? moved : keep).push_back(i);
+            }
+            if (!moved.empty()) {
+                round_ops[r].swap(keep);
+                round_ops[r + 1].insert(round_ops[r + 1].begin(), moved.begin(), moved.end());
+            }
+        }
         hp.rounds.assign(nrounds, DevRound());
         hp.round_thr.assign(nrounds, {}); hp.round_vec.assign(nrounds, {});
         std::vector<uint32_t> ctrl_of_round(nrounds, 0), phase_of_round(nrounds, 0);
@@ -1009,6 +1032,8 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.fused_exchange = g > 0 && opt && opt->reserved[5] == 1;   /* reserved[5] = 1: exchanges fused into the preceding pass (peer stores) */
+    M.sink_phases = opt && opt->reserved[6] == 2;      /* reserved[6] = 2: sink thread-level phases to later rounds (A/B: no gain on random
+                                                          circuits, 7 % slower on QFT where it crowds the padding choice) */
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
