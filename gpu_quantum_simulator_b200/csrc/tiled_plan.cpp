@@ -372,6 +372,12 @@ struct PassBuilder {
          * with the next round's pending scalar.  Rounds left without any phase skip the scalar multiply. */
         if (M.sink_phases) for (int r = 0; r + 1 < nrounds; r++) {
             std::vector<int> keep, moved;
+            /* tile bits the next round cannot use as padding vector bits: its targets, controls and phase qubits */
+            uint32_t busy = roundR[r + 1], nonpack = 0;
+            for (int tb = 0; tb < M.T; tb++) if (tb != P) nonpack |= 1u << tb;
+            for (int i : round_ops[r + 1])
+                for (uint64_t m = ops[i].ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) busy |= 1u << tb; }
+            const uint32_t edgeF = (r + 1 == nrounds - 1) ? F : 0u;
             for (int i : round_ops[r]) {
                 const COp &o = ops[i];
                 bool move = false;
@@ -382,6 +388,9 @@ struct PassBuilder {
                         if (tb == P && tb >= 0) pack = true; else if (tb >= 0) bits |= 1u << tb;
                     }
                     move = !pack && !(bits & roundR[r]) && !(bits & roundR[r + 1]);
+                    /* the next round must still find its padding vector bits among qubits without phases */
+                    if (move && popc(nonpack & ~edgeF & ~(busy | bits)) + popc(roundR[r + 1]) < QSB_NVB) move = false;
+                    if (move) busy |= bits;
                 }
                 (move ? moved : keep).push_back(i);
             }
@@ -463,7 +472,12 @@ struct PassBuilder {
                 if (cd_ == OP_TPHASE) need = true;
                 else if (cd_ == OP_MAT_U || cd_ == OP_MAT_UI) {
                     const int ai = cd_ == OP_MAT_U ? 3 : 5;
-                    if (mux || h.tmask) need = true;   /* per-thread scale */
+                    if (mux && h.c[0][ai][0] == h.c[1][ai][0] && h.c[0][ai][1] == h.c[1][ai][1] && h.c[0][ai][0] == h.c[0][ai][1]) {
+                        /* both variants of the multiplexer carry the same scale (e.g. H | H.X): thread-independent */
+                        pass_scale *= h.c[0][ai][0];
+                        h.c[0][ai][0] = h.c[0][ai][1] = h.c[1][ai][0] = h.c[1][ai][1] = 1.0;
+                    }
+                    else if (mux || h.tmask) need = true;   /* per-thread scale */
                     else { pass_scale *= h.c[0][ai][0]; h.c[0][ai][0] = h.c[0][ai][1] = 1.0; }
                 }
             }
@@ -1032,8 +1046,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.fused_exchange = g > 0 && opt && opt->reserved[5] == 1;   /* reserved[5] = 1: exchanges fused into the preceding pass (peer stores) */
-    M.sink_phases = opt && opt->reserved[6] == 2;      /* reserved[6] = 2: sink thread-level phases to later rounds (A/B: no gain on random
-                                                          circuits, 7 % slower on QFT where it crowds the padding choice) */
+    M.sink_phases = !(opt && opt->reserved[6] == 1);   /* reserved[6] = 1: keep thread-level phases in the round that accepted them (A/B) */
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
