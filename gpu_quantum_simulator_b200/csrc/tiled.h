@@ -22,7 +22,11 @@
  *
  * The whole description of a pass (header, per-round tables, op stream) is a
  * few KiB and travels as a __grid_constant__ kernel parameter: every table and
- * coefficient read is a constant-bank load, no global traffic besides the state.
+ * coefficient read is a (mostly uniform-datapath) constant-bank load, no global
+ * traffic besides the state.  The LOGICAL tables below (DevPass, DevRound, HostOp)
+ * are what the planner reasons about and what the host test double interprets;
+ * serialise() lowers them to the device encoding further down (GPass, GRound,
+ * groups of slots, specials, thread-phase lists).
  *
  * Replaces (reference, /root/reference/): the per-gate launches of
  * naive.cu:163-189, the 2x2/4x4 host fusion of preproces.cu:215-269 and
@@ -34,9 +38,7 @@
 
 #include "common.cuh"
 
-#ifndef QSB_NVB
-#define QSB_NVB 4              /* vector bits per round (build-time: 4 -> 256 threads x 16 vectors, 3 -> 512 x 8) */
-#endif
+#define QSB_NVB 4              /* vector bits per round: 256 threads x 16 vectors (512 x 8 measured slower, round 1a) */
 #define QSB_NV (1 << QSB_NVB)  /* vectors per thread                         */
 #define QSB_TB (12 - QSB_NVB)  /* thread bits                                */
 #define QSB_THREADS (1 << QSB_TB)
