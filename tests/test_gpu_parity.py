@@ -184,3 +184,61 @@ def test_reference_main_links_against_gpu_library(tmp_path):
     assert bound and all("libqsim_b200_refcompat" in l.split(" to ")[1] for l in bound), bound[:3]
     bad = subprocess.run([str(exe)], capture_output=True, text=True)
     assert bad.returncode == 1 and "Usage:" in bad.stdout          # quantum_simulator.c:39-43
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+def test_cx_heavy_circuits_vs_oracle(precision):
+    """CX / X chains exercise the deferred swap (S_XDEF), its merge into the preceding slot and the
+    closed-qubit rule of the round builder."""
+    rng = np.random.RandomState(5)
+    for n in (17, 21):
+        circ = []
+        for _ in range(6 * n):
+            k = rng.randint(0, 5)
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            if k == 0:
+                circ.append(("h", (a,), ()))
+            elif k == 1:
+                circ.append(("x", (a,), ()))
+            elif k == 2:
+                circ.append(("rx", (a,), (float(rng.uniform(-3, 3)),)))
+            else:
+                circ.append(("cx", (a, b), ()))
+        want = helpers.oracle_run_circuit(circ, n)
+        got, _ = run_gpu(circ, n, precision)
+        assert np.max(np.abs(got - want)) <= TOL[precision]
+
+
+def test_planner_knobs_do_not_change_the_result():
+    """Fusion depth cap, lazy diagonals, phase sinking and tail trimming only reschedule: same state (f64, 1e-12)."""
+    n = 24
+    circ = circuits.random_layered(n, depth=8, seed=11) + circuits.qft(n, with_h_layer=False, swaps=False)[:200]
+    gates = q.gates_from_circuit(circ)
+    ref = None
+    for reserved in (None, [0, 0, 0, 12], [0, 2, 1, 0], [0, 0, 0, 0, 1, 0, 1], [0, 0, 3, 20, 0, 0, 0]):
+        with q.Simulator(n, precision=F64, reserved=reserved) as s:
+            st = s.apply(gates)
+            v = s.state_native().copy()
+        if ref is None:
+            ref, ref_passes = v, st["passes"]
+        else:
+            assert np.max(np.abs(v - ref)) <= 1e-12, reserved
+    with q.Simulator(n, precision=F64, reserved=[0, 0, 0, 12]) as s:
+        assert s.apply(gates)["passes"] > ref_passes          # the cap really produced a different schedule
+
+
+def test_qft_of_zero_state_is_uniform_at_32_qubits():
+    """BASELINE size property: QFT|0...0> = uniform superposition, every amplitude 2^-16 (f32, 32 GiB state)."""
+    n = 32
+    circ = circuits.qft(n, with_h_layer=False, swaps=True)
+    with q.Simulator(n, precision=F32) as s:
+        st = s.apply(q.gates_from_circuit(circ))
+        norm, idx, p = s.norm_argmax()
+        head = s.state(0, 1 << 12)
+        tail = s.state((1 << n) - (1 << 12), 1 << 12)
+    amp = 2.0 ** (-n / 2)
+    assert abs(norm - 1.0) < 1e-4
+    assert abs(p - amp * amp) < 1e-4 * amp * amp * 100
+    for part in (head, tail):
+        assert np.max(np.abs(part - amp)) < 1e-5 * amp * 10 + 1e-9
+    assert st["passes"] < len(circ) // 20
