@@ -272,6 +272,7 @@ extern "C" void qsb_destroy(qsb_t *s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->evx0) cudaEventDestroy(s->evx0);
     if (s->evx1) cudaEventDestroy(s->evx1);
+    for (int i = 0; i < 4; i++) if (s->copy_stream[i]) cudaStreamDestroy(s->copy_stream[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

@@ -17,6 +17,7 @@ struct qsb_sim {
     size_t state_bytes = 0;
     BitPerm perm{};          /* logical qubit -> physical bit (identity at reset) */
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};   /* pipelined exchange: peer copies on the copy engines */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
     void *staging = nullptr; /* device staging for readout                      */
     size_t staging_bytes = 0;

@@ -21,7 +21,7 @@
 #include "sim.h"
 #include "tiled.h"
 
-int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst, const PeerTab *peers);
+int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst, const PeerTab *peers, uint64_t tile0, uint64_t ntile);
 
 int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
                      const std::vector<COp> &cops, const double gphase[2], bool /*with_device*/,
@@ -141,7 +141,10 @@ extern "C" int qsb_comm_init(qsb_t *s, const void *id128)
         QSB_CUDA(cudaStreamSynchronize(s->stream));
         s->peers_ok = all_ok == 1;
     }
-    if (s->peers_ok && s->opt.reserved[5] == 0) s->opt.reserved[5] = 1;   /* plans made from now on fuse the exchanges */
+    /* exchange flavour of the plans made from now on: 3 = pipelined (default: measured fastest), 1 = fused peer
+     * scatter, 2 = plain NCCL all-to-all (also the fallback when the peer shards cannot be mapped) */
+    if (s->peers_ok && s->opt.reserved[5] == 0) s->opt.reserved[5] = 3;
+    if (!s->peers_ok) s->opt.reserved[5] = 2;
     return QSB_OK;
 }
 
@@ -177,10 +180,101 @@ static int exchange(qsb_sim *s)
     return QSB_OK;
 }
 
+/* Pipelined exchange (reserved[5] = 3): the in-tile permutation pass that precedes an exchange runs in
+ * slices of tiles; as soon as a slice is through, its part of every chunk goes to the peers' second
+ * buffers with cudaMemcpyAsync on a second stream (copy engines over NVLink) while the SMs compute the
+ * next slice.  A slice fixes the top S outer index bits; tile bits lying above the lowest of them split
+ * its address range into 2^m contiguous pieces per chunk. */
+static int pipelined_exchange(qsb_sim *s, TiledPlan *p, size_t k_pass, bool have_pass, std::vector<cudaEvent_t> &ev)
+{
+    const int NCS = 4;   /* several copy streams so that the transfers spread over the copy engines */
+    for (int i = 0; i < NCS; i++) if (!s->copy_stream[i]) QSB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream[i], cudaStreamNonBlocking));
+    int next_cs = 0;
+    const int P = s->world, g = s->g, nloc = s->nloc;
+    const size_t AMP = amp_bytes(s->prec), chunk = s->state_bytes / P;
+    std::vector<int> slice_pos;                     /* positions of the slicing bits, highest first */
+    uint64_t n_tiles = 1;
+    if (have_pass) {
+        const HostPass &hp = p->passes[k_pass];
+        n_tiles = hp.hdr.n_tiles;
+        std::vector<int> outer;                     /* outer positions, ascending = tile-id bit order */
+        for (uint32_t r = 0; r < hp.hdr.n_runs; r++) for (int b = 0; b < hp.hdr.run_len[r]; b++) outer.push_back(hp.hdr.run_start[r] + b);
+        int S = std::min<int>(3, (int)outer.size());
+        if (!outer.empty() && outer.back() >= nloc - g) S = 0;   /* chunk-select bits outside the tile: no slicing */
+        while (S > 0) {
+            const int lo = outer[outer.size() - S];
+            int m = 0;
+            for (int q = lo + 1; q < nloc - g; q++) if (std::find(outer.begin(), outer.end(), q) == outer.end()) m++;
+            if (m <= 4) break;
+            S--;
+        }
+        for (int i = 0; i < S; i++) slice_pos.push_back(outer[outer.size() - 1 - i]);
+    }
+    const int S = (int)slice_pos.size(), K = 1 << S;
+    const int lo = S ? slice_pos.back() : nloc - g;  /* everything below `lo` is contiguous inside a piece */
+    std::vector<int> mid;                            /* tile bits between lo and the chunk-select bits */
+    for (int q = lo + 1; q < nloc - g; q++) if (std::find(slice_pos.begin(), slice_pos.end(), q) == slice_pos.end()) mid.push_back(q);
+    const size_t piece = ((size_t)1 << lo) * AMP;
+    cudaEvent_t x0, x1;
+    QSB_CUDA(cudaEventCreate(&x0)); QSB_CUDA(cudaEventCreate(&x1));
+    bool x0_recorded = false;
+    for (int sl = 0; sl < K; sl++) {
+        if (have_pass) {
+            int rc = tiled_launch_pass(s, p, k_pass, s->state, s->state, nullptr, (uint64_t)sl * (n_tiles / K), n_tiles / K);
+            if (rc) return rc;
+        }
+        cudaEvent_t e; QSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        QSB_CUDA(cudaEventRecord(e, s->stream));
+        for (int i = 0; i < NCS; i++) QSB_CUDA(cudaStreamWaitEvent(s->copy_stream[i], e, 0));
+        QSB_CUDA(cudaEventDestroy(e));
+        if (sl == K - 1) { QSB_CUDA(cudaEventRecord(x0, s->stream)); x0_recorded = true; }   /* what follows is exposed transfer time */
+        /* slice sl = the slicing bits take the value sl (highest slicing bit = highest bit of sl) */
+        uint64_t base = 0;
+        for (int i = 0; i < S; i++) if ((sl >> (S - 1 - i)) & 1) base |= 1ULL << slice_pos[i];
+        for (uint64_t mm = 0; mm < (1ULL << mid.size()); mm++) {
+            uint64_t off = base;
+            for (size_t b = 0; b < mid.size(); b++) if ((mm >> b) & 1) off |= 1ULL << mid[b];
+            for (int jj = 0; jj < P; jj++) {
+                const int j = (s->rank + jj) % P;    /* start with the local chunk, then round-robin over the peers */
+                const char *src = (const char *)s->state + (size_t)j * chunk + off * AMP;
+                char *dst = (char *)s->peer_state2[j] + (size_t)s->rank * chunk + off * AMP;
+                QSB_CUDA(cudaMemcpyAsync(dst, src, piece, cudaMemcpyDeviceToDevice, s->copy_stream[next_cs]));
+                next_cs = (next_cs + 1) % NCS;
+            }
+        }
+    }
+    (void)x0_recorded;
+    for (int i = 0; i < NCS; i++) {
+        cudaEvent_t done; QSB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        QSB_CUDA(cudaEventRecord(done, s->copy_stream[i]));
+        QSB_CUDA(cudaStreamWaitEvent(s->stream, done, 0));
+        QSB_CUDA(cudaEventDestroy(done));
+    }
+    int *flag = (int *)((char *)s->d_scratch + 65536);
+    QSB_NCCL(g_nccl.AllReduce(flag, flag + 1, 1, 2 /* ncclInt32 */, 3 /* ncclMin */, (qsb_nccl_comm_t)s->comm, s->stream));
+    QSB_CUDA(cudaEventRecord(x1, s->stream));
+    ev.push_back(x0); ev.push_back(x1);
+    std::swap(s->state, s->state2);
+    for (int r = 0; r < P; r++) std::swap(s->peer_state[r], s->peer_state2[r]);
+    return QSB_OK;
+}
+
 int tiled_execute(qsb_sim *s, TiledPlan *p)
 {
     std::vector<cudaEvent_t> ev;
+    const bool pipelined = s->peers_ok && s->opt.reserved[5] == 3;
     for (size_t k = 0; k < p->passes.size(); k++) {
+        if (pipelined && !p->passes[k].is_swap && k + 1 < p->passes.size() && p->passes[k + 1].is_swap) {
+            int rc = pipelined_exchange(s, p, k, true, ev);
+            if (rc) return rc;
+            k++;                                    /* the marker is consumed */
+            continue;
+        }
+        if (pipelined && p->passes[k].is_swap) {
+            int rc = pipelined_exchange(s, p, k, false, ev);
+            if (rc) return rc;
+            continue;
+        }
         if (p->passes[k].is_swap) {
             cudaEvent_t a, b;
             QSB_CUDA(cudaEventCreate(&a)); QSB_CUDA(cudaEventCreate(&b));
@@ -200,7 +294,7 @@ int tiled_execute(qsb_sim *s, TiledPlan *p)
             PeerTab pt; memset(&pt, 0, sizeof pt);
             for (int r = 0; r < s->world; r++) pt.p[r] = (char *)s->peer_state2[r];
             pt.shard_bytes = s->state_bytes; pt.world = (uint32_t)s->world;
-            int rc = tiled_launch_pass(s, p, k, s->state, s->state2, &pt);
+            int rc = tiled_launch_pass(s, p, k, s->state, s->state2, &pt, 0, 0);
             if (rc) return rc;
             QSB_CUDA(cudaEventRecord(a, s->stream));
             int *flag = (int *)((char *)s->d_scratch + 65536);
@@ -211,7 +305,7 @@ int tiled_execute(qsb_sim *s, TiledPlan *p)
             for (int r = 0; r < s->world; r++) std::swap(s->peer_state[r], s->peer_state2[r]);
             continue;
         }
-        int rc = tiled_launch_pass(s, p, k, s->state, s->state, nullptr);
+        int rc = tiled_launch_pass(s, p, k, s->state, s->state, nullptr, 0, 0);
         if (rc) return rc;
     }
     s->perm = p->end_perm;

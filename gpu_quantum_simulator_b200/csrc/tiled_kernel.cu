@@ -243,7 +243,7 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
  * named by its victim bits (peer memory over NVLink), so the qubit exchange costs no extra sweep. */
 template <typename R, int BLOB, bool PEER>
 __global__ void __launch_bounds__(QSB_THREADS, 2)
-k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst, const __grid_constant__ PeerTab peers)
+k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst, const __grid_constant__ PeerTab peers, uint32_t tile_base)
 {
     typedef VT<R> T; typedef typename T::V V; typedef typename T::S S;
     static_assert(QSB_NVB == 4, "the interpreter is written for 4 vector bits");
@@ -254,7 +254,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     const uint64_t AMP = sizeof(R) * 2;
 
     /* tile id -> outer index bits (uniform) */
-    uint64_t tile = blockIdx.x, outer = 0;
+    uint64_t tile = (uint64_t)blockIdx.x + tile_base, outer = 0;   /* tile_base: a pass may be launched in slices (pipelined exchange) */
     {
         const int nr = (int)P.n_runs;
         for (int r = 0; r < nr; r++) {
@@ -451,7 +451,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 
 /* ------------------------------------------------------------------ launching */
 template <typename R, int BLOB, bool PEER>
-static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab &peers)
+static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab &peers, uint64_t tile0, uint64_t ntile)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -459,30 +459,32 @@ static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst
         attr_set = true;
     }
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
+    if (ntile == 0) { tile0 = 0; ntile = hp.hdr.n_tiles; }
     const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
-    k_tile_pass<R, BLOB, PEER><<<(unsigned)hp.hdr.n_tiles, QSB_THREADS, 65536, s->stream>>>(*blob, (const char *)src, (char *)dst, peers);
+    k_tile_pass<R, BLOB, PEER><<<(unsigned)ntile, QSB_THREADS, 65536, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, (uint32_t)tile0);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
 }
 
 template <typename R>
-static int launch_pass(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab *peers)
+static int launch_pass(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab *peers, uint64_t tile0, uint64_t ntile)
 {
     if (peers) {
         /* the descriptor and the peer table together must stay below the 32764-byte kernel-parameter limit */
-        if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL, true>(s, hp, src, dst, *peers);
-        if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM, true>(s, hp, src, dst, *peers);
-        return launch_one<R, QSB_BLOB_LARGE, true>(s, hp, src, dst, *peers);
+        if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL, true>(s, hp, src, dst, *peers, tile0, ntile);
+        if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM, true>(s, hp, src, dst, *peers, tile0, ntile);
+        return launch_one<R, QSB_BLOB_LARGE, true>(s, hp, src, dst, *peers, tile0, ntile);
     }
     static const PeerTab none = {};
-    if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL, false>(s, hp, src, dst, none);
-    if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM, false>(s, hp, src, dst, none);
-    return launch_one<R, QSB_BLOB_LARGE, false>(s, hp, src, dst, none);
+    if (hp.blob.size() <= QSB_BLOB_SMALL) return launch_one<R, QSB_BLOB_SMALL, false>(s, hp, src, dst, none, tile0, ntile);
+    if (hp.blob.size() <= QSB_BLOB_MEDIUM) return launch_one<R, QSB_BLOB_MEDIUM, false>(s, hp, src, dst, none, tile0, ntile);
+    return launch_one<R, QSB_BLOB_LARGE, false>(s, hp, src, dst, none, tile0, ntile);
 }
 
-/* peers: the destination shards of a fused-exchange pass (indexed by rank), or null */
-int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst, const PeerTab *peers)
+/* peers: the destination shards of a fused-exchange pass (indexed by rank), or null.
+ * [tile0, tile0 + ntile): the slice of the pass to launch (ntile = 0: the whole pass). */
+int tiled_launch_pass(qsb_sim *s, const TiledPlan *p, size_t k, const void *src, void *dst, const PeerTab *peers, uint64_t tile0, uint64_t ntile)
 {
     const HostPass &hp = p->passes[k];
-    return s->prec == QSB_F32 ? launch_pass<float>(s, hp, src, dst, peers) : launch_pass<double>(s, hp, src, dst, peers);
+    return s->prec == QSB_F32 ? launch_pass<float>(s, hp, src, dst, peers, tile0, ntile) : launch_pass<double>(s, hp, src, dst, peers, tile0, ntile);
 }

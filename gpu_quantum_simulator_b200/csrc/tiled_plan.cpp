@@ -88,7 +88,7 @@ struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
     bool f32, lazy_diag, defer_diag, sink_phases;
     int trim_thin, cost_cap;
-    bool fused_exchange;
+    bool fused_exchange, force_top;
 };
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
@@ -1045,6 +1045,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                                                         same speed on random circuits, 2.4x more rounds on QFT) */
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
+    M.force_top = g > 0 && opt && opt->reserved[5] == 3;        /* reserved[5] = 3: NCCL-style plan executed as a pipelined exchange */
     M.fused_exchange = g > 0 && opt && opt->reserved[5] == 1;   /* reserved[5] = 1: exchanges fused into the preceding pass (peer stores) */
     M.sink_phases = !(opt && opt->reserved[6] == 1);   /* reserved[6] = 1: keep thread-level phases in the round that accepted them (A/B) */
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
@@ -1166,7 +1167,9 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             forced |= (1ULL << pv) | (1ULL << pt);
         }
         const bool fuse = M.fused_exchange;
-        if (fuse) forced |= top_pos;   /* the victim bits select the destination rank: they must be tile bits */
+        /* the victim bits select the destination rank (fused exchange) or the chunk (pipelined exchange, which
+         * slices the pass along its top outer bits): they must be tile bits */
+        if (fuse || M.force_top) forced |= top_pos;
         if (forced) {
             /* resident set: low qubits + the qubits living on the forced positions */
             uint64_t S0 = lowS; int n0 = M.a;

@@ -19,10 +19,11 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     worst = 0.0
-    for prec, tol in ((q.F32, 1e-5), (q.F64, 1e-12)):
+    # exchange flavours (qsb_options_t.reserved[5]): 0 = default (pipelined copies), 1 = fused peer scatter, 2 = NCCL all-to-all
+    for prec, tol, mode in ((q.F32, 1e-5, 0), (q.F64, 1e-12, 0), (q.F32, 1e-5, 1), (q.F64, 1e-12, 1), (q.F32, 1e-5, 2)):
         for n, depth, seed in ((22, 8, 7), (23, 5, 8)):
             circ = circuits.random_layered(n, depth=depth, seed=seed)
-            sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local)
+            sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local, reserved=[0, 0, 0, 0, 0, mode])
             qdist.init_comm(sim, dist)
             st = sim.apply(q.gates_from_circuit(circ))
             got = qdist.gather_state(sim, dist)
@@ -31,7 +32,7 @@ def main():
                 want = helpers.oracle_run_circuit(circ, n)
                 err = float(np.max(np.abs(got - want)))
                 worst = max(worst, err / tol)
-                print(f"n={n} prec={prec} world={world} swaps={st['swaps']} passes={st['passes']} err={err:.3e}")
+                print(f"n={n} prec={prec} world={world} exchange_mode={mode} swaps={st['swaps']} passes={st['passes']} err={err:.3e}")
                 assert st["swaps"] >= 1
                 assert err <= tol, (n, prec, err)
     if rank == 0:
