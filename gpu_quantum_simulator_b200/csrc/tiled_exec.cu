@@ -141,9 +141,11 @@ extern "C" int qsb_comm_init(qsb_t *s, const void *id128)
         QSB_CUDA(cudaStreamSynchronize(s->stream));
         s->peers_ok = all_ok == 1;
     }
-    /* exchange flavour of the plans made from now on: 3 = pipelined (default: measured fastest), 1 = fused peer
-     * scatter, 2 = plain NCCL all-to-all (also the fallback when the peer shards cannot be mapped) */
-    if (s->peers_ok && s->opt.reserved[5] == 0) s->opt.reserved[5] = 3;
+    /* exchange flavour of the plans made from now on: 1 = fused peer scatter, 3 = pipelined copy-engine exchange,
+     * 2 = plain NCCL all-to-all (also the fallback when the peer shards cannot be mapped).  Measured on 34 q
+     * (DESIGN.md section 6): pipelined wins with one peer (2 GPUs: 1585 vs 1640 ms), the fused scatter with
+     * several (4 GPUs: 847 vs 977 ms, 8 GPUs: 482 vs 585 ms) -- the copy engines do not spread over 7 peers. */
+    if (s->peers_ok && s->opt.reserved[5] == 0) s->opt.reserved[5] = s->world <= 2 ? 3 : 1;
     if (!s->peers_ok) s->opt.reserved[5] = 2;
     return QSB_OK;
 }

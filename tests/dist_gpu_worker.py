@@ -19,8 +19,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     worst = 0.0
-    # exchange flavours (qsb_options_t.reserved[5]): 0 = default (pipelined copies), 1 = fused peer scatter, 2 = NCCL all-to-all
-    for prec, tol, mode in ((q.F32, 1e-5, 0), (q.F64, 1e-12, 0), (q.F32, 1e-5, 1), (q.F64, 1e-12, 1), (q.F32, 1e-5, 2)):
+    # exchange flavours (qsb_options_t.reserved[5]): 0 = default by world size, 1 = fused peer scatter, 2 = NCCL all-to-all,
+    # 3 = pipelined copy-engine exchange
+    for prec, tol, mode in ((q.F32, 1e-5, 0), (q.F64, 1e-12, 0), (q.F32, 1e-5, 1), (q.F64, 1e-12, 1), (q.F32, 1e-5, 2), (q.F32, 1e-5, 3), (q.F64, 1e-12, 3)):
         for n, depth, seed in ((22, 8, 7), (23, 5, 8)):
             circ = circuits.random_layered(n, depth=depth, seed=seed)
             sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local, reserved=[0, 0, 0, 0, 0, mode])
