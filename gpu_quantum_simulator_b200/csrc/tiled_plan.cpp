@@ -316,6 +316,11 @@ struct PassBuilder {
                 if (can) {
                     mine.push_back((int)i); done[i] = 1; left--; ctrl_used |= cbits; ctrl_real |= creal;
                     if (o.kind == C_X && tile_of_qubit[o.target] != P) closed |= 1ULL << o.target;
+                    /* a matrix with a small m00 (in either variant of a multiplexer) is cheapest as a pivoted unit
+                     * form + deferred X (see emit): that needs it to be the last gate on its qubit in this round */
+                    if ((o.kind == C_MAT || o.kind == C_MUX) && tile_of_qubit[o.target] != P &&
+                        (hypot(o.m[0], o.m[1]) < 0.3 || (o.kind == C_MUX && hypot(o.m2[0], o.m2[1]) < 0.3)))
+                        closed |= 1ULL << o.target;
                 }
                 else { B.block(o); if (B.full >= M.n) break; }
             }
