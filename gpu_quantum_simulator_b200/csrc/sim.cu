@@ -405,11 +405,9 @@ extern "C" int qsb_execute(qsb_t *s, qsb_plan_t *p)
     QSB_CUDA(cudaStreamSynchronize(s->stream));
     float ms = 0;
     QSB_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    double xms = s->last.exchange_ms;
     s->last = p->stats;
     s->last.device_ms = ms;
     s->last.exchange_ms = (p->mode == QSB_MODE_TILED) ? tiled_last_exchange_ms(p->tiled) : 0.0;
-    (void)xms;
     return QSB_OK;
 }
 

@@ -219,7 +219,6 @@ static int pipelined_exchange(qsb_sim *s, TiledPlan *p, size_t k_pass, bool have
     const size_t piece = ((size_t)1 << lo) * AMP;
     cudaEvent_t x0, x1;
     QSB_CUDA(cudaEventCreate(&x0)); QSB_CUDA(cudaEventCreate(&x1));
-    bool x0_recorded = false;
     for (int sl = 0; sl < K; sl++) {
         if (have_pass) {
             int rc = tiled_launch_pass(s, p, k_pass, s->state, s->state, nullptr, (uint64_t)sl * (n_tiles / K), n_tiles / K);
@@ -229,7 +228,7 @@ static int pipelined_exchange(qsb_sim *s, TiledPlan *p, size_t k_pass, bool have
         QSB_CUDA(cudaEventRecord(e, s->stream));
         for (int i = 0; i < NCS; i++) QSB_CUDA(cudaStreamWaitEvent(s->copy_stream[i], e, 0));
         QSB_CUDA(cudaEventDestroy(e));
-        if (sl == K - 1) { QSB_CUDA(cudaEventRecord(x0, s->stream)); x0_recorded = true; }   /* what follows is exposed transfer time */
+        if (sl == K - 1) QSB_CUDA(cudaEventRecord(x0, s->stream));   /* what follows is exposed transfer time */
         /* slice sl = the slicing bits take the value sl (highest slicing bit = highest bit of sl) */
         uint64_t base = 0;
         for (int i = 0; i < S; i++) if ((sl >> (S - 1 - i)) & 1) base |= 1ULL << slice_pos[i];
@@ -245,7 +244,6 @@ static int pipelined_exchange(qsb_sim *s, TiledPlan *p, size_t k_pass, bool have
             }
         }
     }
-    (void)x0_recorded;
     for (int i = 0; i < NCS; i++) {
         cudaEvent_t done; QSB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
         QSB_CUDA(cudaEventRecord(done, s->copy_stream[i]));

@@ -18,7 +18,16 @@
  *     predicates / phases on physical index bits (OP_TPHASE costs ~nothing);
  *   - a CX next to a one-qubit gate on its target is absorbed into that gate
  *     as a thread-level multiplexer (U vs X.U), costing zero extra arithmetic
- *     (the 4x4.cu pair accumulator did this with dense 4x4 products).
+ *     (the 4x4.cu pair accumulator did this with dense 4x4 products);
+ *   - an X / CX that is the last gate on its qubit in a round is DEFERRED: the
+ *     kernel flips one bit of the thread's vector-index mask and the swap
+ *     happens in the next store address (OP_XDEF).  Matrices with a small m00
+ *     are pivoted (M = X.M') so that every matrix runs in the 3-FMA unit form;
+ *   - phase gates wait for a round in which all their qubits are thread-level
+ *     (one entry of the pending-scalar list) unless a later gate of the round
+ *     depends on them; thin tail rounds of SM-bound passes move to the next pass.
+ * Multi-GPU: Belady-style victim choice and three exchange flavours (fused
+ * peer scatter, pipelined copies, NCCL), see DESIGN.md section 5.
  */
 #include <math.h>
 #include <string.h>
@@ -647,7 +656,7 @@ struct PassBuilder {
                 x.kind = OPK(OP_XDEF, vb, 0, 0); x.tmask = tmask; x.n_coef = 0;
                 hp.ops.push_back(x);
             };
-            double d0[8], d1[8], s0[8], s1[8], u0[8], u1[8];
+            double d0[8], d1[8], s0[8], s1[8], u0[8];
             bool t0 = false, t1 = false;
             if (is_mux) {
                 rowswap(m1, s1);
@@ -772,7 +781,6 @@ struct PassBuilder {
     int serialise()
     {
         const bool f32 = M.f32;
-        const size_t SS = f32 ? 4 : 8;                 /* scalar size */
         const uint64_t AMP = f32 ? 8 : 16;             /* bytes per amplitude */
         const uint64_t loc_mask = (1ULL << M.nloc) - 1;
         auto al16 = [](size_t x) { return (x + 15) / 16 * 16; };

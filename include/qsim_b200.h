@@ -66,12 +66,21 @@ typedef struct qsb_options {
     int32_t precision;    /* QSB_F32 | QSB_F64 (state dtype on the device)    */
     int32_t device;       /* CUDA ordinal, -1 = current                       */
     int32_t mode;         /* QSB_MODE_*                                       */
-    int32_t tile_bits;    /* 0 = default (13 for f32, 12 for f64)             */
-    int32_t low_bits;     /* contiguous low index bits every tile keeps, 0 = default */
+    int32_t tile_bits;    /* reserved: the tile is 2^13 (f32) / 2^12 (f64) amplitudes */
+    int32_t low_bits;     /* contiguous low index bits every tile keeps, 0 = default (4 f32 / 3 f64) */
     int32_t rank;         /* this process' shard, 0..world-1                  */
     int32_t world_size;   /* power of two; state sharded on the top log2(world) qubits */
-    int32_t use_graph;    /* 1: replay a circuit's passes as one CUDA graph   */
+    int32_t use_graph;    /* reserved (passes are plain stream launches; descriptors travel as kernel parameters) */
     int32_t verbose;
+    /* planner / exchange tuning knobs, all 0 = default (used by bench.py A/B runs and the tests):
+     *   [0] minimum number of local gates a pass must still find before a qubit exchange is scheduled (default 10)
+     *   [1] 2 = keep the qubits of phase gates thread-level at any price ("lazy diagonals")
+     *   [2] k+1 = trim tail rounds of SM-bound passes that hold fewer than k gates (default k = 2; 1 = off)
+     *   [3] fusion-depth cap: stop adding rounds to a pass at this estimated SM cost (unit-form gate units)
+     *   [4] 1 = do not defer phase gates that touch a vector bit
+     *   [5] exchange flavour: 1 fused peer scatter, 2 NCCL all-to-all, 3 pipelined copy-engine exchange
+     *       (0: chosen by qsb_comm_init -- pipelined at 2 ranks, fused beyond, NCCL if peers cannot be mapped)
+     *   [6] 1 = do not sink thread-level phases to later rounds                                            */
     int32_t reserved[7];
 } qsb_options_t;
 
