@@ -117,6 +117,13 @@ def ref_run_circuit(circ, n):
     return v * complex(math.cos(phi), math.sin(phi))
 
 
+def hostcheck_use_blob(on):
+    """Switch the host test double between the planner's logical tables (False) and the DEVICE ENCODING, i.e. the
+    kernel-parameter blob exactly as k_tile_pass reads it (True)."""
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck")))
+    L.qsb_hostcheck_use_blob(1 if on else 0)
+
+
 def hostcheck_run(circ_gates, n, precision=32, low_bits=0, state=None):
     """Schedule with the product planner, interpret the tables on the host (tests/hostcheck).
     -> (complex128 state in LOGICAL order, report dict)"""

@@ -24,8 +24,13 @@ struct Report { int max_conflict; int bad_slots; int noncontig; int passes; int 
 
 /* outs: fused-exchange passes scatter into the shard of the rank named by the index bits above nloc
  * (outs[rank] = that rank's NEW shard); null for ordinary in-place passes */
+int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, cd *const *outs);   /* blob_emulate.cpp */
+static int g_use_blob = 0;   /* 1: interpret the device encoding (the kernel-parameter blob) instead of the logical tables */
+extern "C" void qsb_hostcheck_use_blob(int on) { g_use_blob = on; }
+
 static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, Report &rep, cd *const *outs = nullptr)
 {
+    if (g_use_blob) { rep.bad_slots += blob_run_pass(hp, f32, nloc, st, outs); return; }
     const int L = f32 ? 2 : 1;                  /* pack lanes */
     const int nb = 3;
     const int phase_lanes = 8;                  /* lanes per 128-bit shared-memory phase (16-byte slots) */

@@ -67,3 +67,50 @@ def test_multi_control_and_global_phase_gates():
     for prec in (32, 64):
         got, want, rep = run_both(circ, 3, prec)
         assert np.max(np.abs(got - want)) < 1e-13
+
+
+@pytest.fixture
+def device_encoding():
+    """Interpret the kernel-parameter blob (what k_tile_pass reads) instead of the planner's logical tables."""
+    helpers.hostcheck_use_blob(True)
+    yield
+    helpers.hostcheck_use_blob(False)
+
+
+@pytest.mark.parametrize("precision,tol", [(32, 2e-5), (64, 1e-12)])
+@pytest.mark.parametrize("n,ng,seed", [(2, 30, 1), (7, 150, 2), (13, 250, 4), (14, 200, 5), (16, 120, 6)])
+def test_device_encoding_reproduces_oracle(device_encoding, n, ng, seed, precision, tol):
+    """The lowering (groups of slots, specials, thread-phase lists, gather / scatter / smem tables, deferred X)
+    interpreted byte for byte as the kernel does; f32 blobs carry float coefficients, hence 2e-5."""
+    circ = circuits.random_superset(n, ng, seed)
+    got, want, rep = run_both(circ, n, precision)
+    assert rep["bad_slots"] == 0
+    assert np.max(np.abs(got - want)) < tol
+
+
+def test_device_encoding_on_the_circuit_families(device_encoding):
+    for circ, n in ((circuits.qft(15), 15), (circuits.random_layered(17, depth=5, seed=3), 17),
+                    (helpers.load_case(os.path.join(helpers.GOLDEN, "grover_3_18.npz"))[0], 6)):
+        for precision, tol in ((32, 2e-5), (64, 1e-12)):
+            got, want, rep = run_both(circ, n, precision)
+            assert rep["bad_slots"] == 0
+            assert np.max(np.abs(got - want)) < tol
+
+
+def test_device_encoding_of_fused_exchange_passes(device_encoding):
+    """Peer-scatter offsets (rank field << 48 | local byte offset) of the fused exchange, all ranks in one process."""
+    n, world = 20, 4
+    circ = circuits.random_layered(n, depth=5, seed=2)
+    got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, 32, fused=True)
+    want = helpers.oracle_run_circuit(circ, n)
+    assert rep["swaps"] >= 1 and rep["bad_slots"] == 0
+    assert np.max(np.abs(got - want)) < 2e-5
+
+
+def test_fusion_depth_cap_reschedules_without_changing_the_plan_totals():
+    circ = circuits.random_layered(30, 20, 12345)
+    g = q.gates_from_circuit(circ)
+    full = q.plan_dry_run(30, g, precision=32)
+    capped = q.plan_dry_run(30, g, precision=32, reserved=[0, 0, 0, 12])
+    assert capped["passes"] > 1.5 * full["passes"]
+    assert abs(capped["rounds"] - full["rounds"]) <= 0.1 * full["rounds"]      # same SM work, more HBM sweeps
