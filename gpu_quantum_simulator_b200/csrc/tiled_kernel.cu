@@ -453,10 +453,11 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 template <typename R, int BLOB, bool PEER>
 static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab &peers, uint64_t tile0, uint64_t ntile)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   /* the opt-in to 64 KiB of dynamic shared memory is per device */
+    const int dev = s->device & 63;
+    if (!attr_set[dev]) {
         QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
     if (ntile == 0) { tile0 = 0; ntile = hp.hdr.n_tiles; }

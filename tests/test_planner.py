@@ -99,12 +99,13 @@ def test_device_encoding_on_the_circuit_families(device_encoding):
 
 def test_device_encoding_of_fused_exchange_passes(device_encoding):
     """Peer-scatter offsets (rank field << 48 | local byte offset) of the fused exchange, all ranks in one process."""
-    n, world = 20, 4
-    circ = circuits.random_layered(n, depth=5, seed=2)
-    got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, 32, fused=True)
-    want = helpers.oracle_run_circuit(circ, n)
-    assert rep["swaps"] >= 1 and rep["bad_slots"] == 0
-    assert np.max(np.abs(got - want)) < 2e-5
+    for n, world, precision, tol in ((20, 4, 32, 2e-5), (19, 2, 64, 1e-12)):
+        circ = circuits.random_layered(n, depth=5, seed=2)
+        want = helpers.oracle_run_circuit(circ, n)
+        for fused in (True, False):
+            got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, precision, fused=fused)
+            assert rep["swaps"] >= 1 and rep["bad_slots"] == 0
+            assert np.max(np.abs(got - want)) < tol
 
 
 def test_fusion_depth_cap_reschedules_without_changing_the_plan_totals():
