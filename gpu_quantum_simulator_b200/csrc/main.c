@@ -44,7 +44,7 @@ static void format_help(void)
     printf("qubit[<num_qubit>] q; or qubit q[<num_qubit>]; \\\\single quantum register \n");
     printf("<quantum_circuit>\n\n");
     printf("Supported operations: cx, x, sx, z, s, sdg, t, tdg, rz, h\n");
-    printf("(extensions: y p rx ry u cz cy ch cp swap ccx, pi expressions)\n");
+    printf("(extensions: y p rx ry u cz cy ch cp swap ccx, gate definitions, ctrl/negctrl/inv/pow modifiers, gphase, pi expressions)\n");
 }
 
 int main(int argc, char **argv)

@@ -165,7 +165,9 @@ int qsb_comm_init(qsb_t *s, const void *nccl_unique_id128);
  * Accepts the reference grammar bit-for-bit (quantum_simulator.c:133-242:
  * two header statements, `qubit[n] q;` or `qubit q[n];`, operands `q[k]` or
  * `$k`, CRLF, gate set cx x sx z s sdg t tdg rz h) plus a superset
- * (y p rx ry u cz cp crz swap ccx, `pi` expressions, barrier/measure ignored).
+ * (y p rx ry u cz cp crz swap ccx ..., `gate` definitions, ctrl @ / negctrl @ / inv @ / pow(k) @
+ * modifiers, gphase, several registers, whole-register operands, `pi` expressions and the
+ * usual functions in parameters; barrier / measure / reset / classical statements ignored).
  * The CUDA variants' "<num_q> <num_g>" header (naive.cu:239-240) is accepted
  * too.  *gates is malloc'ed; release with qsb_free(). */
 int qsb_parse_qasm_file(const char *path, int *num_qubits, qsb_gate_t **gates, size_t *n);

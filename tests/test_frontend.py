@@ -104,3 +104,66 @@ def test_writer_roundtrip_matches_generator():
     assert n == 7 and len(g) == len(g2)
     for a, b in zip(g, g2):
         assert a.controls == b.controls and a.target == b.target and list(a.m) == list(b.m)
+
+
+HDR = 'OPENQASM 3.0;\ninclude "stdgates.inc";\n'
+
+
+def same_gates(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x.controls == y.controls and x.target == y.target
+        assert np.allclose(list(x.m), list(y.m), atol=1e-15)
+
+
+def test_gate_definitions_expand_with_parameters_and_nesting():
+    text = HDR + '''qubit[3] q;
+gate bell a, b { h a; cx a, b; }
+gate twist(theta, phi) a, b { bell a, b; rz(theta / 2) a; rx(phi + pi) b; bell b, a; }
+twist(0.5, -0.25) q[2], q[0];
+'''
+    flat = HDR + '''qubit[3] q;
+h q[2]; cx q[2], q[0]; rz(0.25) q[2]; rx(-0.25 + pi) q[0]; h q[0]; cx q[0], q[2];
+'''
+    n, g = q.parse_qasm_string(text)
+    n2, g2 = q.parse_qasm_string(flat)
+    assert n == n2 == 3
+    same_gates(g, g2)
+
+
+def test_modifiers_ctrl_negctrl_inv_pow():
+    n, g = q.parse_qasm_string(HDR + 'qubit[4] q;\nctrl @ x q[0], q[1];\nctrl(2) @ rz(0.3) q[0], q[1], q[2];\n'
+                                     'inv @ s q[3];\npow(3) @ t q[3];\nnegctrl @ x q[2], q[0];\n')
+    n2, g2 = q.parse_qasm_string(HDR + 'qubit[4] q;\ncx q[0], q[1];\nccrz(0.3) q[0], q[1], q[2];\nsdg q[3];\n'
+                                       't q[3]; t q[3]; t q[3];\nx q[2]; cx q[2], q[0]; x q[2];\n')
+    same_gates(g, g2)
+    # inverse of a defined gate: reversed order, adjoint matrices; ctrl @ of a defined gate: every gate controlled
+    text = HDR + 'qubit[3] q;\ngate g2(t) a, b { rx(t) a; cx a, b; s b; }\ninv @ g2(0.7) q[0], q[1];\nctrl @ g2(0.7) q[2], q[0], q[1];\n'
+    flat = HDR + 'qubit[3] q;\nsdg q[1]; cx q[0], q[1]; rx(-0.7) q[0];\ncrx(0.7) q[2], q[0]; ccx q[2], q[0], q[1]; cs q[2], q[1];\n'
+    same_gates(q.parse_qasm_string(text)[1], q.parse_qasm_string(flat)[1])
+
+
+def test_gphase_registers_and_broadcast():
+    n, g = q.parse_qasm_string(HDR + 'qubit[2] a;\nqubit[3] b;\nh a;\ncx a[1], b[2];\ngphase(0.5);\nctrl @ gphase(0.25) b[0];\ncx a, b[0];\n')
+    assert n == 5
+    assert [(x.controls, x.target) for x in g[:3]] == [(0, 0), (0, 1), (2, 4)]
+    assert np.allclose(list(g[3].m), [math.cos(0.5), math.sin(0.5), 0, 0, 0, 0, math.cos(0.5), math.sin(0.5)])
+    assert g[4].target == 2 and g[4].controls == 0 and np.allclose(list(g[4].m)[6:], [math.cos(0.25), math.sin(0.25)])
+    assert [(x.controls, x.target) for x in g[5:]] == [(1, 2), (2, 2)]          # cx a, b[0] broadcasts over register a
+    # a global phase changes the amplitudes, not the probabilities: check through the host interpreter of the plan
+    circ_text = HDR + 'qubit[2] q;\nh q[0];\ngphase(0.5);\n'
+    n, g = q.parse_qasm_string(circ_text)
+    got, _ = helpers.hostcheck_run(g, n, 64)
+    want = np.exp(0.5j) * np.array([1, 1, 0, 0]) / math.sqrt(2)
+    assert np.max(np.abs(got - want)) < 1e-15
+
+
+def test_front_end_errors_of_the_superset():
+    for bad in ('qubit[2] q;\ngate g a { h a; }\ng q[0], q[1];\n',             # operand count
+                'qubit[2] q;\ngate g(t) a { rz(t) a; }\ng q[0];\n',               # parameter count
+                'qubit[2] q;\ngate r a { r a; }\nr q[0];\n',                      # recursion
+                'qubit[2] q;\nctrl @ x q[0], q[0];\n',                            # control == target
+                'qubit[2] q;\npow(0.5) @ x q[0];\n',                              # fractional power
+                'qubit[2] q;\ngate g a { h b; }\ng q[0];\n'):                     # unknown qubit argument
+        with pytest.raises(q.QsbError):
+            q.parse_qasm_string(HDR + bad)
