@@ -140,6 +140,14 @@ extern "C" int qsb_comm_init(qsb_t *s, const void *id128)
         QSB_CUDA(cudaMemcpyAsync(&all_ok, flag + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         QSB_CUDA(cudaStreamSynchronize(s->stream));
         s->peers_ok = all_ok == 1;
+        if (!s->peers_ok) {   /* some rank could not map its peers: drop the mappings made here */
+            for (int r = 0; r < s->world; r++) if (r != s->rank) {
+                if (s->peer_state[r]) cudaIpcCloseMemHandle(s->peer_state[r]);
+                if (s->peer_state2[r]) cudaIpcCloseMemHandle(s->peer_state2[r]);
+                s->peer_state[r] = s->peer_state2[r] = nullptr;
+            }
+            (void)cudaGetLastError();
+        }
     }
     /* exchange flavour of the plans made from now on: 1 = fused peer scatter, 3 = pipelined copy-engine exchange,
      * 2 = plain NCCL all-to-all (also the fallback when the peer shards cannot be mapped).  Measured on 34 q
