@@ -30,6 +30,7 @@
  * peer scatter, pipelined copies, NCCL), see DESIGN.md section 5.
  */
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -292,47 +293,62 @@ struct PassBuilder {
             if ((int)roundR.size() >= MAX_PASS_ROUNDS - 1) break;
             if (M.cost_cap > 0 && !roundR.empty() && more_passes_follow && sm_cost >= M.cost_cap) break;   /* fusion-depth limit (sweeps) */
             const bool is_first = roundR.empty();
-            uint32_t R = 0, ctrl_used = 0, ctrl_real = 0; int nR = 0;
+            uint32_t R = 0;
             uint32_t nonpack = 0;
             for (int tb = 0; tb < M.T; tb++) if (tb != P) nonpack |= 1u << tb;
             /* every round needs QSB_NVB vector bits that are neither controls of its gates nor (edge rounds) lane bits */
             auto paddable = [&](uint32_t R_, uint32_t creal) { return popc(nonpack & ~F & ~(creal | R_)) + popc(R_) >= QSB_NVB; };
-            uint64_t closed = 0;   /* qubits that took a bare X / CX in this round: nothing may follow on them here,
-                                      so that the X is deferred into the store address instead of being computed */
-            Blocker B; B.clear();
             std::vector<int> mine;
-            for (size_t i = first_open; i < n; i++) {
-                if (done[i]) continue;
-                const COp &o = ops[i];
-                bool can = B.ok(o);
-                if (can && ((o.ctrl & closed) || (o.target >= 0 && ((closed >> o.target) & 1)))) can = false;
-                uint32_t cbits = 0; /* tile bits this op uses as (non-diagonal-gate) controls */
-                if (can && (o.kind != C_PHASE || lazy_diag)) {
-                    /* controls must stay thread-level; with lazy diagonals so must the qubits of a phase gate: it
-                     * then costs one entry of the per-thread phase list instead of arithmetic on the vectors */
-                    for (uint64_t m = o.ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) cbits |= 1u << tb; }
-                    if (cbits & R) can = false;
+            /* One greedy scan of the open ops.  `allowed`: tile bits that may become vector bits; `cap`: how many of
+             * them; commit = false is a dry run (used to choose the vector bits) that reports, per tile bit, how many
+             * gates with arithmetic it would run as a target. */
+            auto scan = [&](bool commit, uint32_t allowed, int cap, std::vector<int> &acc, std::vector<int> *per_tb) -> uint32_t {
+                uint32_t ctrl_used = 0; int nR_ = 0; uint32_t R_ = 0, creal_all = 0;
+                uint64_t closed = 0;   /* qubits that took a bare X / CX (or a matrix to be pivoted) in this round: nothing
+                                          may follow on them here, so that the X is deferred into the store address */
+                Blocker B; B.clear();
+                std::vector<char> taken;
+                if (!commit) taken.assign(n, 0);
+                for (size_t i = first_open; i < n; i++) {
+                    if (done[i]) continue;
+                    const COp &o = ops[i];
+                    bool can = B.ok(o);
+                    if (can && ((o.ctrl & closed) || (o.target >= 0 && ((closed >> o.target) & 1)))) can = false;
+                    uint32_t cbits = 0; /* tile bits this op uses as (non-diagonal-gate) controls */
+                    if (can && (o.kind != C_PHASE || lazy_diag)) {
+                        /* controls must stay thread-level; with lazy diagonals so must the qubits of a phase gate: it
+                         * then costs one entry of the per-thread phase list instead of arithmetic on the vectors */
+                        for (uint64_t m = o.ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) cbits |= 1u << tb; }
+                        if (cbits & R_) can = false;
+                    }
+                    const uint32_t creal = (o.kind != C_PHASE) ? cbits : 0u;
+                    if (can && o.target >= 0) {
+                        int tb = tile_of_qubit[o.target];
+                        if (tb == P) { if (!paddable(R_, creal_all | creal)) can = false; }
+                        else if (is_first && ((F >> tb) & 1)) can = false;
+                        else if ((R_ >> tb) & 1) { if (!paddable(R_, creal_all | creal)) can = false; }
+                        else if (nR_ < cap && ((allowed >> tb) & 1) && !((ctrl_used >> tb) & 1) &&
+                                 (cap > QSB_NVB || paddable(R_ | (1u << tb), creal_all | creal))) { R_ |= 1u << tb; nR_++; }
+                        else can = false;
+                    }
+                    if (can) {
+                        acc.push_back((int)i); ctrl_used |= cbits; creal_all |= creal;
+                        if (commit) { done[i] = 1; left--; }
+                        if (per_tb && o.target >= 0 && tile_of_qubit[o.target] != P && o.kind != C_X) (*per_tb)[tile_of_qubit[o.target]]++;
+                        if (o.kind == C_X && tile_of_qubit[o.target] != P) closed |= 1ULL << o.target;
+                        /* a matrix with a small m00 (in either variant of a multiplexer) is cheapest as a pivoted unit
+                         * form + deferred X (see emit): that needs it to be the last gate on its qubit in this round */
+                        if ((o.kind == C_MAT || o.kind == C_MUX) && tile_of_qubit[o.target] != P &&
+                            (hypot(o.m[0], o.m[1]) < 0.3 || (o.kind == C_MUX && hypot(o.m2[0], o.m2[1]) < 0.3)))
+                            closed |= 1ULL << o.target;
+                    }
+                    else { B.block(o); if (B.full >= M.n) break; }
                 }
-                const uint32_t creal = (o.kind != C_PHASE) ? cbits : 0u;
-                if (can && o.target >= 0) {
-                    int tb = tile_of_qubit[o.target];
-                    if (tb == P) { if (!paddable(R, ctrl_real | creal)) can = false; }
-                    else if (is_first && ((F >> tb) & 1)) can = false;
-                    else if ((R >> tb) & 1) { if (!paddable(R, ctrl_real | creal)) can = false; }
-                    else if (nR < QSB_NVB && !((ctrl_used >> tb) & 1) && paddable(R | (1u << tb), ctrl_real | creal)) { R |= 1u << tb; nR++; }
-                    else can = false;
-                }
-                if (can) {
-                    mine.push_back((int)i); done[i] = 1; left--; ctrl_used |= cbits; ctrl_real |= creal;
-                    if (o.kind == C_X && tile_of_qubit[o.target] != P) closed |= 1ULL << o.target;
-                    /* a matrix with a small m00 (in either variant of a multiplexer) is cheapest as a pivoted unit
-                     * form + deferred X (see emit): that needs it to be the last gate on its qubit in this round */
-                    if ((o.kind == C_MAT || o.kind == C_MUX) && tile_of_qubit[o.target] != P &&
-                        (hypot(o.m[0], o.m[1]) < 0.3 || (o.kind == C_MUX && hypot(o.m2[0], o.m2[1]) < 0.3)))
-                        closed |= 1ULL << o.target;
-                }
-                else { B.block(o); if (B.full >= M.n) break; }
-            }
+                return R_;
+            };
+            /* (choosing the vector bits by a dry run -- the QSB_NVB targets with the most runnable gates -- was tried
+             * and does not reduce the number of rounds: first come, first served stays) */
+            R = scan(true, nonpack, QSB_NVB, mine, nullptr);
             /* A heavy pass is bound by the SM, not by HBM: a thin tail round (fewer than `trim` gates with
              * arithmetic) costs a full shared-memory exchange for almost no work.  Leave its ops to the
              * next pass, whose tile is chosen around them. */
