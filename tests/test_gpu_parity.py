@@ -242,3 +242,27 @@ def test_qft_of_zero_state_is_uniform_at_32_qubits():
     for part in (head, tail):
         assert np.max(np.abs(part - amp)) < 1e-5 * amp * 10 + 1e-9
     assert st["passes"] < len(circ) // 20
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+def test_edge_case_circuits(precision):
+    """Empty gate list, diagonal-only, CX-only chains, a 1-qubit register and a global phase (reference has no such tests;
+    these are the degenerate inputs of its grammar)."""
+    with q.Simulator(3, precision=precision) as s:
+        st = s.apply(q.gates_from_circuit([]))
+        v = s.state()
+        assert st["passes"] == 0 and v[0] == 1 and np.count_nonzero(v) == 1
+    cases = [
+        ([("h", (k,), ()) for k in range(5)] + [("rz", (k,), (0.1 * (k + 1),)) for k in range(5)] + [("cz", (0, 4), ()), ("cp", (1, 3), (0.7,))], 5),
+        ([("x", (0,), ())] + [("cx", (k, k + 1), ()) for k in range(19)], 20),
+        ([("h", (0,), ()), ("z", (0,), ()), ("s", (0,), ()), ("h", (0,), ())], 1),
+    ]
+    for circ, n in cases:
+        want = helpers.oracle_run_circuit(circ, n)
+        got, _ = run_gpu(circ, n, precision)
+        assert np.max(np.abs(got - want)) <= TOL[precision]
+    nq, g = q.parse_qasm_string('OPENQASM 3.0;\ninclude "stdgates.inc";\nqubit[2] q;\nh q[0];\ngphase(0.5);\nctrl @ gphase(0.25) q[1];\n')
+    with q.Simulator(nq, precision=precision) as s:
+        s.apply(g)
+        want = np.exp(0.5j) * np.array([1, 1, 0, 0]) / math.sqrt(2)
+        assert np.max(np.abs(s.state() - want)) <= TOL[precision]

@@ -115,3 +115,20 @@ def test_fusion_depth_cap_reschedules_without_changing_the_plan_totals():
     capped = q.plan_dry_run(30, g, precision=32, reserved=[0, 0, 0, 12])
     assert capped["passes"] > 1.5 * full["passes"]
     assert abs(capped["rounds"] - full["rounds"]) <= 0.1 * full["rounds"]      # same SM work, more HBM sweeps
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_edge_case_circuits_on_the_host_double(precision):
+    """Empty gate list, diagonal-only, CX-only and global-phase-only circuits; 1-qubit register (padded to a tile)."""
+    cases = [
+        ([], 3),
+        ([("rz", (k,), (0.1 * (k + 1),)) for k in range(5)] + [("cz", (0, 4), ()), ("cp", (1, 3), (0.7,))], 5),
+        ([("x", (0,), ())] + [("cx", (k, k + 1), ()) for k in range(13)], 14),
+        ([("h", (0,), ()), ("z", (0,), ()), ("s", (0,), ()), ("h", (0,), ())], 1),
+    ]
+    for circ, n in cases:
+        gates = q.gates_from_circuit(circ)
+        got, rep = helpers.hostcheck_run(gates, n, precision)
+        want = helpers.oracle_run_circuit(circ, n) if circ else np.eye(1, 1 << n, 0, dtype=complex)[0]
+        assert rep["bad_slots"] == 0
+        assert np.max(np.abs(got - want)) < 1e-12
