@@ -59,6 +59,9 @@ SYMBOLS = {
     "qsb_probabilities": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "qsb_cdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "qsb_sample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "qsb_sample_uniform": (C.c_double, [C.c_uint64, C.c_int]),
+    "qsb_save_state": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "qsb_load_state": (C.c_int, [C.c_void_p, C.c_char_p]),
     "qsb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "qsb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qsb_parse_qasm_file": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.POINTER(Gate)), C.POINTER(C.c_size_t)]),

@@ -8,6 +8,8 @@
  *   --dump-amplitudes   "%llu : %f + %f i" per non-zero amplitude, then
  *                       "MOST LIKELY MEASUREMENT: %llu (%f)"   (naive.cu:207-216)
  *   <number_of_measurement> > 0 with --shots: "MEASUREMENT: <bits> (%ld)" (quantum_simulator.c:68-73)
+ *   --save-state FILE / --load-state FILE   raw shard + qubit map after / before the circuit (checkpoint;
+ *                       the reference keeps the state only in memory, quantum_simulator.c:75)
  * Errors go to stdout followed by exit(1), like the reference (:56,:129,:213-219).
  */
 #include <stdio.h>
@@ -49,7 +51,7 @@ static void format_help(void)
 
 int main(int argc, char **argv)
 {
-    const char *file = NULL, *dump_bin = NULL;
+    const char *file = NULL, *dump_bin = NULL, *save_state = NULL, *load_state = NULL;
     long num_m = 0;
     int precision = 32, dump = 0, shots = 0, prec_out = 0, profile = 0, sweep = 0, have_m = 0;
     unsigned long long seed = 0; int have_seed = 0;
@@ -58,6 +60,8 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--dump-amplitudes")) dump = 1;
         else if (!strcmp(argv[i], "--precision-out") && i + 1 < argc) prec_out = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--dump-bin") && i + 1 < argc) dump_bin = argv[++i];
+        else if (!strcmp(argv[i], "--save-state") && i + 1 < argc) save_state = argv[++i];
+        else if (!strcmp(argv[i], "--load-state") && i + 1 < argc) load_state = argv[++i];
         else if (!strcmp(argv[i], "--shots")) shots = 1;
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) { seed = strtoull(argv[++i], NULL, 10); have_seed = 1; }
         else if (!strcmp(argv[i], "--profile")) profile = 1;
@@ -84,7 +88,9 @@ int main(int argc, char **argv)
     if (sweep) o.mode = QSB_MODE_SWEEP;
     qsb_t *s = NULL;
     rc = qsb_create(&s, nq, &o);
+    if (!rc && load_state) rc = qsb_load_state(s, load_state);
     if (!rc) rc = qsb_apply_gates(s, gates, n);
+    if (!rc && save_state) rc = qsb_save_state(s, save_state);
     if (rc) { printf("%s\n", qsb_last_error()); return 1; }
     printf("%lf\n", now_s() - t0);
 

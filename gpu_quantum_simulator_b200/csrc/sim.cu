@@ -8,8 +8,7 @@
  *   init_state_vector            naive.cu:64-70      -> k_init
  *   kernel_gate / kernel_gate_2  naive.cu:72-95      -> k_sweep_mat
  *   kernel_cnot                  naive.cu:97-122     -> k_sweep_x
- *   compute_state_cumulative_distribution  quantum_simulator.c:256-268 -> qsb_cdf
- *   measurement                  quantum_simulator.c:270-283 -> qsb_sample
+ *   (compute_state_cumulative_distribution / measurement, quantum_simulator.c:256-283 -> readout.cu)
  * None of the reference's code is reused: indices are 64-bit throughout (the
  * reference's `int th_id` caps it at 31 qubits), control masks are generic,
  * and the fp32 state uses the packed pair-interleaved layout of common.cuh.
@@ -619,43 +618,4 @@ extern "C" int qsb_probabilities(qsb_t *s, double *p, uint64_t first, uint64_t c
     return QSB_OK;
 }
 
-/* Inclusive prefix sum in index order with a serial fp64 accumulator, i.e. the
- * exact summation order of quantum_simulator.c:262-266.  |a|^2 is produced on
- * the device chunk by chunk; the running sum is a readout step, not part of
- * the apply path. */
-extern "C" int qsb_cdf(qsb_t *s, double *cdf, uint64_t first, uint64_t count)
-{
-    int rc = qsb_probabilities(s, cdf, first, count);
-    if (rc) return rc;
-    double acc = 0.0;
-    for (uint64_t i = 0; i < count; i++) { acc += cdf[i]; cdf[i] = acc; }
-    return QSB_OK;
-}
-
-static inline uint64_t splitmix64(uint64_t *x)
-{
-    uint64_t z = (*x += 0x9E3779B97F4A7C15ULL);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-
-extern "C" int qsb_sample(qsb_t *s, uint64_t seed, int shots, uint64_t *out)
-{
-    if (!s || shots < 0 || (shots && !out)) { qsb_set_error("qsb_sample: bad argument"); return QSB_ERR_ARG; }
-    if (s->g) { qsb_set_error("qsb_sample: sharded sampling is not implemented"); return QSB_ERR_ARG; }
-    if (s->n > 30) { qsb_set_error("qsb_sample: n > 30 needs the streaming sampler (not implemented)"); return QSB_ERR_ARG; }
-    const uint64_t N = 1ULL << s->n;
-    std::vector<double> cdf(N);
-    int rc = qsb_cdf(s, cdf.data(), 0, N);
-    if (rc) return rc;
-    uint64_t st = seed;
-    for (int k = 0; k < shots; k++) {
-        double r = (double)(splitmix64(&st) >> 11) * (1.0 / 9007199254740992.0);
-        /* first index with cdf != 0 and cdf >= r (quantum_simulator.c:277-281), by bisection on the monotone cdf */
-        uint64_t lo = 0, hi = N - 1;
-        while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (cdf[mid] == 0.0 || cdf[mid] < r) lo = mid + 1; else hi = mid; }
-        out[k] = lo;
-    }
-    return QSB_OK;
-}
+/* qsb_cdf, qsb_sample, qsb_save_state, qsb_load_state: readout.cu */

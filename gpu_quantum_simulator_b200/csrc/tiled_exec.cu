@@ -158,6 +158,20 @@ extern "C" int qsb_comm_init(qsb_t *s, const void *id128)
     return QSB_OK;
 }
 
+/* small collectives for the readout (readout.cu): buffers are device pointers, the calls are ordered on s->stream */
+int tiled_comm_allgather(qsb_sim *s, const void *dsrc, void *ddst, size_t bytes)
+{
+    if (!s->comm) { qsb_set_error("sharded readout needs qsb_comm_init first"); return QSB_ERR_COMM; }
+    QSB_NCCL(g_nccl.AllGather(dsrc, ddst, bytes, 1 /* ncclUint8 */, (qsb_nccl_comm_t)s->comm, s->stream));
+    return QSB_OK;
+}
+int tiled_comm_allreduce_sum_u64(qsb_sim *s, void *dbuf, size_t count)
+{
+    if (!s->comm) { qsb_set_error("sharded readout needs qsb_comm_init first"); return QSB_ERR_COMM; }
+    QSB_NCCL(g_nccl.AllReduce(dbuf, dbuf, count, 5 /* ncclUint64 */, 0 /* ncclSum */, (qsb_nccl_comm_t)s->comm, s->stream));
+    return QSB_OK;
+}
+
 void tiled_comm_destroy(qsb_sim *s)
 {
     if (s->peers_ok) {

@@ -9,6 +9,7 @@
     measurement(shots, seed)                   :270-283
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -250,3 +251,15 @@ class Simulator:
         out = np.empty(shots, dtype=np.uint64)
         check(lib.qsb_sample(self._h, seed, shots, out.ctypes.data))
         return out
+
+    def save_state(self, path):
+        """Dump this rank's shard (device dtype, physical order) with its qubit map; one file per rank."""
+        check(lib.qsb_save_state(self._h, os.fsencode(path)))
+
+    def load_state(self, path):
+        check(lib.qsb_load_state(self._h, os.fsencode(path)))
+
+
+def sample_uniform(seed, k):
+    """The r in [0, 1) that shot k of Simulator.measurement(seed=seed) searches for."""
+    return lib.qsb_sample_uniform(seed, k)

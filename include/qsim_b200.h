@@ -147,12 +147,30 @@ int qsb_download_native(qsb_t *s, void *dst, uint64_t first, uint64_t count);
 int qsb_norm_argmax(qsb_t *s, double *norm, uint64_t *argmax_idx, double *argmax_p);
 /* |a_i|^2 for i in [first, first+count), fp64. */
 int qsb_probabilities(qsb_t *s, double *p, uint64_t first, uint64_t count);
-/* Inclusive prefix sum of |a|^2 -- compute_state_cumulative_distribution (:256-268). */
+/* Inclusive prefix sum of |a|^2 in logical index order -- compute_state_cumulative_distribution
+ * (:256-268).  |a|^2 and the prefix sums are computed on the device (block scans chained by serial
+ * offsets: monotone, equal to the reference's single fp64 accumulator up to re-association, <= 1e-12). */
 int qsb_cdf(qsb_t *s, double *cdf, uint64_t first, uint64_t count);
-/* `shots` draws from the distribution; same search rule as measurement()
- * (:270-283: first index with cdf != 0 and cdf >= r), r from a seeded
- * generator instead of rand(). */
+/* `shots` draws from the distribution; same search rule as measurement() (:270-283: first index
+ * with cdf != 0 and cdf >= r, clamped to the last index), r from a seeded generator instead of
+ * rand().  Device-side and streaming: no 2^n array is built (segment totals + one re-scanned
+ * segment per shot), so it works at any n that fits the device.  On one GPU the result equals a
+ * search of qsb_cdf with the same r.  On a sharded state every rank must call it with the same
+ * seed and shots (collective: per-rank totals are all-gathered, the shots all-reduced); every rank
+ * receives all shots, drawn in rank-major physical order and returned as logical indices. */
 int qsb_sample(qsb_t *s, uint64_t seed, int shots, uint64_t *out);
+/* The r of shot k for a seed (splitmix64 -> 53-bit uniform in [0,1)): lets a caller replay
+ * measurement()'s search on a CDF of its own. */
+double qsb_sample_uniform(uint64_t seed, int k);
+
+/* ---- shard dump / reload ----------------------------------------------------
+ * The reference keeps the state only in memory (quantum_simulator.c:75 frees it
+ * at exit); long sharded runs want a checkpoint.  File = 128-byte header (magic
+ * "QSBSHARD", version, qubits, precision, world, rank, local bits, the logical ->
+ * physical qubit map) + the shard exactly as it lies in HBM.  One file per rank;
+ * loading checks that the handle has the same shape and restores the qubit map. */
+int qsb_save_state(qsb_t *s, const char *path);
+int qsb_load_state(qsb_t *s, const char *path);
 
 /* ---- multi-GPU (one process per GPU) --------------------------------------
  * nccl_unique_id: the 128 bytes of an ncclUniqueId, identical on every rank

@@ -13,6 +13,44 @@ import gpu_quantum_simulator_b200 as q  # noqa: E402
 from gpu_quantum_simulator_b200 import circuits, dist as qdist  # noqa: E402
 
 
+def check_sharded_readout(sim, got, n, rank, world, prec):
+    """Collective sampler: every rank receives the same shots; each one is what the reference's search rule
+    (first index with cdf != 0 and cdf >= r) gives on the CDF taken in rank-major physical order.  Then a
+    per-rank shard dump / reload round trip."""
+    seed, count = 17, 96
+    shots = sim.measurement(count, seed=seed)
+    perm, nloc = sim.layout()
+    t = torch.from_numpy(shots.astype(np.int64)).cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    assert all(torch.equal(parts[0], p) for p in parts)
+    idx = np.arange(1 << n, dtype=np.uint64)
+    phys = np.zeros_like(idx)
+    for qb in range(n):
+        phys |= ((idx >> np.uint64(qb)) & np.uint64(1)) << np.uint64(int(perm[qb]))
+    p_phys = np.zeros(1 << n)
+    p_phys[phys] = np.abs(got) ** 2
+    cdf = np.cumsum(p_phys)
+    L = helpers.oracle_lib()
+    for k in range(count):
+        r = q.sample_uniform(seed, k)
+        want = int(L.oc_measure(cdf.ctypes.data, n, r))
+        g_phys = int(phys[int(shots[k])])
+        assert p_phys[g_phys] > 0.0
+        if g_phys != want:
+            assert abs(cdf[want] - r) < 1e-9 or abs(cdf[g_phys] - r) < 1e-9, (k, r, g_phys, want)
+    path = f"/tmp/qsb_shard_{os.getpid()}_{rank}.bin"
+    before = sim.shard_physical().copy()
+    sim.save_state(path)
+    sim.reset()
+    sim.load_state(path)
+    os.unlink(path)
+    assert np.array_equal(sim.shard_physical(), before)
+    assert np.array_equal(sim.layout()[0], perm)
+    if rank == 0:
+        print(f"sharded readout ok: n={n} prec={prec} world={world} shots={count}")
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -28,6 +66,8 @@ def main():
             qdist.init_comm(sim, dist)
             st = sim.apply(q.gates_from_circuit(circ))
             got = qdist.gather_state(sim, dist)
+            if mode == 0:
+                check_sharded_readout(sim, got, n, rank, world, prec)
             sim.close()
             if rank == 0:
                 want = helpers.oracle_run_circuit(circ, n)
