@@ -59,8 +59,12 @@ def main():
     worst = 0.0
     # exchange flavours (qsb_options_t.reserved[5]): 0 = default by world size, 1 = fused peer scatter, 2 = NCCL all-to-all,
     # 3 = pipelined copy-engine exchange
-    for prec, tol, mode in ((q.F32, 1e-5, 0), (q.F64, 1e-12, 0), (q.F32, 1e-5, 1), (q.F64, 1e-12, 1), (q.F32, 1e-5, 2), (q.F32, 1e-5, 3), (q.F64, 1e-12, 3)):
-        for n, depth, seed in ((22, 8, 7), (23, 5, 8)):
+    configs = ((q.F32, 1e-5, 0), (q.F64, 1e-12, 0), (q.F32, 1e-5, 1), (q.F64, 1e-12, 1), (q.F32, 1e-5, 2), (q.F32, 1e-5, 3), (q.F64, 1e-12, 3))
+    sizes = ((22, 8, 7), (23, 5, 8))
+    if os.environ.get("QSB_DIST_QUICK"):       # readout-only run: default exchange flavour, one small circuit per precision
+        configs, sizes = configs[:2], ((22, 5, 7),)
+    for prec, tol, mode in configs:
+        for n, depth, seed in sizes:
             circ = circuits.random_layered(n, depth=depth, seed=seed)
             sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local, reserved=[0, 0, 0, 0, 0, mode])
             qdist.init_comm(sim, dist)
