@@ -355,6 +355,7 @@ extern "C" void qsb_plan_destroy(qsb_plan_t *p)
 {
     if (!p) return;
     if (p->tiled) tiled_plan_free(p->tiled);
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     delete p;
 }
 
@@ -390,14 +391,50 @@ static int sweep_execute(qsb_sim *s, const qsb_plan *p)
     return QSB_OK;
 }
 
+int tiled_prepare_capture(qsb_sim *s);
+
+/* use_graph: capture the pass launches of a single-GPU tiled plan into a CUDA graph (once per plan and
+ * state buffer).  Pays off when one plan is executed many times on a small register, where a pass is
+ * shorter than its launch (the regime of the reference's own 5-22 qubit benchmarks). */
+static int capture_plan(qsb_sim *s, qsb_plan *p)
+{
+    int rc = tiled_prepare_capture(s);
+    if (rc) return rc;
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    const BitPerm before = s->perm;
+    QSB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+    rc = tiled_execute(s, p->tiled);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    s->perm = before;                       /* nothing ran yet */
+    if (rc) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return rc; }
+    if (e != cudaSuccess) { qsb_set_error("%s while capturing the plan", cudaGetErrorString(e)); (void)cudaGetLastError(); return QSB_ERR_CUDA; }
+    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { p->graph_exec = nullptr; qsb_set_error("%s while instantiating the plan graph", cudaGetErrorString(e)); (void)cudaGetLastError(); return QSB_ERR_CUDA; }
+    p->graph_state = s->state;
+    return QSB_OK;
+}
+
 extern "C" int qsb_execute(qsb_t *s, qsb_plan_t *p)
 {
     if (!s || !p) { qsb_set_error("qsb_execute: null argument"); return QSB_ERR_ARG; }
     if (p->n != s->n || p->prec != s->prec || p->world != s->world) { qsb_set_error("plan was built for a different machine"); return QSB_ERR_ARG; }
     QSB_CUDA(cudaSetDevice(s->device));
+    const bool graphed = s->opt.use_graph && p->mode == QSB_MODE_TILED && s->world == 1;
+    if (graphed && (!p->graph_exec || p->graph_state != s->state)) {
+        int rc = capture_plan(s, p);
+        if (rc) return rc;
+    }
     QSB_CUDA(cudaEventRecord(s->ev0, s->stream));
     int rc;
-    if (p->mode == QSB_MODE_SWEEP) rc = (s->prec == QSB_F32) ? sweep_execute<float>(s, p) : sweep_execute<double>(s, p);
+    if (graphed) {
+        rc = QSB_OK;
+        cudaError_t e = cudaGraphLaunch(p->graph_exec, s->stream);
+        if (e != cudaSuccess) { qsb_set_error("%s while launching the plan graph", cudaGetErrorString(e)); rc = QSB_ERR_CUDA; }
+        else tiled_plan_end_perm(p->tiled, &s->perm);
+    }
+    else if (p->mode == QSB_MODE_SWEEP) rc = (s->prec == QSB_F32) ? sweep_execute<float>(s, p) : sweep_execute<double>(s, p);
     else rc = tiled_execute(s, p->tiled);
     if (rc) { cudaStreamSynchronize(s->stream); (void)cudaGetLastError(); return rc; }
     QSB_CUDA(cudaEventRecord(s->ev1, s->stream));

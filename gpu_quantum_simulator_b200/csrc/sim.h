@@ -37,6 +37,9 @@ struct qsb_plan {
     double gphase[2] = {1.0, 0.0}; /* global scalar factored out of diagonal gates */
     TiledPlan *tiled = nullptr;
     qsb_run_stats_t stats{};
+    /* qsb_options_t.use_graph: the pass launches of this plan captured once, replayed by every later qsb_execute */
+    cudaGraphExec_t graph_exec = nullptr;
+    void *graph_state = nullptr;   /* the state buffer the captured launches point at */
 };
 
 /* canonicalise source gates -> COps (+ global phase) */

@@ -49,6 +49,7 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
 }
 
 void tiled_plan_free(TiledPlan *p) { delete p; }
+void tiled_plan_end_perm(const TiledPlan *p, BitPerm *out) { *out = p->end_perm; }
 double tiled_last_exchange_ms(const TiledPlan *p) { return p ? p->last_exchange_ms : 0.0; }
 
 /* ------------------------------------------------------------------ NCCL (dlopen) */

@@ -450,21 +450,44 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 }
 
 /* ------------------------------------------------------------------ launching */
+/* the opt-in to 64 KiB of dynamic shared memory is per device and per instantiation */
 template <typename R, int BLOB, bool PEER>
-static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab &peers, uint64_t tile0, uint64_t ntile)
+static int ensure_smem_optin(int device)
 {
-    static bool attr_set[64] = {false};   /* the opt-in to 64 KiB of dynamic shared memory is per device */
-    const int dev = s->device & 63;
+    static bool attr_set[64] = {false};
+    const int dev = device & 63;
     if (!attr_set[dev]) {
         QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         attr_set[dev] = true;
     }
+    return QSB_OK;
+}
+
+template <typename R, int BLOB, bool PEER>
+static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst, const PeerTab &peers, uint64_t tile0, uint64_t ntile)
+{
+    int rc = ensure_smem_optin<R, BLOB, PEER>(s->device);
+    if (rc) return rc;
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
     if (ntile == 0) { tile0 = 0; ntile = hp.hdr.n_tiles; }
     const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
     k_tile_pass<R, BLOB, PEER><<<(unsigned)ntile, QSB_THREADS, 65536, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, (uint32_t)tile0);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
+}
+
+/* everything a stream capture must not do later (function attributes of the single-GPU instantiations) */
+int tiled_prepare_capture(qsb_sim *s)
+{
+    int rc;
+    if (s->prec == QSB_F32) {
+        if ((rc = ensure_smem_optin<float, QSB_BLOB_SMALL, false>(s->device))) return rc;
+        if ((rc = ensure_smem_optin<float, QSB_BLOB_MEDIUM, false>(s->device))) return rc;
+        return ensure_smem_optin<float, QSB_BLOB_LARGE, false>(s->device);
+    }
+    if ((rc = ensure_smem_optin<double, QSB_BLOB_SMALL, false>(s->device))) return rc;
+    if ((rc = ensure_smem_optin<double, QSB_BLOB_MEDIUM, false>(s->device))) return rc;
+    return ensure_smem_optin<double, QSB_BLOB_LARGE, false>(s->device);
 }
 
 template <typename R>

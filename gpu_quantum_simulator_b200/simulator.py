@@ -67,7 +67,7 @@ def gates_from_circuit(circ):
     return (Gate * len(out)).from_buffer(arr) if out else (Gate * 0)()
 
 
-def _options(precision, mode, low_bits, rank, world_size, device, reserved=None):
+def _options(precision, mode, low_bits, rank, world_size, device, reserved=None, use_graph=False):
     """reserved: planner tuning knobs (qsb_options_t.reserved): [0] min gates before a qubit exchange,
     [1] 2 = lazy diagonals on, [2] k+1 = trim tail rounds with < k gates (1 = off), [3] fusion-depth cost cap."""
     o = Options()
@@ -80,6 +80,7 @@ def _options(precision, mode, low_bits, rank, world_size, device, reserved=None)
     o.rank = rank
     o.world_size = world_size
     o.device = device
+    o.use_graph = 1 if use_graph else 0
     return o
 
 
@@ -110,9 +111,10 @@ class Plan:
 
 
 class Simulator:
-    def __init__(self, num_qubits, precision=F32, mode=MODE_TILED, low_bits=0, rank=0, world_size=1, device=-1, reserved=None):
+    def __init__(self, num_qubits, precision=F32, mode=MODE_TILED, low_bits=0, rank=0, world_size=1, device=-1, reserved=None,
+                 use_graph=False):
         self._h = C.c_void_p()
-        o = _options(precision, mode, low_bits, rank, world_size, device, reserved)
+        o = _options(precision, mode, low_bits, rank, world_size, device, reserved, use_graph)
         check(lib.qsb_create(C.byref(self._h), num_qubits, C.byref(o)))
         self.num_qubits, self.precision = num_qubits, precision
         self.rank, self.world_size = rank, world_size

@@ -70,7 +70,9 @@ typedef struct qsb_options {
     int32_t low_bits;     /* contiguous low index bits every tile keeps, 0 = default (4 f32 / 3 f64) */
     int32_t rank;         /* this process' shard, 0..world-1                  */
     int32_t world_size;   /* power of two; state sharded on the top log2(world) qubits */
-    int32_t use_graph;    /* reserved (passes are plain stream launches; descriptors travel as kernel parameters) */
+    int32_t use_graph;    /* 1 = capture the pass launches of a plan into a CUDA graph on its first qsb_execute and
+                           * replay it afterwards (single-GPU tiled plans; for plans executed many times on small
+                           * registers, where a pass is shorter than its launch).  0 = plain stream launches. */
     int32_t verbose;
     /* planner / exchange tuning knobs, all 0 = default (used by bench.py A/B runs and the tests):
      *   [0] minimum number of local gates a pass must still find before a qubit exchange is scheduled (default 10)

@@ -266,3 +266,30 @@ def test_edge_case_circuits(precision):
         s.apply(g)
         want = np.exp(0.5j) * np.array([1, 1, 0, 0]) / math.sqrt(2)
         assert np.max(np.abs(s.state() - want)) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+def test_graph_replay_of_a_plan_equals_plain_launches(precision):
+    """qsb_options_t.use_graph: the first execute captures the pass launches, later ones replay the graph;
+    results must be bit-identical to plain stream launches and correct against the oracle."""
+    n = 15
+    circ = circuits.random_layered(n, depth=12, seed=21)
+    gates = q.gates_from_circuit(circ)
+    want = helpers.oracle_run_circuit(circ, n)
+    with q.Simulator(n, precision=precision) as s:
+        plan = s.plan(gates)
+        s.execute(plan)
+        plain = s.state()
+        plan.close()
+    with q.Simulator(n, precision=precision, use_graph=True) as s:
+        plan = s.plan(gates)
+        for _ in range(3):                      # capture + launch, then two replays
+            s.reset()
+            st = s.execute(plan)
+            assert np.array_equal(s.state(), plain)
+            assert st["passes"] >= 2 and st["device_ms"] > 0
+        plan.close()
+        s.reset()
+        s.apply(gates)                          # plan + capture + execute + free in one call
+        assert np.array_equal(s.state(), plain)
+    assert np.max(np.abs(plain - want)) <= TOL[precision]
