@@ -185,6 +185,17 @@ struct GTPhase {               /* thread-level phase, applied through the pendin
     uint8_t val[16];           /* (pr, pi) in the state precision */
 };
 
+/* Unit-modulus thread-level phases, when a round holds several of them (QFT ladders): the angle as a
+ * fixed-point fraction of a turn.  The kernel adds the angles of the entries a thread satisfies with integer
+ * adds (exact, wraps modulo one turn) and pays ONE sincospi per round instead of a complex multiply per entry.
+ * f32 passes store 16-byte entries (ang32 = the top 32 bits), f64 passes the full 32 bytes. */
+struct GTAngle {
+    uint32_t tmask, ang32;
+    uint64_t omask;
+    uint64_t ang64, pad;
+};
+#define QSB_TANGLE_MIN 4       /* fewer qualifying phases in a round: they stay GTPhase entries */
+
 struct GSegment {              /* 16 bytes */
     uint32_t n_special, special_off16;
     uint32_t n_groups, group_off16;
@@ -195,7 +206,8 @@ struct GSegment {              /* 16 bytes */
 struct GRound {
     uint32_t n_seg, seg_off16; /* GSegment array, 16-byte units from the blob start                  */
     uint32_t n_tph, tph_off16; /* GTPhase array                                                      */
-    uint32_t flags, pad[3];    /* bit0: apply the pending scalar at the end of the round             */
+    uint32_t flags, n_ang, pad[2]; /* flags bit0: apply the pending scalar at the end of the round; n_ang: GTAngle
+                                  entries, stored right after the n_tph GTPhase entries                */
     uint32_t thr_x[QSB_TB];    /* smem byte XOR per thread bit: load side | store side << 16         */
     uint32_t vld_x[QSB_NV];    /* smem byte XOR per vector, load side                                */
     uint32_t vst_x[QSB_NV];    /*                            store side                              */

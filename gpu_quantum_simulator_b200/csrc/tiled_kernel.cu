@@ -60,6 +60,11 @@ template <> struct VT<float> {
     static __device__ __forceinline__ void vec2(const uint4 *c, int k, V &x, V &y) { const uint4 u = c[k]; x = ((V)u.y << 32) | u.x; y = ((V)u.w << 32) | u.z; }
     static __device__ __forceinline__ void tph(const uint4 u, S &pr, S &pi) { pr = __uint_as_float(u.x); pi = __uint_as_float(u.y); }
     enum { SET4 = 1 };   /* 16-byte units per 4-scalar coefficient set */
+    /* GTAngle entries: 16 bytes, the angle is the top 32 bits of the turn fraction */
+    typedef uint32_t A;
+    enum { ANG16 = 1 };
+    static __device__ __forceinline__ A ang(const uint4 h, const uint4 *) { return h.y; }
+    static __device__ __forceinline__ void turn(A acc, S &c, S &s) { sincospif((float)(int)acc * 4.656612873077393e-10f, &s, &c); }   /* acc / 2^31 half-turns */
 };
 template <> struct VT<double> {
     typedef double V;
@@ -82,6 +87,10 @@ template <> struct VT<double> {
     static __device__ __forceinline__ void vec2(const uint4 *c, int k, V &x, V &y) { const uint4 u = c[k]; x = lohi(u.x, u.y); y = lohi(u.z, u.w); }
     static __device__ __forceinline__ void tph(const uint4 u, S &pr, S &pi) { pr = lohi(u.x, u.y); pi = lohi(u.z, u.w); }
     enum { SET4 = 2 };
+    typedef uint64_t A;
+    enum { ANG16 = 2 };
+    static __device__ __forceinline__ A ang(const uint4, const uint4 *e) { const uint4 w = e[1]; return ((uint64_t)w.y << 32) | w.x; }
+    static __device__ __forceinline__ void turn(A acc, S &c, S &s) { sincospi((double)(long long)acc * 1.0842021724855044e-19, &s, &c); }   /* acc / 2^63 half-turns */
 };
 
 #define NV QSB_NV
@@ -392,6 +401,20 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 if ((src_outer & om) != om) continue;          /* uniform */
                 S pr, pi; T::tph(e[1], pr, pi);
                 if ((tid & h.x) != h.x) { pr = S(1); pi = S(0); }
+                const S nr = psr * pr - psi * pi;
+                psi = psr * pi + psi * pr; psr = nr;
+            }
+            /* unit-modulus phases as fixed-point angles (GTAngle): integer adds per entry, one sincospi per round */
+            const uint32_t n_ang = RD.n_ang;
+            if (n_ang) {
+                typename T::A acc = 0;
+                for (uint32_t i = 0; i < n_ang; i++, e += T::ANG16) {
+                    const uint4 h = e[0];
+                    const uint64_t om = ((uint64_t)h.w << 32) | h.z;
+                    if ((src_outer & om) != om) continue;          /* uniform */
+                    acc += ((tid & h.x) == h.x) ? T::ang(h, e) : (typename T::A)0;
+                }
+                S pr, pi; T::turn(acc, pr, pi);
                 const S nr = psr * pr - psi * pi;
                 psi = psr * pi + psi * pr; psr = nr;
             }

@@ -207,6 +207,49 @@ void absorb_cx(std::vector<COp> &ops, int n)
     ops.swap(out);
 }
 
+/* SWAP as a relabelling.  Three CX in a row on the same pair with alternating direction (what a front end
+ * makes of `swap a, b`; SURVEY.md 8c lists SWAP = 3 CX) exchange the states of the two qubits: instead of
+ * moving amplitudes, the two logical qubits trade wires -- every later op is rewritten onto the wire that
+ * holds its qubit and the plan's final qubit map absorbs the permutation.  Ops between the three CX that
+ * touch neither qubit commute with them, so only the ops touching a or b have to be consecutive.
+ * wire[q] on return: the wire (= logical label used by the rewritten ops) that holds logical qubit q. */
+void relabel_swaps(std::vector<COp> &ops, int n, int8_t *wire)
+{
+    const int N = (int)ops.size();
+    for (int q = 0; q < 64; q++) wire[q] = (int8_t)q;
+    auto is_cx = [&](const COp &o) { return o.kind == C_X && popc(o.ctrl) == 1; };
+    auto touches = [&](const COp &o, uint64_t m) { return ((o.ctrl | (o.target >= 0 ? 1ULL << o.target : 0)) & m) != 0; };
+    std::vector<char> drop(N, 0), event(N, 0);
+    for (int i = 0; i < N; i++) {
+        if (drop[i] || !is_cx(ops[i])) continue;
+        const int a = __builtin_ctzll(ops[i].ctrl), b = ops[i].target;
+        const uint64_t m = (1ULL << a) | (1ULL << b);
+        int idx[2], found = 0;
+        for (int j = i + 1; j < N && found < 2; j++) {
+            if (!touches(ops[j], m)) continue;
+            const int wc = found == 0 ? b : a, wt = found == 0 ? a : b;     /* expected control / target */
+            if (drop[j] || !is_cx(ops[j]) || __builtin_ctzll(ops[j].ctrl) != wc || ops[j].target != wt) break;
+            idx[found++] = j;
+        }
+        if (found < 2) continue;
+        drop[i] = drop[idx[0]] = drop[idx[1]] = 1;
+        event[i] = 1;
+    }
+    std::vector<COp> out; out.reserve(N);
+    for (int i = 0; i < N; i++) {
+        if (event[i]) std::swap(wire[__builtin_ctzll(ops[i].ctrl)], wire[ops[i].target]);
+        if (drop[i]) continue;
+        COp o = ops[i];
+        if (o.target >= 0) o.target = wire[o.target];
+        uint64_t c = 0;
+        for (uint64_t mm = o.ctrl; mm; mm &= mm - 1) c |= 1ULL << wire[__builtin_ctzll(mm)];
+        o.ctrl = c;
+        out.push_back(o);
+    }
+    (void)n;
+    ops.swap(out);
+}
+
 } // namespace
 
 /* ------------------------------------------------------------ pass building */
@@ -831,7 +874,7 @@ struct PassBuilder {
         gp.st_fixed = hp.fused_swap ? (hp.hdr.dst_fixed & loc_mask) * AMP : 0;
 
         std::vector<GRound> gr(nrounds);
-        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds);
+        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds), angstream(nrounds);
         /* body offsets inside segstream entries are relative to the round's body; fixed up below */
         struct SegRec { uint32_t n_special, special_rel, n_groups, group_rel; };
         std::vector<std::vector<SegRec>> segrec(nrounds);
@@ -867,7 +910,13 @@ struct PassBuilder {
                 return true;
             };
             std::vector<uint8_t> &ts = tphstream[r];
-            uint32_t n_tph = 0;
+            uint32_t n_tph = 0, n_ang = 0;
+            /* unit-modulus thread-level phases travel as fixed-point angles when the round has enough of them */
+            auto is_unit_phase = [](const HostOp &h) { return fabs(h.tph[0] * h.tph[0] + h.tph[1] * h.tph[1] - 1.0) <= 1e-15; };
+            int n_unit = 0;
+            for (uint32_t k = hp.round_op_begin[r]; k < hp.round_op_begin[r] + hp.round_op_count[r]; k++)
+                if ((hp.ops[k].kind & 0xff) == OP_TPHASE && is_unit_phase(hp.ops[k])) n_unit++;
+            const bool use_angles = n_unit >= QSB_TANGLE_MIN;
 
             /* segment under construction */
             std::vector<uint8_t> specials; uint32_t n_special = 0;
@@ -891,6 +940,24 @@ struct PassBuilder {
                 const bool mux = (h.kind >> 16) & 1;
                 uint32_t tm8; uint64_t om;
                 split_mask(h.tmask, tm8, om);
+                if (code == OP_TPHASE && use_angles && is_unit_phase(h)) {
+                    GTAngle e; memset(&e, 0, sizeof e);
+                    e.tmask = tm8; e.omask = om;
+                    long double turns = (long double)atan2(h.tph[1], h.tph[0]) / (2.0L * 3.14159265358979323846264338327950288L);
+                    /* exact fractions for the phases circuits are made of (-1, +-i, e^{i pi/4}, pi/2^k ladders) */
+                    if (h.tph[1] == 0.0) turns = h.tph[0] > 0 ? 0.0L : 0.5L;
+                    else if (h.tph[0] == 0.0) turns = h.tph[1] > 0 ? 0.25L : 0.75L;
+                    turns -= floorl(turns);
+                    long double scaled = roundl(ldexpl(turns, 64));
+                    if (scaled >= ldexpl(1.0L, 64)) scaled = 0.0L;
+                    e.ang64 = (uint64_t)scaled;
+                    /* f32 passes read the top 32 bits, rounded to nearest */
+                    const uint64_t r32 = (e.ang64 + 0x80000000ULL) >> 32;
+                    e.ang32 = (uint32_t)r32;     /* wraps to 0 at one full turn */
+                    const uint8_t *q = (const uint8_t *)&e; angstream[r].insert(angstream[r].end(), q, q + (f32 ? 16 : 32));
+                    n_ang++;
+                    continue;
+                }
                 if (code == OP_TPHASE) {
                     GTPhase e; memset(&e, 0, sizeof e);
                     e.tmask = tm8; e.omask = om;
@@ -1027,7 +1094,7 @@ struct PassBuilder {
                 n_special++;
             }
             close_segment();
-            G.n_tph = n_tph; G.n_seg = (uint32_t)segrec[r].size();
+            G.n_tph = n_tph; G.n_ang = n_ang; G.n_seg = (uint32_t)segrec[r].size();
         }
         gp.n_cond = n_cond;
         size_t off = al16(sizeof(GPass));
@@ -1042,7 +1109,7 @@ struct PassBuilder {
                 const uint8_t *q = (const uint8_t *)&gs; segstream[r].insert(segstream[r].end(), q, q + sizeof gs);
             }
             off = body0 + bodystream[r].size();
-            gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size();
+            gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size() + angstream[r].size();
         }
         const size_t total = off + 64;   /* slack: the group loop prefetches one group header past the last group */
         if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_ERR_ARG; }
@@ -1057,6 +1124,7 @@ struct PassBuilder {
             at += segstream[r].size();
             if (!bodystream[r].empty()) memcpy(&b[at], bodystream[r].data(), bodystream[r].size());
             if (!tphstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16], tphstream[r].data(), tphstream[r].size());
+            if (!angstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16 + tphstream[r].size()], angstream[r].data(), angstream[r].size());
         }
         return QSB_OK;
     }
@@ -1089,6 +1157,8 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     plan->passes.clear();
 
     std::vector<COp> cops = cops_in;
+    int8_t wire[64];
+    relabel_swaps(cops, n, wire);
     absorb_cx(cops, n);
     if (!(gphase[0] == 1.0 && gphase[1] == 0.0)) {
         COp c; memset(&c, 0, sizeof c); c.kind = C_PHASE; c.target = -1; c.ctrl = 0; c.m[0] = gphase[0]; c.m[1] = gphase[1];
@@ -1221,6 +1291,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             else if (p >= nloc - g) perm.pos[q] = (int8_t)(p + g);
         }
     }
-    plan->end_perm = perm;
+    /* logical qubit q ended on wire[q] (relabel_swaps) */
+    for (int q = 0; q < 64; q++) plan->end_perm.pos[q] = q < n ? perm.pos[wire[q]] : perm.pos[q];
     return QSB_OK;
 }

@@ -155,6 +155,21 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                 const cd ph(rd.S(T.val, 0), rd.S(T.val, 1));
                 for (int tid = 0; tid < QSB_THREADS; tid++) if (((uint32_t)tid & T.tmask) == T.tmask) pend[tid] *= ph;
             }
+            /* GTAngle entries follow the GTPhase entries: fixed-point turn fractions, summed per thread (wrapping) */
+            if (RD.n_ang) {
+                const size_t stride = f32 ? 16 : 32;
+                std::vector<uint64_t> acc(QSB_THREADS, 0);
+                for (uint32_t i = 0; i < RD.n_ang; i++, e += stride) {
+                    GTAngle T; memset(&T, 0, sizeof T); memcpy(&T, e, stride);
+                    if ((src_outer & T.omask) != T.omask) continue;
+                    for (int tid = 0; tid < QSB_THREADS; tid++) if (((uint32_t)tid & T.tmask) == T.tmask) acc[tid] += f32 ? (uint64_t)T.ang32 : T.ang64;
+                }
+                for (int tid = 0; tid < QSB_THREADS; tid++) {
+                    const double half_turns = f32 ? (double)(int32_t)(uint32_t)acc[tid] / 2147483648.0 : (double)(int64_t)acc[tid] / 9223372036854775808.0;
+                    const double PI_ = 3.14159265358979323846;
+                    pend[tid] *= cd(cos(PI_ * half_turns), sin(PI_ * half_turns));
+                }
+            }
             for (int tid = 0; tid < QSB_THREADS; tid++) {
                 if (RD.flags & 1u) { for (int k = 0; k < QSB_NV * L; k++) regs[(size_t)tid * QSB_NV * L + k] *= pend[tid]; }
                 else if (std::abs(pend[tid] - cd(1.0, 0.0)) > 0) bad++;     /* a scalar nobody applies */

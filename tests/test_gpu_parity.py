@@ -293,3 +293,33 @@ def test_graph_replay_of_a_plan_equals_plain_launches(precision):
         s.apply(gates)                          # plan + capture + execute + free in one call
         assert np.array_equal(s.state(), plain)
     assert np.max(np.abs(plain - want)) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("n", [9, 18, 21])
+def test_phase_ladders_and_swaps(n, precision):
+    """Rounds with many thread-level phases run them as fixed-point angles (one sincospi per round); `swap`
+    (three alternating CX) is a relabelling of the final qubit map.  Random and dyadic angles, f32 and f64."""
+    rng = np.random.RandomState(40 + n)
+    circ = [("h", (k,), ()) for k in range(n)]
+    for _ in range(6 * n):
+        a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+        r = rng.rand()
+        if r < 0.45:
+            circ.append(("cp", (a, b), (float(rng.uniform(-7, 7)),)))
+        elif r < 0.7:
+            circ.append(("cp", (a, b), (math.pi / 2 ** int(rng.randint(0, 14)),)))
+        elif r < 0.8:
+            circ.append(("rz", (a,), (float(rng.uniform(-7, 7)),)))
+        elif r < 0.87:
+            circ.append((["t", "sdg", "z"][int(rng.randint(3))], (a,), ()))
+        elif r < 0.9:
+            circ.append(("cz", (a, b), ()))
+        else:
+            circ.append(("swap", (a, b), ()))
+    circ += [("h", (k,), ()) for k in range(n)] + circuits.qft(n)
+    want = helpers.oracle_run_circuit(circ, n)
+    got, st = run_gpu(circ, n, precision)
+    assert np.max(np.abs(got - want)) <= TOL[precision]
+    sweep, _ = run_gpu(circ, n, precision, mode=q.MODE_SWEEP)
+    assert np.max(np.abs(got - sweep)) <= 2 * TOL[precision]

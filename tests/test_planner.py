@@ -132,3 +132,41 @@ def test_edge_case_circuits_on_the_host_double(precision):
         want = helpers.oracle_run_circuit(circ, n) if circ else np.eye(1, 1 << n, 0, dtype=complex)[0]
         assert rep["bad_slots"] == 0
         assert np.max(np.abs(got - want)) < 1e-12
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_swaps_become_a_relabelling(precision):
+    """Three alternating CX on one pair (= `swap`) cost nothing: the two qubits trade wires and the final qubit map
+    absorbs the permutation.  Near misses (an op on one of the qubits in between, a repeated direction, a second
+    control) must still run as ordinary CX."""
+    n = 14
+    rng = np.random.RandomState(3)
+    circ = circuits.random_layered(n, depth=2, seed=5)
+    for _ in range(12):
+        a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+        circ.append(("swap", (a, b), ()))
+        c = int(rng.randint(n))
+        circ.append(("h", (c,), ()))
+        circ.append(("rz", (int(rng.randint(n)),), (0.3,)))
+    # interleaved with ops on other qubits: still a swap
+    circ += [("cx", (0, 1), ()), ("h", (5,), ()), ("cx", (1, 0), ()), ("cp", (6, 7), (0.4,)), ("cx", (0, 1), ())]
+    # near misses
+    circ += [("cx", (2, 3), ()), ("cx", (3, 2), ()), ("t", (2,), ()), ("cx", (2, 3), ())]
+    circ += [("cx", (4, 5), ()), ("cx", (4, 5), ()), ("cx", (5, 4), ())]
+    circ += [("cx", (6, 7), ()), ("ccx", (7, 8, 6), ()), ("cx", (6, 7), ())]
+    circ += [("cx", (9, 10), ()), ("cx", (10, 9), ()), ("cz", (9, 3), ()), ("cx", (9, 10), ())]
+    circ += circuits.random_layered(n, depth=1, seed=6)
+    gates = q.gates_from_circuit(circ)
+    for blob in (False, True):
+        helpers.hostcheck_use_blob(blob)
+        got, rep = helpers.hostcheck_run(gates, n, precision)
+        want = helpers.oracle_run_circuit(circ, n)
+        assert rep["bad_slots"] == 0
+        assert np.max(np.abs(got - want)) < (2e-6 if blob and precision == 32 else 1e-12)
+    helpers.hostcheck_use_blob(False)
+    # a circuit of swaps only needs no pass at all, and the QFT's final bit reversal is free
+    only = [("swap", (k, n - 1 - k), ()) for k in range(n // 2)]
+    assert q.plan_dry_run(n, q.gates_from_circuit(only), precision=precision)["passes"] == 0
+    full = q.plan_dry_run(30, q.gates_from_circuit(circuits.qft(30)), precision=precision)
+    bare = q.plan_dry_run(30, q.gates_from_circuit(circuits.qft(30, swaps=False)), precision=precision)
+    assert full["passes"] == bare["passes"] and full["rounds"] == bare["rounds"]
