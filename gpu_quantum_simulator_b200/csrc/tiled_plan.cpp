@@ -40,6 +40,43 @@
 #include "tiled.h"
 
 /* ---------------------------------------------------------------- canonical */
+/* one (multi-)controlled 2x2 matrix -> canonical ops appended to `out`; global scalars go to gphase.
+ * Returns false for a singular diagonal matrix. */
+static bool canon_one(const double *m, uint64_t controls, int target, std::vector<COp> &out, double gphase[2])
+{
+    const bool offdiag_zero = m[2] == 0 && m[3] == 0 && m[4] == 0 && m[5] == 0;
+    const bool diag_zero = m[0] == 0 && m[1] == 0 && m[6] == 0 && m[7] == 0;
+    COp c; memset(&c, 0, sizeof c);
+    if (offdiag_zero) {
+        /* diag(d0, d1) = d0 * diag(1, d1/d0) */
+        double d0r = m[0], d0i = m[1], d1r = m[6], d1i = m[7];
+        if (!(d0r == 1.0 && d0i == 0.0)) {
+            double den = d0r * d0r + d0i * d0i;
+            if (den == 0) return false;
+            if (controls == 0) { /* a global scalar: fold */
+                double r = gphase[0] * d0r - gphase[1] * d0i, i = gphase[0] * d0i + gphase[1] * d0r;
+                gphase[0] = r; gphase[1] = i;
+            } else {
+                c.kind = C_PHASE; c.ctrl = controls; c.target = -1; c.m[0] = d0r; c.m[1] = d0i;
+                out.push_back(c);
+            }
+            double qr = (d1r * d0r + d1i * d0i) / den, qi = (d1i * d0r - d1r * d0i) / den;
+            d1r = qr; d1i = qi;
+        }
+        if (!(d1r == 1.0 && d1i == 0.0)) {
+            c.kind = C_PHASE; c.ctrl = controls | (1ULL << target); c.target = -1; c.m[0] = d1r; c.m[1] = d1i;
+            out.push_back(c);
+        }
+    } else if (diag_zero && m[2] == 1 && m[3] == 0 && m[4] == 1 && m[5] == 0) {
+        c.kind = C_X; c.target = target; c.ctrl = controls;
+        out.push_back(c);
+    } else {
+        c.kind = C_MAT; c.target = target; c.ctrl = controls; memcpy(c.m, m, sizeof c.m);
+        out.push_back(c);
+    }
+    return true;
+}
+
 int qsb_canonicalise(const qsb_gate_t *gates, size_t n, int num_qubits, std::vector<COp> &out, double gphase[2])
 {
     gphase[0] = 1.0; gphase[1] = 0.0;
@@ -49,37 +86,7 @@ int qsb_canonicalise(const qsb_gate_t *gates, size_t n, int num_qubits, std::vec
         if (g.target < 0 || g.target >= num_qubits) { qsb_set_error("gate %zu: target %d outside the %d-qubit register", k, g.target, num_qubits); return QSB_ERR_ARG; }
         if (num_qubits < 64 && (g.controls >> num_qubits)) { qsb_set_error("gate %zu: control outside the register", k); return QSB_ERR_ARG; }
         if (g.controls & (1ULL << g.target)) { qsb_set_error("gate %zu: target %d is also a control", k, g.target); return QSB_ERR_ARG; }
-        const double *m = g.m;
-        const bool offdiag_zero = m[2] == 0 && m[3] == 0 && m[4] == 0 && m[5] == 0;
-        const bool diag_zero = m[0] == 0 && m[1] == 0 && m[6] == 0 && m[7] == 0;
-        COp c; memset(&c, 0, sizeof c);
-        if (offdiag_zero) {
-            /* diag(d0, d1) = d0 * diag(1, d1/d0) */
-            double d0r = m[0], d0i = m[1], d1r = m[6], d1i = m[7];
-            if (!(d0r == 1.0 && d0i == 0.0)) {
-                double den = d0r * d0r + d0i * d0i;
-                if (den == 0) { qsb_set_error("gate %zu: singular diagonal matrix", k); return QSB_ERR_ARG; }
-                if (g.controls == 0) { /* a global scalar: fold */
-                    double r = gphase[0] * d0r - gphase[1] * d0i, i = gphase[0] * d0i + gphase[1] * d0r;
-                    gphase[0] = r; gphase[1] = i;
-                } else {
-                    c.kind = C_PHASE; c.ctrl = g.controls; c.target = -1; c.m[0] = d0r; c.m[1] = d0i;
-                    out.push_back(c);
-                }
-                double qr = (d1r * d0r + d1i * d0i) / den, qi = (d1i * d0r - d1r * d0i) / den;
-                d1r = qr; d1i = qi;
-            }
-            if (!(d1r == 1.0 && d1i == 0.0)) {
-                c.kind = C_PHASE; c.ctrl = g.controls | (1ULL << g.target); c.target = -1; c.m[0] = d1r; c.m[1] = d1i;
-                out.push_back(c);
-            }
-        } else if (diag_zero && m[2] == 1 && m[3] == 0 && m[4] == 1 && m[5] == 0) {
-            c.kind = C_X; c.target = g.target; c.ctrl = g.controls;
-            out.push_back(c);
-        } else {
-            c.kind = C_MAT; c.target = g.target; c.ctrl = g.controls; memcpy(c.m, m, sizeof c.m);
-            out.push_back(c);
-        }
+        if (!canon_one(g.m, g.controls, g.target, out, gphase)) { qsb_set_error("gate %zu: singular diagonal matrix", k); return QSB_ERR_ARG; }
     }
     return QSB_OK;
 }
@@ -205,6 +212,95 @@ void absorb_cx(std::vector<COp> &ops, int n)
     std::vector<COp> out; out.reserve(N);
     for (int i = 0; i < N; i++) if (alive[i]) out.push_back(ops[i]);
     ops.swap(out);
+}
+
+/* 2x2 products per qubit -- the reference's "preprocessing" (preproces.cu:128-163, 215-269: one product
+ * accumulator per qubit, flushed before a CX), done in fp64 and only where it pays:
+ *   - consecutive uncontrolled one-qubit gates on a qubit (matrix or X; nothing else touches the qubit in
+ *     between) multiply into one matrix when the product keeps a cheap form (real, rx-form, diagonal,
+ *     anti-diagonal).  H.H disappears, rx(a).rx(b) is one gate, X.H stays real.  A product that would need the
+ *     general complex form (H.rx) is left as two cheap gates.
+ *   - phase gates with the same qubit mask multiply when no non-diagonal gate on one of their qubits lies
+ *     between them (diagonal gates commute with each other and with controls).
+ * The reference multiplies in fp32 and drops products within 1e-3 of the identity (preproces.cu:151-160);
+ * here nothing is dropped that is not the identity to rounding. */
+void fuse_same_qubit(std::vector<COp> &ops, int n, double gphase[2])
+{
+    const int N = (int)ops.size();
+    std::vector<COp> out; out.reserve(N);
+    std::vector<char> dead;                    /* per output op */
+    std::vector<int> acc(n, -1);               /* qubit -> output index of the matrix still open for products */
+    struct PhaseSlot { uint64_t mask; int idx; };
+    std::vector<PhaseSlot> open_phase;         /* phases that may still absorb an equal-mask phase */
+    auto close_phases_on = [&](uint64_t qubits) {
+        for (size_t k = 0; k < open_phase.size();) {
+            if (open_phase[k].mask & qubits) { open_phase[k] = open_phase.back(); open_phase.pop_back(); } else k++;
+        }
+    };
+    auto as_matrix = [&](const COp &o, double *m) {
+        if (o.kind == C_X) { const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0}; memcpy(m, X, sizeof X); }
+        else memcpy(m, o.m, sizeof(double) * 8);
+    };
+    for (int i = 0; i < N; i++) {
+        const COp &o = ops[i];
+        if (o.kind == C_PHASE) {
+            /* touches its qubits diagonally: closes their matrix accumulators, may join an open phase */
+            for (uint64_t m = o.ctrl; m; m &= m - 1) acc[__builtin_ctzll(m)] = -1;
+            bool joined = false;
+            if (o.ctrl) for (PhaseSlot &ps : open_phase) if (ps.mask == o.ctrl) {
+                COp &a = out[ps.idx];
+                const double r = a.m[0] * o.m[0] - a.m[1] * o.m[1], im = a.m[0] * o.m[1] + a.m[1] * o.m[0];
+                a.m[0] = r; a.m[1] = im;
+                joined = true; break;
+            }
+            if (!joined) {
+                out.push_back(o); dead.push_back(0);
+                if (o.ctrl) open_phase.push_back({o.ctrl, (int)out.size() - 1});
+            }
+            continue;
+        }
+        const int t = o.target;
+        close_phases_on(1ULL << t);            /* a non-diagonal gate on t: phases involving t stop absorbing */
+        const bool plain = o.ctrl == 0 && (o.kind == C_MAT || o.kind == C_X);
+        if (plain && acc[t] >= 0) {
+            COp &a = out[acc[t]];
+            double A[8], B[8], P[8];
+            as_matrix(a, A); as_matrix(o, B);
+            /* P = B . A (A acts first) */
+            for (int r = 0; r < 2; r++) for (int c = 0; c < 2; c++) {
+                double pr = 0, pi = 0;
+                for (int k = 0; k < 2; k++) {
+                    const double br = B[2 * (2 * r + k)], bi = B[2 * (2 * r + k) + 1], ar = A[2 * (2 * k + c)], ai = A[2 * (2 * k + c) + 1];
+                    pr += br * ar - bi * ai; pi += br * ai + bi * ar;
+                }
+                P[2 * (2 * r + c)] = pr; P[2 * (2 * r + c) + 1] = pi;
+            }
+            double S[8]; snap_mat(P, S);
+            const bool diag = S[2] == 0 && S[3] == 0 && S[4] == 0 && S[5] == 0;
+            const bool anti = S[0] == 0 && S[1] == 0 && S[6] == 0 && S[7] == 0;
+            if (diag || anti || classify(S) <= 2 || is_jform(S)) {
+                std::vector<COp> repl;
+                if (canon_one(S, 0, t, repl, gphase) && repl.size() <= 1 && (repl.empty() || repl[0].kind != C_PHASE)) {
+                    if (repl.empty()) { dead[acc[t]] = 1; acc[t] = -1; }          /* identity (global scalar folded) */
+                    else a = repl[0];                                              /* one matrix or X, same place */
+                    continue;
+                }
+                if (!repl.empty() && repl[0].kind == C_PHASE && repl.size() == 1) {
+                    /* the product is a phase gate on t: it replaces the accumulator and closes it */
+                    a = repl[0]; acc[t] = -1;
+                    continue;
+                }
+                /* anything else (cannot happen for 2x2 inputs): fall through and keep the gate */
+            }
+        }
+        /* ordinary op: controls close the accumulators of their qubits, the target opens / closes its own */
+        for (uint64_t m = o.ctrl; m; m &= m - 1) acc[__builtin_ctzll(m)] = -1;
+        out.push_back(o); dead.push_back(0);
+        acc[t] = plain ? (int)out.size() - 1 : -1;
+    }
+    std::vector<COp> res; res.reserve(out.size());
+    for (size_t i = 0; i < out.size(); i++) if (!dead[i]) res.push_back(out[i]);
+    ops.swap(res);
 }
 
 /* SWAP as a relabelling.  Three CX in a row on the same pair with alternating direction (what a front end
@@ -1159,9 +1255,11 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     std::vector<COp> cops = cops_in;
     int8_t wire[64];
     relabel_swaps(cops, n, wire);
+    double gph[2] = {gphase[0], gphase[1]};
+    if (!(opt && opt->reserved[4] == 2)) fuse_same_qubit(cops, n, gph);      /* reserved[4] = 2: no 2x2 products (A/B, tests) */
     absorb_cx(cops, n);
-    if (!(gphase[0] == 1.0 && gphase[1] == 0.0)) {
-        COp c; memset(&c, 0, sizeof c); c.kind = C_PHASE; c.target = -1; c.ctrl = 0; c.m[0] = gphase[0]; c.m[1] = gphase[1];
+    if (!(gph[0] == 1.0 && gph[1] == 0.0)) {
+        COp c; memset(&c, 0, sizeof c); c.kind = C_PHASE; c.target = -1; c.ctrl = 0; c.m[0] = gph[0]; c.m[1] = gph[1];
         cops.push_back(c);
     }
     BitPerm perm = start;

@@ -79,7 +79,7 @@ typedef struct qsb_options {
      *   [1] 2 = keep the qubits of phase gates thread-level at any price ("lazy diagonals")
      *   [2] k+1 = trim tail rounds of SM-bound passes that hold fewer than k gates (default k = 2; 1 = off)
      *   [3] fusion-depth cap: stop adding rounds to a pass at this estimated SM cost (unit-form gate units)
-     *   [4] 1 = do not defer phase gates that touch a vector bit
+     *   [4] 1 = do not defer phase gates that touch a vector bit; 2 = no 2x2 products of consecutive one-qubit gates
      *   [5] exchange flavour: 1 fused peer scatter, 2 NCCL all-to-all, 3 pipelined copy-engine exchange
      *       (0: chosen by qsb_comm_init -- pipelined at 2 ranks, fused beyond, NCCL if peers cannot be mapped)
      *   [6] 1 = do not sink thread-level phases to later rounds                                            */

@@ -170,3 +170,49 @@ def test_swaps_become_a_relabelling(precision):
     full = q.plan_dry_run(30, q.gates_from_circuit(circuits.qft(30)), precision=precision)
     bare = q.plan_dry_run(30, q.gates_from_circuit(circuits.qft(30, swaps=False)), precision=precision)
     assert full["passes"] == bare["passes"] and full["rounds"] == bare["rounds"]
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_same_qubit_products(precision):
+    """The reference's 2x2 preprocessing (preproces.cu:215-269) in fp64: consecutive one-qubit gates on a qubit
+    multiply when the product keeps a cheap form; phases with equal masks multiply; anything touching the qubit
+    in between (a control, a phase) stops the product."""
+    n = 13
+    hh = [("h", (k,), ()) for k in range(n)] * 2
+    assert q.plan_dry_run(n, q.gates_from_circuit(hh), precision=precision)["device_ops"] <= 1       # identity (+ global scalar)
+    rx = [("rx", (k,), (0.1 * (k + 1) * (d + 1),)) for d in range(5) for k in range(n)]
+    one = [("rx", (k,), (0.1 * (k + 1),)) for k in range(n)]
+    a, b = (q.plan_dry_run(n, q.gates_from_circuit(c), precision=precision) for c in (rx, one))
+    assert a["rounds"] == b["rounds"] and a["passes"] == b["passes"]
+    zz = [("rz", (3,), (0.2,)), ("cp", (3, 5), (0.3,)), ("rz", (3,), (0.4,)), ("cp", (5, 3), (0.1,)), ("t", (3,), ())]
+    assert q.plan_dry_run(n, q.gates_from_circuit(zz), precision=precision)["device_ops"] == 2         # one phase on q3, one on {q3, q5}
+    off = q.plan_dry_run(n, q.gates_from_circuit(rx), precision=precision, reserved=[0, 0, 0, 0, 2])
+    assert off["device_ops"] > 3 * a["device_ops"]
+    rng = np.random.RandomState(11)
+    circ = []
+    for _ in range(400):
+        t = int(rng.randint(n)); r = rng.rand()
+        if r < 0.5:
+            circ.append((["h", "x", "y", "sx", "rx", "ry"][int(rng.randint(6))], (t,), ()))
+            if circ[-1][0] in ("rx", "ry"):
+                circ[-1] = (circ[-1][0], (t,), (float(rng.uniform(-3, 3)),))
+        elif r < 0.75:
+            circ.append((["z", "s", "t", "tdg", "rz"][int(rng.randint(5))], (t,), ()))
+            if circ[-1][0] == "rz":
+                circ[-1] = ("rz", (t,), (float(rng.uniform(-3, 3)),))
+        else:
+            c = int(rng.choice([x for x in range(n) if x != t]))
+            circ.append((["cx", "cz", "cp"][int(rng.randint(3))], (c, t), ()))
+            if circ[-1][0] == "cp":
+                circ[-1] = ("cp", (c, t), (float(rng.uniform(-3, 3)),))
+    gates = q.gates_from_circuit(circ)
+    want = helpers.oracle_run_circuit(circ, n)
+    for blob in (False, True):
+        helpers.hostcheck_use_blob(blob)
+        got, rep = helpers.hostcheck_run(gates, n, precision)
+        assert rep["bad_slots"] == 0
+        assert np.max(np.abs(got - want)) < (2e-6 if blob and precision == 32 else 1e-12)
+    helpers.hostcheck_use_blob(False)
+    fused = q.plan_dry_run(n, gates, precision=precision)
+    plain = q.plan_dry_run(n, gates, precision=precision, reserved=[0, 0, 0, 0, 2])
+    assert fused["device_ops"] < 0.9 * plain["device_ops"]
