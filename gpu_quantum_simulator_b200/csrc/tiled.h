@@ -194,7 +194,16 @@ struct GTAngle {
     uint64_t omask;
     uint64_t ang64, pad;
 };
-#define QSB_TANGLE_MIN 4       /* fewer qualifying phases in a round: they stay GTPhase entries */
+/* Fewer qualifying phases in a round: they stay GTPhase entries.  Break-even measured on B200 (profiles/
+ * r1h_angle_ab.txt): an entry costs ~12 instructions as a complex multiply and ~5 as an angle, the sincospi
+ * ~40 (f32) / ~150 (f64); with a threshold of 4 the 30 q layered circuit lost 1.8 % (f32) and 4.8 % (f64). */
+#ifdef QSB_NO_TANGLE            /* A/B builds: no GTAngle entries, kernel without the angle loop */
+#define QSB_TANGLE_MIN_F32 (1 << 30)
+#define QSB_TANGLE_MIN_F64 (1 << 30)
+#else
+#define QSB_TANGLE_MIN_F32 8
+#define QSB_TANGLE_MIN_F64 24
+#endif
 
 struct GSegment {              /* 16 bytes */
     uint32_t n_special, special_off16;

@@ -405,7 +405,11 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 psi = psr * pi + psi * pr; psr = nr;
             }
             /* unit-modulus phases as fixed-point angles (GTAngle): integer adds per entry, one sincospi per round */
+#ifdef QSB_NO_TANGLE   /* A/B builds only: the planner must then be told not to emit GTAngle entries */
+            const uint32_t n_ang = 0;
+#else
             const uint32_t n_ang = RD.n_ang;
+#endif
             if (n_ang) {
                 typename T::A acc = 0;
                 for (uint32_t i = 0; i < n_ang; i++, e += T::ANG16) {

@@ -1012,7 +1012,7 @@ struct PassBuilder {
             int n_unit = 0;
             for (uint32_t k = hp.round_op_begin[r]; k < hp.round_op_begin[r] + hp.round_op_count[r]; k++)
                 if ((hp.ops[k].kind & 0xff) == OP_TPHASE && is_unit_phase(hp.ops[k])) n_unit++;
-            const bool use_angles = n_unit >= QSB_TANGLE_MIN;
+            const bool use_angles = n_unit >= (f32 ? QSB_TANGLE_MIN_F32 : QSB_TANGLE_MIN_F64);
 
             /* segment under construction */
             std::vector<uint8_t> specials; uint32_t n_special = 0;
