@@ -10,7 +10,7 @@
  * the qubit-remapping layer: high-stride qubits are gathered into the tile
  * instead of being swept with strided passes.
  *
- * Inside a pass the tile lives in REGISTERS: each of the 256 threads holds
+ * Inside a pass the tile lives in REGISTERS: each of the 128 threads holds
  * 2^NVB vectors (NVB = 4).  For f32 a vector is a float2 holding the same
  * component (re or im) of the two amplitudes that differ in the PACK bit
  * (tile bit 0 == physical bit 0), so every butterfly is issued as packed
@@ -38,12 +38,23 @@
 
 #include "common.cuh"
 
-#define QSB_NVB 4              /* vector bits per round: 256 threads x 16 vectors (512 x 8 measured slower, round 1a) */
+#define QSB_NVB 4              /* vector bits per round: 16 vectors per thread (8 per thread measured slower, round 1a) */
 #define QSB_NV (1 << QSB_NVB)  /* vectors per thread                         */
-#define QSB_TB (12 - QSB_NVB)  /* thread bits                                */
+/* Thread bits.  Build-time geometry switch, A/B measured on B200 (profiles/r1h_tile_geometry_ab.txt):
+ *   QSB_TB = 8: 256 threads, two CTAs per SM, tiles of 2^13 (f32) / 2^12 (f64) amplitudes
+ *   QSB_TB = 7: 128 threads, FOUR CTAs per SM, tiles of 2^12 / 2^11 -- 11 % (f32) / 6.5 % (f64) faster on the
+ *               30 q depth-20 circuit although it needs 30 instead of 25 passes: a CTA runs gather -> rounds ->
+ *               scatter one after the other, and four resident CTAs overlap HBM, shared-memory and FP32 phases
+ *               better than two.  Default. */
+#ifndef QSB_TB
+#define QSB_TB 7
+#endif
 #define QSB_THREADS (1 << QSB_TB)
-#define QSB_T_F32 13           /* tile bits f32: pack + NVB + TB             */
-#define QSB_T_F64 12           /* tile bits f64: NVB + TB                    */
+#define QSB_T_F64 (QSB_NVB + QSB_TB)   /* tile bits f64: NVB + TB (11)               */
+#define QSB_T_F32 (QSB_T_F64 + 1)      /* tile bits f32: pack + NVB + TB (12)        */
+#define QSB_SLOTS (1 << QSB_T_F64)     /* 16-byte shared-memory slots of a tile       */
+#define QSB_SMEM_BYTES (QSB_SLOTS * 16)
+#define QSB_CTAS_PER_SM (512 / QSB_THREADS)
 #define QSB_MAX_RUNS 16
 #define QSB_BLOB_SMALL 4000    /* pass descriptor sizes (kernel parameter)   */
 #define QSB_BLOB_MEDIUM 12000
@@ -212,7 +223,7 @@ struct GSegment {              /* 16 bytes */
 
 #define QSB_MAX_COND 24        /* distinct outer conditions a pass can name through W */
 
-struct GRound {
+struct alignas(16) GRound {    /* the kernel steps through the round array in 16-byte units */
     uint32_t n_seg, seg_off16; /* GSegment array, 16-byte units from the blob start                  */
     uint32_t n_tph, tph_off16; /* GTPhase array                                                      */
     uint32_t flags, n_ang, pad[2]; /* flags bit0: apply the pending scalar at the end of the round; n_ang: GTAngle

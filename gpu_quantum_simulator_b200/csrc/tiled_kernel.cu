@@ -251,7 +251,7 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
 /* PEER: the scatter of a fused-exchange pass -- every amplitude goes straight into the shard of the rank
  * named by its victim bits (peer memory over NVLink), so the qubit exchange costs no extra sweep. */
 template <typename R, int BLOB, bool PEER>
-__global__ void __launch_bounds__(QSB_THREADS, 2)
+__global__ void __launch_bounds__(QSB_THREADS, QSB_CTAS_PER_SM)
 k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst, const __grid_constant__ PeerTab peers, uint32_t tile_base)
 {
     typedef VT<R> T; typedef typename T::V V; typedef typename T::S S;
@@ -277,7 +277,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     uint32_t tw = tid;
     {
         const int nc = (int)P.n_cond;
-        for (int i = 0; i < nc; i++) { const uint64_t m = P.cond[i]; if ((src_outer & m) == m) tw |= 256u << i; }
+        for (int i = 0; i < nc; i++) { const uint64_t m = P.cond[i]; if ((src_outer & m) == m) tw |= (uint32_t)QSB_THREADS << i; }
     }
     const int n_rounds = (int)P.n_rounds;
 
@@ -484,7 +484,7 @@ static int ensure_smem_optin(int device)
     static bool attr_set[64] = {false};
     const int dev = device & 63;
     if (!attr_set[dev]) {
-        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSB_SMEM_BYTES));
         attr_set[dev] = true;
     }
     return QSB_OK;
@@ -498,7 +498,7 @@ static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
     if (ntile == 0) { tile0 = 0; ntile = hp.hdr.n_tiles; }
     const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
-    k_tile_pass<R, BLOB, PEER><<<(unsigned)ntile, QSB_THREADS, 65536, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, (uint32_t)tile0);
+    k_tile_pass<R, BLOB, PEER><<<(unsigned)ntile, QSB_THREADS, QSB_SMEM_BYTES, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, (uint32_t)tile0);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
 }

@@ -1094,7 +1094,7 @@ struct PassBuilder {
                     if (mux) { slot_set(0, false); slot_set(1, false); }
                     else { slot_set(0, true); slot_set(0, false); }
                     if ((int)slot.size() != 2 * SET16 * 16) { qsb_set_error("internal: slot of %zu bytes", slot.size()); return QSB_ERR_ARG; }
-                    const uint32_t pm_new = tm8 | (wbits << 8);
+                    const uint32_t pm_new = tm8 | (wbits << QSB_TB);
                     if (sform == S_XDEF && next_group[vb] > 0) {
                         /* merge a deferred X into the gate it follows on the same vector bit: same slot, same predicate.
                          * An unconditional single-set gate takes the X's predicate (both coefficient sets identical). */

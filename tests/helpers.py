@@ -132,7 +132,7 @@ def hostcheck_run(circ_gates, n, precision=32, low_bits=0, state=None):
     L.qsb_hostcheck_run.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(Gate), C.c_size_t, C.c_void_p,
                                     C.POINTER(C.c_int), C.c_void_p]
     L.qsb_hostcheck_run.restype = C.c_int
-    T = 13 if precision == 32 else 12
+    T = L.qsb_hostcheck_tile_bits(precision)        # the tile geometry is a build-time switch (tiled.h QSB_TB)
     nloc = max(n, T)
     v = np.zeros(1 << nloc, dtype=np.complex128)
     if state is None:

@@ -40,7 +40,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
     GPass P; memcpy(&P, B, sizeof P);
     const int SET16 = QSB_SET16(f32), G16 = QSB_GROUP16(f32);
     const uint64_t loc_bytes = ((uint64_t)1 << nloc) * AMP;
-    std::vector<cd> regs((size_t)QSB_THREADS * QSB_NV * L), smem((size_t)4096 * L);
+    std::vector<cd> regs((size_t)QSB_THREADS * QSB_NV * L), smem((size_t)QSB_SLOTS * L);
     std::vector<uint32_t> xm(QSB_THREADS);
     std::vector<cd> pend(QSB_THREADS);
     auto amp_at = [&](uint64_t byte_off, int lane) -> uint64_t { return f32 ? (byte_off / 8 + lane) : byte_off / 16; };
@@ -68,7 +68,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
             for (int tid = 0; tid < QSB_THREADS; tid++) for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb[tid] ^= RD.thr_x[j];
             if (r > 0) for (int tid = 0; tid < QSB_THREADS; tid++) for (int v = 0; v < QSB_NV; v++) {
                 const uint32_t a = (sb[tid] & 0xffffu) ^ RD.vld_x[v];
-                if (a % 16 || a / 16 >= 4096) { bad++; continue; }
+                if (a % 16 || a / 16 >= QSB_SLOTS) { bad++; continue; }
                 for (int l = 0; l < L; l++) regs[((size_t)tid * QSB_NV + v) * L + l] = smem[(size_t)(a / 16) * L + l];
             }
             for (int tid = 0; tid < QSB_THREADS; tid++) pend[tid] = cd(1.0, 0.0);
@@ -133,7 +133,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                         if (!form) continue;
                         const uint8_t *c0 = gp + 32 + (size_t)vb * 2 * SET16 * 16, *c1 = c0 + (size_t)SET16 * 16;
                         for (int tid = 0; tid < QSB_THREADS; tid++) {
-                            const uint32_t tw = (uint32_t)tid | (W << 8);
+                            const uint32_t tw = (uint32_t)tid | (W << QSB_TB);
                             const bool pred = (tw & pm[vb]) == pm[vb];
                             const uint8_t *cs = pred ? c1 : c0;
                             const double a0 = rd.S(cs, 0), a1 = rd.S(cs, 1), a2 = rd.S(cs, 2), a3 = rd.S(cs, 3);
@@ -175,19 +175,19 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                 else if (std::abs(pend[tid] - cd(1.0, 0.0)) > 0) bad++;     /* a scalar nobody applies */
             }
             if (r + 1 < P.n_rounds) {
-                std::vector<int> written(4096, 0);
+                std::vector<int> written(QSB_SLOTS, 0);
                 for (int tid = 0; tid < QSB_THREADS; tid++) {
                     uint32_t ss = sb[tid] >> 16;
                     for (int b = 0; b < QSB_NVB; b++) if ((xm[tid] >> b) & 1) ss ^= RD.vst_x[1 << b];
                     xm[tid] = 0;
                     for (int v = 0; v < QSB_NV; v++) {
                         const uint32_t a = ss ^ RD.vst_x[v];
-                        if (a % 16 || a / 16 >= 4096) { bad++; continue; }
+                        if (a % 16 || a / 16 >= QSB_SLOTS) { bad++; continue; }
                         written[a / 16]++;
                         for (int l = 0; l < L; l++) smem[(size_t)(a / 16) * L + l] = regs[((size_t)tid * QSB_NV + v) * L + l];
                     }
                 }
-                for (int k = 0; k < 4096; k++) if (written[k] != 1) bad++;
+                for (int k = 0; k < QSB_SLOTS; k++) if (written[k] != 1) bad++;
             }
         }
         /* scatter */

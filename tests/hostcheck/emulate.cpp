@@ -36,8 +36,8 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
     const int phase_lanes = 8;                  /* lanes per 128-bit shared-memory phase (16-byte slots) */
     const uint64_t loc_mask = (1ULL << nloc) - 1;
     std::vector<cd> regs((size_t)QSB_THREADS * QSB_NV * L);
-    std::vector<cd> smem((size_t)4096 * L);
-    std::vector<int> written(4096);
+    std::vector<cd> smem((size_t)QSB_SLOTS * L);
+    std::vector<int> written(QSB_SLOTS);
     const int nr = (int)hp.hdr.n_rounds;
     for (uint64_t tile = 0; tile < hp.hdr.n_tiles; tile++) {
         uint64_t t = tile, outer = 0;
@@ -177,12 +177,12 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                     for (int v = 0; v < QSB_NV; v++) {
                         uint32_t slot = sb;
                         for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) slot ^= RD.vec[b].st;
-                        if (slot >= 4096) { rep.bad_slots++; continue; }
+                        if (slot >= QSB_SLOTS) { rep.bad_slots++; continue; }
                         written[slot]++;
                         for (int l = 0; l < L; l++) smem[(size_t)slot * L + l] = regs[((size_t)tid * QSB_NV + v) * L + l];
                     }
                 }
-                for (int s = 0; s < 4096; s++) if (written[s] != 1) rep.bad_slots++;
+                for (int s = 0; s < QSB_SLOTS; s++) if (written[s] != 1) rep.bad_slots++;
                 for (int w = 0; w < QSB_THREADS / phase_lanes; w++) for (int v = 0; v < QSB_NV; v++) {
                     std::set<uint32_t> banks;
                     for (int ln = 0; ln < phase_lanes; ln++) {
@@ -307,6 +307,9 @@ extern "C" void qsb_hostcheck_finish(void *hv, int *report5, int8_t *perm_out)
     for (int q = 0; q < 64; q++) perm_out[q] = h->plan.end_perm.pos[q];
     delete h;
 }
+
+/* tile bits of this build (the tile geometry is a build-time switch, tiled.h QSB_TB) */
+extern "C" int qsb_hostcheck_tile_bits(int prec) { return tiled_min_local_bits(prec, nullptr); }
 
 /* plan statistics for tuning: per pass "rounds ops | histogram of op codes" on stdout */
 extern "C" void qsb_hostcheck_describe(void *hv)
