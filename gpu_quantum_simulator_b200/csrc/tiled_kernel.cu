@@ -2,9 +2,9 @@
  * tiled_kernel.cu -- the sm_100a apply kernel: one launch = one PASS (one
  * read + one write of the local state), any number of gates.
  *
- * See tiled.h for the schedule this kernel interprets.  Per CTA (256 threads,
- * two CTAs per SM):
- *   1. gather: 16 x 128-bit loads per thread pull the 64 KiB tile straight from
+ * See tiled.h for the schedule this kernel interprets.  Per CTA (128 threads,
+ * four CTAs per SM; QSB_TB in tiled.h):
+ *   1. gather: 16 x 128-bit loads per thread pull the 32 KiB tile straight from
  *      HBM into registers; a warp instruction covers 128-byte contiguous segments
  *      (f32: one load = {re,re',im,im'} of an amplitude pair = two packed
  *      operands for FFMA2/FMUL2; f64: one (re,im) double2).
@@ -477,7 +477,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 }
 
 /* ------------------------------------------------------------------ launching */
-/* the opt-in to 64 KiB of dynamic shared memory is per device and per instantiation */
+/* the dynamic shared-memory size attribute (needed above 48 KiB, i.e. for the QSB_TB = 8 geometry) is per device and per instantiation */
 template <typename R, int BLOB, bool PEER>
 static int ensure_smem_optin(int device)
 {

@@ -66,7 +66,7 @@ typedef struct qsb_options {
     int32_t precision;    /* QSB_F32 | QSB_F64 (state dtype on the device)    */
     int32_t device;       /* CUDA ordinal, -1 = current                       */
     int32_t mode;         /* QSB_MODE_*                                       */
-    int32_t tile_bits;    /* reserved: the tile is 2^13 (f32) / 2^12 (f64) amplitudes */
+    int32_t tile_bits;    /* reserved: the tile is 2^12 (f32) / 2^11 (f64) amplitudes (build-time, csrc/tiled.h) */
     int32_t low_bits;     /* contiguous low index bits every tile keeps, 0 = default (4 f32 / 3 f64) */
     int32_t rank;         /* this process' shard, 0..world-1                  */
     int32_t world_size;   /* power of two; state sharded on the top log2(world) qubits */
