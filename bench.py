@@ -317,7 +317,8 @@ def run_ours(args):
                 "effective_gate_GBps": len(circ) * 2 * (1 << n) * amp_bytes / (ms_per_step * 1e-3) / 1e9,
                 "wall_ms_per_step": wall_ms / args.steps, "exchange_ms_per_step": xch_ms / args.steps,
                 "roofline": roofline, "at_30q": at_30q, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(pst["kernel_launches"]) * args.steps, "clocks": clocks}
+                "gpu_launches": int(pst["kernel_launches"]) * args.steps, "clocks": clocks,
+                "lib": q.lib.qsb_version().decode()}
         print(json.dumps(line))
     plan.close()
     sim.close()

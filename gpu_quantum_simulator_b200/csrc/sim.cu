@@ -204,7 +204,13 @@ extern "C" void qsb_options_default(qsb_options_t *o)
     o->rank = 0; o->world_size = 1; o->use_graph = 0;
 }
 
-extern "C" const char *qsb_version(void) { return QSB_VERSION; }
+/* the tile geometry is a build-time switch (tiled.h): keep it visible in every bench line and bug report */
+extern "C" const char *qsb_version(void)
+{
+    static char v[128];
+    if (!v[0]) snprintf(v, sizeof v, "%s; %d threads x %d CTAs/SM, tile bits f32/f64 = %d/%d", QSB_VERSION, QSB_THREADS, QSB_CTAS_PER_SM, QSB_T_F32, QSB_T_F64);
+    return v;
+}
 
 static int ilog2(int v) { int r = 0; while ((1 << r) < v) r++; return r; }
 
