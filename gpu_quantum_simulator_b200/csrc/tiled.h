@@ -58,7 +58,9 @@
 #define QSB_MAX_RUNS 16
 #define QSB_BLOB_SMALL 4000    /* pass descriptor sizes (kernel parameter)   */
 #define QSB_BLOB_MEDIUM 12000
+#ifndef QSB_BLOB_LARGE
 #define QSB_BLOB_LARGE 31744   /* + two pointers + the peer table stay below the 32764-byte parameter limit */
+#endif
 
 /* ---- op codes ---------------------------------------------------------- */
 enum {

@@ -100,6 +100,7 @@ namespace {
  * each op occupies a whole group, 160 bytes in f32 and 288 bytes in f64 */
 inline int max_pass_ops(bool f32) { return f32 ? 120 : 72; }
 const int MAX_PASS_ROUNDS = 32;
+const int QSB_PLAN_OVERFLOW = -100;   /* internal: serialise() could not fit the pass into QSB_BLOB_LARGE */
 
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
@@ -1208,7 +1209,7 @@ struct PassBuilder {
             gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size() + angstream[r].size();
         }
         const size_t total = off + 64;   /* slack: the group loop prefetches one group header past the last group */
-        if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_ERR_ARG; }
+        if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_PLAN_OVERFLOW; }
         hp.hdr.blob_bytes = (uint32_t)total;
         std::vector<uint8_t> &b = hp.blob;
         b.assign(total <= QSB_BLOB_SMALL ? QSB_BLOB_SMALL : total <= QSB_BLOB_MEDIUM ? QSB_BLOB_MEDIUM : QSB_BLOB_LARGE, 0);
@@ -1269,12 +1270,19 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     const int SWAP_MIN_OPS = opt && opt->reserved[0] > 0 ? opt->reserved[0] : 10;
 
     /* greedy op collection for one pass.  S0/n0: qubits / slots already resident. */
+    bool strict_count = false;
     auto collect = [&](uint64_t S0, int n0, std::vector<COp> &mine, std::vector<size_t> &mine_idx, uint64_t &S_out, int op_limit = 0) {
         uint64_t S = S0; int nS = n0;
         Blocker B; B.clear();
         mine.clear(); mine_idx.clear();
+        /* Budget of the pass descriptor.  A matrix op may take a whole group (the worst case max_pass_ops is sized
+         * for); a phase gate is usually one 16/32-byte entry of a thread-phase list, so it is charged a quarter
+         * (QFT ladders: hundreds of phases per pass).  Should the optimistic count overflow the descriptor after
+         * all, the caller retries with `strict` (every op charged in full). */
         const int max_ops = op_limit > 0 ? op_limit : max_pass_ops(M.f32);
-        for (size_t i = first_open; i < N && (int)mine.size() < max_ops; i++) {
+        const bool weighted = op_limit == 0 && !strict_count;
+        int budget = 4 * max_ops;
+        for (size_t i = first_open; i < N && budget > 0; i++) {
             if (done[i]) continue;
             const COp &o = cops[i];
             bool can = B.ok(o);
@@ -1284,7 +1292,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                 else if (nS < M.T) { S |= 1ULL << o.target; nS++; }
                 else can = false;
             }
-            if (can) { mine.push_back(o); mine_idx.push_back(i); }
+            if (can) { mine.push_back(o); mine_idx.push_back(i); budget -= (weighted && o.kind == C_PHASE) ? 1 : 4; }
             else { B.block(o); if (B.full >= n) break; }
         }
         S_out = S;
@@ -1296,12 +1304,12 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         std::vector<char> used;
         int rc = pb.build_rounds(mine, used, !allow_empty && mine_idx.size() < left);
         if (rc) return rc;
+        rc = pb.serialise();
+        if (rc) return rc;          /* QSB_PLAN_OVERFLOW: nothing is committed yet, the caller collects again */
         size_t consumed = 0;
         for (size_t k = 0; k < mine_idx.size(); k++) if (used[k]) { done[mine_idx[k]] = 1; left--; consumed++; }
         if (!consumed && !allow_empty) { qsb_set_error("scheduler made no progress inside a pass"); return QSB_ERR_ARG; }
         while (first_open < N && done[first_open]) first_open++;
-        rc = pb.serialise();
-        if (rc) return rc;
         if (pos_map) for (int q = 0; q < n; q++) if (perm.pos[q] < nloc) perm.pos[q] = pos_map[perm.pos[q]];
         plan->passes.push_back(std::move(pb.hp));
         return QSB_OK;
@@ -1329,7 +1337,11 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         if (!want_swap) {
             if (mine.empty()) { qsb_set_error("scheduler made no progress (gate on a non-local qubit?)"); return QSB_ERR_ARG; }
             int rc = emit_pass(S, 0, nullptr, mine, mine_idx, false);
-            if (rc) return rc;
+            if (rc == QSB_PLAN_OVERFLOW) {      /* the optimistic phase-gate budget did not fit: charge every op in full */
+                strict_count = true; collect(lowS, M.a, mine, mine_idx, S); strict_count = false;
+                rc = emit_pass(S, 0, nullptr, mine, mine_idx, false);
+            }
+            if (rc) return rc == QSB_PLAN_OVERFLOW ? QSB_ERR_ARG : rc;
             continue;
         }
 
@@ -1375,7 +1387,11 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             /* a fused-exchange pass also carries the peer table as a kernel parameter: keep its descriptor in the medium class */
             collect(S0, n0, mine, mine_idx, S, fuse ? max_pass_ops(M.f32) / 3 : 0);
             int rc = emit_pass(S, forced, pos_map, mine, mine_idx, true, fuse);
-            if (rc) return rc;
+            if (rc == QSB_PLAN_OVERFLOW) {
+                strict_count = true; collect(S0, n0, mine, mine_idx, S, fuse ? max_pass_ops(M.f32) / 3 : 0); strict_count = false;
+                rc = emit_pass(S, forced, pos_map, mine, mine_idx, true, fuse);
+            }
+            if (rc) return rc == QSB_PLAN_OVERFLOW ? QSB_ERR_ARG : rc;
         }
         if (!fuse) {
             /* exchange marker: top g local positions <-> rank bits (NCCL all-to-all of contiguous chunks) */
