@@ -527,6 +527,7 @@ int qsb_parse_qasm_string(const char *text, int *num_qubits, qsb_gate_t **gates,
         long a = strtol(s, &e1, 10);
         long b = strtol(e1, &e2, 10);
         if (e2 == e1) { free(c.defs); qsb_set_error("bad \"<num_q> <num_g>\" header"); return QSB_ERR_PARSE; }
+        if (a < 1 || a > 62) { free(c.defs); qsb_set_error("bad qubit count %ld in the \"<num_q> <num_g>\" header", a); return QSB_ERR_PARSE; }
         (void)b; /* the gate count is implied by the text */
         c.nq = (int)a; s = e2;
     }

@@ -167,3 +167,50 @@ def test_front_end_errors_of_the_superset():
                 'qubit[2] q;\ngate g a { h b; }\ng q[0];\n'):                     # unknown qubit argument
         with pytest.raises(q.QsbError):
             q.parse_qasm_string(HDR + bad)
+
+
+def test_cuda_variant_header_rejects_absurd_qubit_counts():
+    for head in ("0 4", "63 4", "39999999999 4", "-3 4"):
+        with pytest.raises((q.QsbError, Exception)):
+            q.parse_qasm_string(head + "\nh q[0];\n")
+
+
+def test_mutated_programs_never_yield_invalid_gates():
+    """Robustness: random edits of valid programs either fail with a message or parse into gates whose target
+    and controls lie inside the declared register (the reference exits on the first unknown token, :213)."""
+    import ctypes as C
+    import random
+    rnd = random.Random(7)
+    base = [
+        'OPENQASM 3.0;\ninclude "stdgates.inc";\nqubit[4] q;\nh q[0];\ncx q[0], q[1];\nrz(0.5) q[2];\nsx q[3];\ntdg q[1];\n',
+        'OPENQASM 3.0;\ninclude "stdgates.inc";\nqubit q[3];\nh $0;\ncx $0, $1;\nrz(1.25) $2;\n',
+        'OPENQASM 3.0;\ninclude "stdgates.inc";\nqubit[3] a;\nqubit[2] b;\ngate foo(t) x, y { rx(t/2) x; cx x, y; p(pi*t) y; }\n'
+        'foo(0.3) a[0], b[1];\nctrl @ inv @ foo(1) a[1], a[2], b[0];\npow(3) @ s a;\ngphase(0.1);\nnegctrl(2) @ x a[0], a[1], b[0];\n',
+        '3 4\nh q[0];\ncx q[0], q[1];\nrz(0.5) q[2];\nx q[1];\n',
+    ]
+    tokens = ["q[", "]", "(", ")", ",", ";", "{", "}", "@", "pi", "ctrl", "gate", "qubit", "$", "9999999999", "-", "1e309", "/0",
+              "inv", "pow(", "rz(", "\n", "\r\n", "//", "/*", "\"", "[" * 50, "(" * 50, "a" * 300, "q[-1]", "q[4]", "q[99999999999]"]
+    parsed = failed = 0
+    for _ in range(3000):
+        s = rnd.choice(base)
+        for _ in range(rnd.randint(1, 6)):
+            k, pos = rnd.random(), rnd.randrange(len(s) + 1)
+            if k < 0.3 and len(s) > 2:
+                s = s[:pos] + s[min(len(s), pos + rnd.randint(1, 8)):]
+            elif k < 0.7:
+                s = s[:pos] + rnd.choice(tokens) + s[pos:]
+            else:
+                s = s[:pos] + chr(rnd.randint(1, 255)) + s[pos + 1:]
+        nq, gp, n = C.c_int(), C.POINTER(q.Gate)(), C.c_size_t()
+        rc = q.lib.qsb_parse_qasm_string(s.encode("latin-1", "replace"), C.byref(nq), C.byref(gp), C.byref(n))
+        if rc == 0:
+            parsed += 1
+            assert 0 < nq.value <= 62
+            for i in range(n.value):
+                g = gp[i]
+                assert 0 <= g.target < nq.value and not (g.controls >> nq.value) and not (g.controls >> g.target) & 1
+            q.lib.qsb_free(gp)
+        else:
+            failed += 1
+            assert q.lib.qsb_last_error()
+    assert parsed > 100 and failed > 100
