@@ -426,6 +426,12 @@ extern "C" int qsb_execute(qsb_t *s, qsb_plan_t *p)
 {
     if (!s || !p) { qsb_set_error("qsb_execute: null argument"); return QSB_ERR_ARG; }
     if (p->n != s->n || p->prec != s->prec || p->world != s->world) { qsb_set_error("plan was built for a different machine"); return QSB_ERR_ARG; }
+    /* fused passes leave the qubits permuted, and a tiled plan addresses the layout it was made for */
+    if (p->mode == QSB_MODE_TILED && !tiled_plan_starts_at(p->tiled, s->perm)) {
+        qsb_set_error("plan was built for another qubit layout: the state has moved since qsb_plan_create "
+                      "(a plan runs once per layout: qsb_reset / qsb_load_state to its layout, or plan again)");
+        return QSB_ERR_ARG;
+    }
     QSB_CUDA(cudaSetDevice(s->device));
     const bool graphed = s->opt.use_graph && p->mode == QSB_MODE_TILED && s->world == 1;
     if (graphed && (!p->graph_exec || p->graph_state != s->state)) {

@@ -296,6 +296,7 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
                      TiledPlan **out, qsb_run_stats_t *stats);
 void tiled_plan_free(TiledPlan *p);
 void tiled_plan_end_perm(const TiledPlan *p, BitPerm *out);   /* qubit layout the plan leaves behind */
+bool tiled_plan_starts_at(const TiledPlan *p, const BitPerm &perm);   /* was the plan made for this layout? */
 struct qsb_sim;
 int tiled_execute(qsb_sim *s, TiledPlan *p);
 double tiled_last_exchange_ms(const TiledPlan *p);

@@ -50,6 +50,11 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
 
 void tiled_plan_free(TiledPlan *p) { delete p; }
 void tiled_plan_end_perm(const TiledPlan *p, BitPerm *out) { *out = p->end_perm; }
+bool tiled_plan_starts_at(const TiledPlan *p, const BitPerm &perm)
+{
+    for (int q = 0; q < p->n; q++) if (p->start_perm.pos[q] != perm.pos[q]) return false;
+    return true;
+}
 double tiled_last_exchange_ms(const TiledPlan *p) { return p ? p->last_exchange_ms : 0.0; }
 
 /* ------------------------------------------------------------------ NCCL (dlopen) */

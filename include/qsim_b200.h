@@ -120,6 +120,10 @@ int qsb_precision(const qsb_t *s);
  * naive.cu:163-189) and the host "preprocessing" of the CUDA variants
  * (preproces.cu:215-269, 4x4.cu:327-501, 4x4_permute.cu:350-434). */
 int qsb_apply_gates(qsb_t *s, const qsb_gate_t *gates, size_t n); /* plan + execute + free */
+/* A plan is made for the qubit layout the handle has at qsb_plan_create (the identity after qsb_create /
+ * qsb_reset; fused passes leave the qubits permuted, qsb_get_layout).  qsb_execute from any other layout is
+ * refused with QSB_ERR_ARG instead of computing on the wrong bits: to run a plan again, qsb_reset first (or
+ * plan again from the current layout, which is what qsb_apply_gates does). */
 int qsb_plan_create(qsb_t *s, const qsb_gate_t *gates, size_t n, qsb_plan_t **out);
 int qsb_execute(qsb_t *s, qsb_plan_t *plan);
 void qsb_plan_destroy(qsb_plan_t *plan);

@@ -52,9 +52,11 @@ def main():
                 plan = s.plan(q.gates_from_circuit(circ))
                 st = plan.stats()
                 for _ in range(3):
+                    s.reset()
                     s.execute(plan)
                 reps, ms = 10, 0.0
                 for _ in range(reps):
+                    s.reset()
                     ms += s.execute(plan)["device_ms"]
                 ms /= reps
                 floor = st["passes"] * 2 * (1 << N) * (8 if prec == q.F32 else 16) / 6546.6e9 * 1e3

@@ -19,11 +19,13 @@ def main():
             with q.Simulator(n, use_graph=use_graph) as s:
                 plan = s.plan(gates)
                 for _ in range(5):
+                    s.reset()
                     s.execute(plan)
                 reps = 200
                 dev = 0.0
                 t0 = time.perf_counter()
                 for _ in range(reps):
+                    s.reset()
                     dev += s.execute(plan)["device_ms"]
                 wall = (time.perf_counter() - t0) * 1e3
                 st = plan.stats()

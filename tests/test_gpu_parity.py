@@ -323,3 +323,25 @@ def test_phase_ladders_and_swaps(n, precision):
     assert np.max(np.abs(got - want)) <= TOL[precision]
     sweep, _ = run_gpu(circ, n, precision, mode=q.MODE_SWEEP)
     assert np.max(np.abs(got - sweep)) <= 2 * TOL[precision]
+
+
+def test_a_plan_is_refused_from_another_layout():
+    """Fused passes leave the qubits permuted; executing a plan from a layout it was not made for would compute on
+    the wrong bits, so it is an error (qsim_b200.h).  After a reset the same plan runs again, bit-identically."""
+    n = 16
+    gates = q.gates_from_circuit(circuits.random_layered(n, depth=6, seed=9))
+    with q.Simulator(n) as s:
+        plan = s.plan(gates)
+        s.execute(plan)
+        first = s.state()
+        perm, _ = s.layout()
+        if not np.array_equal(perm[:n], np.arange(n)):
+            with pytest.raises(q.QsbError) as e:
+                s.execute(plan)
+            assert "another qubit layout" in str(e.value)
+            assert np.array_equal(s.state(), first)          # nothing ran
+        s.reset()
+        s.execute(plan)
+        assert np.array_equal(s.state(), first)
+        s.apply(gates)                                       # plans from the current layout: always fine
+        plan.close()
