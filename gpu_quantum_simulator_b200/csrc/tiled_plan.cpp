@@ -104,7 +104,7 @@ const int QSB_PLAN_OVERFLOW = -100;   /* internal: serialise() could not fit the
 
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
-    bool f32, lazy_diag, defer_diag, sink_phases;
+    bool f32, lazy_diag, defer_diag, sink_phases, tile_search;
     int trim_thin, cost_cap;
     bool fused_exchange, force_top;
 };
@@ -1241,6 +1241,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.force_top = g > 0 && opt && opt->reserved[5] == 3;        /* reserved[5] = 3: NCCL-style plan executed as a pipelined exchange */
     M.fused_exchange = g > 0 && opt && opt->reserved[5] == 1;   /* reserved[5] = 1: exchanges fused into the preceding pass (peer stores) */
+    M.tile_search = !(opt && opt->reserved[6] == 2);   /* reserved[6] = 2: first-come tile choice (A/B runs) */
     M.sink_phases = !(opt && opt->reserved[6] == 1);   /* reserved[6] = 1: keep thread-level phases in the round that accepted them (A/B) */
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
@@ -1297,6 +1298,38 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         }
         S_out = S;
     };
+    /* ops a pass would run if exactly the qubits of S were resident (no growth): the score of a tile choice */
+    auto count_fixed = [&](uint64_t S) -> int {
+        Blocker B; B.clear();
+        int score = 0, budget = 4 * max_pass_ops(M.f32);
+        for (size_t i = first_open; i < N && budget > 0; i++) {
+            if (done[i]) continue;
+            const COp &o = cops[i];
+            bool can = B.ok(o);
+            if (can && o.target >= 0 && (perm.pos[o.target] >= nloc || !((S >> o.target) & 1))) can = false;
+            if (can) { score += o.target >= 0 ? 8 : 1; budget -= o.kind == C_PHASE ? 1 : 4; }
+            else { B.block(o); if (B.full >= n) break; }
+        }
+        return score;
+    };
+    /* hill climbing over the tile: trade one chosen qubit for one outside while the pass gets more ops */
+    auto improve_tile = [&](uint64_t lowS, uint64_t S) -> uint64_t {
+        int best = count_fixed(S);
+        for (int sweep = 0; sweep < 3; sweep++) {
+            bool any = false;
+            for (int qo = 0; qo < n; qo++) {
+                if (!((S >> qo) & 1) || ((lowS >> qo) & 1)) continue;
+                for (int qi = 0; qi < n; qi++) {
+                    if (((S >> qi) & 1) || perm.pos[qi] >= nloc) continue;
+                    const uint64_t S2 = (S & ~(1ULL << qo)) | (1ULL << qi);
+                    const int c = count_fixed(S2);
+                    if (c > best) { best = c; S = S2; any = true; break; }
+                }
+            }
+            if (!any) break;
+        }
+        return S;
+    };
     auto emit_pass = [&](uint64_t S, uint64_t forced_pos, const int8_t *pos_map, const std::vector<COp> &mine,
                          const std::vector<size_t> &mine_idx, bool allow_empty, bool fuse_exchange = false) -> int {
         PassBuilder pb(M, perm);
@@ -1335,6 +1368,11 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             if (blocked_global && nd < SWAP_MIN_OPS) want_swap = true;
         }
         if (!want_swap) {
+            if (M.tile_search && !mine.empty()) {
+                const uint64_t S2 = improve_tile(lowS, S);
+                /* collect again with the tile fixed: every slot is taken, so no qubit joins */
+                if (S2 != S) collect(S2, M.T, mine, mine_idx, S);
+            }
             if (mine.empty()) { qsb_set_error("scheduler made no progress (gate on a non-local qubit?)"); return QSB_ERR_ARG; }
             int rc = emit_pass(S, 0, nullptr, mine, mine_idx, false);
             if (rc == QSB_PLAN_OVERFLOW) {      /* the optimistic phase-gate budget did not fit: charge every op in full */

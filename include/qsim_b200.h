@@ -82,7 +82,7 @@ typedef struct qsb_options {
      *   [4] 1 = do not defer phase gates that touch a vector bit; 2 = no 2x2 products of consecutive one-qubit gates
      *   [5] exchange flavour: 1 fused peer scatter, 2 NCCL all-to-all, 3 pipelined copy-engine exchange
      *       (0: chosen by qsb_comm_init -- pipelined at 2 ranks, fused beyond, NCCL if peers cannot be mapped)
-     *   [6] 1 = do not sink thread-level phases to later rounds                                            */
+     *   [6] 1 = do not sink thread-level phases to later rounds; 2 = first-come tile choice (no hill climbing) */
     int32_t reserved[7];
 } qsb_options_t;
 
