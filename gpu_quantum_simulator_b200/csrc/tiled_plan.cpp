@@ -1354,6 +1354,11 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         std::vector<COp> mine; std::vector<size_t> mine_idx; uint64_t S = 0;
         /* the low positions always occupy `a` tile slots, whether or not a logical qubit lives there */
         collect(lowS, M.a, mine, mine_idx, S);
+        if (M.tile_search && !mine.empty()) {
+            const uint64_t S2 = improve_tile(lowS, S);
+            /* collect again with the tile fixed: every slot is taken, so no qubit joins */
+            if (S2 != S) collect(S2, M.T, mine, mine_idx, S);
+        }
 
         bool want_swap = false;
         if (g > 0) {
@@ -1368,11 +1373,6 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             if (blocked_global && nd < SWAP_MIN_OPS) want_swap = true;
         }
         if (!want_swap) {
-            if (M.tile_search && !mine.empty()) {
-                const uint64_t S2 = improve_tile(lowS, S);
-                /* collect again with the tile fixed: every slot is taken, so no qubit joins */
-                if (S2 != S) collect(S2, M.T, mine, mine_idx, S);
-            }
             if (mine.empty()) { qsb_set_error("scheduler made no progress (gate on a non-local qubit?)"); return QSB_ERR_ARG; }
             int rc = emit_pass(S, 0, nullptr, mine, mine_idx, false);
             if (rc == QSB_PLAN_OVERFLOW) {      /* the optimistic phase-gate budget did not fit: charge every op in full */
