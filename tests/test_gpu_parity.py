@@ -210,12 +210,13 @@ def test_cx_heavy_circuits_vs_oracle(precision):
 
 
 def test_planner_knobs_do_not_change_the_result():
-    """Fusion depth cap, lazy diagonals, phase sinking and tail trimming only reschedule: same state (f64, 1e-12)."""
+    """Fusion depth cap, lazy diagonals, phase sinking, tail trimming, 2x2 products and the tile choice only
+    reschedule: same state (f64, 1e-12)."""
     n = 24
     circ = circuits.random_layered(n, depth=8, seed=11) + circuits.qft(n, with_h_layer=False, swaps=False)[:200]
     gates = q.gates_from_circuit(circ)
     ref = None
-    for reserved in (None, [0, 0, 0, 12], [0, 2, 1, 0], [0, 0, 0, 0, 1, 0, 1], [0, 0, 3, 20, 0, 0, 0]):
+    for reserved in (None, [0, 0, 0, 12], [0, 2, 1, 0], [0, 0, 0, 0, 1, 0, 1], [0, 0, 3, 20, 0, 0, 0], [0, 0, 0, 0, 2, 0, 2]):
         with q.Simulator(n, precision=F64, reserved=reserved) as s:
             st = s.apply(gates)
             v = s.state_native().copy()
