@@ -234,6 +234,18 @@ def run_ours(args):
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": "k_tile_pass", "bytes_per_launch": bytes_per_launch,
                     "avg_launch_ms": pass_ms, "peak_source": peak_src}
+        # second limit of the same kernel: every round but the first of a pass moves the whole tile
+        # through shared memory once in each direction; peak = SMs x 128 B/clk x SM clock
+        try:
+            props = torch.cuda.get_device_properties(local_rank)
+            smem_peak = props.multi_processor_count * 128 * (props.clock_rate * 1e3) / 1e9          # GB/s at the max SM clock
+            exchanges = max(pst["rounds"] - pst["passes"], 0)
+            smem_bytes = exchanges * bytes_per_launch
+            smem_achieved = smem_bytes / ((dev_ms - xch_ms) / steps * 1e-3) / 1e9
+            roofline["shared_memory"] = {"achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s", "frac": smem_achieved / smem_peak,
+                                         "exchanges_per_circuit": exchanges, "bytes_per_exchange": bytes_per_launch}
+        except Exception:
+            pass
         return {"n": n, "circ": circ, "sim": sim, "plan": plan, "pst": pst, "ms_per_step": ms_per_step,
                 "value": len(circ) / (ms_per_step * 1e-3), "wall_ms": wall_ms, "xch_ms": xch_ms, "clocks": clocks,
                 "roofline": roofline, "n_loc_amps": n_loc_amps}
