@@ -10,6 +10,8 @@
  *   <number_of_measurement> > 0 with --shots: "MEASUREMENT: <bits> (%ld)" (quantum_simulator.c:68-73)
  *   --save-state FILE / --load-state FILE   raw shard + qubit map after / before the circuit (checkpoint;
  *                       the reference keeps the state only in memory, quantum_simulator.c:75)
+ *   --plan-only [--gpus N]   host-side fusion only (no GPU needed): one JSON line with the passes, rounds, ops and
+ *                       qubit exchanges the circuit would run as on N ranks, instead of running it
  * Errors go to stdout followed by exit(1), like the reference (:56,:129,:213-219).
  */
 #include <stdio.h>
@@ -53,7 +55,7 @@ int main(int argc, char **argv)
 {
     const char *file = NULL, *dump_bin = NULL, *save_state = NULL, *load_state = NULL;
     long num_m = 0;
-    int precision = 32, dump = 0, shots = 0, prec_out = 0, profile = 0, sweep = 0, have_m = 0;
+    int precision = 32, dump = 0, shots = 0, prec_out = 0, profile = 0, sweep = 0, have_m = 0, plan_only = 0, gpus = 1;
     unsigned long long seed = 0; int have_seed = 0;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--precision") && i + 1 < argc) precision = atoi(argv[++i]);
@@ -65,6 +67,8 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--shots")) shots = 1;
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) { seed = strtoull(argv[++i], NULL, 10); have_seed = 1; }
         else if (!strcmp(argv[i], "--profile")) profile = 1;
+        else if (!strcmp(argv[i], "--plan-only")) plan_only = 1;
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--sweep")) sweep = 1;
         else if (!file) file = argv[i];
         else if (!have_m) { num_m = atol(argv[i]); have_m = 1; }
@@ -86,6 +90,17 @@ int main(int argc, char **argv)
     qsb_options_t o; qsb_options_default(&o);
     o.precision = precision == 64 ? QSB_F64 : QSB_F32;
     if (sweep) o.mode = QSB_MODE_SWEEP;
+    if (plan_only) {
+        qsb_run_stats_t st;
+        o.world_size = gpus;
+        if (qsb_plan_dry_run(nq, &o, gates, n, &st)) { printf("%s\n", qsb_last_error()); return 1; }
+        printf("{\"qubits\": %d, \"gates\": %llu, \"ranks\": %d, \"precision\": %d, \"passes\": %u, \"rounds\": %u, \"device_ops\": %llu, "
+               "\"exchanges\": %u, \"bytes_moved_per_rank\": %llu, \"bytes_exchanged_per_rank\": %llu, \"plan_ms\": %.3f, \"lib\": \"%s\"}\n",
+               nq, (unsigned long long)st.source_gates, gpus, precision == 64 ? 64 : 32, st.passes, st.rounds, (unsigned long long)st.device_ops,
+               st.swaps, (unsigned long long)st.bytes_moved, (unsigned long long)st.bytes_exchanged, st.plan_ms, qsb_version());
+        qsb_free(gates);
+        return 0;
+    }
     qsb_t *s = NULL;
     rc = qsb_create(&s, nq, &o);
     if (!rc && load_state) rc = qsb_load_state(s, load_state);

@@ -72,6 +72,37 @@ static bool canon_one(const double *m, uint64_t controls, int target, std::vecto
         out.push_back(c);
     } else {
         c.kind = C_MAT; c.target = target; c.ctrl = controls; memcpy(c.m, m, sizeof c.m);
+        /* e^{i phi} x (a real or an rx-form matrix), e.g. SX = e^{i pi/4} RX(pi/2) (quantum_simulator.c:187): pull the
+         * scalar out -- a global factor, or a phase gate on the controls -- so that the gate runs in a cheap form
+         * instead of the general complex one */
+        const bool real_form = m[1] == 0 && m[3] == 0 && m[5] == 0 && m[7] == 0;
+        const bool rx_form = m[1] == 0 && m[7] == 0 && m[2] == 0 && m[4] == 0;
+        const bool j_form = m[0] == 0 && m[6] == 0 && m[3] == 0 && m[5] == 0;
+        if (!real_form && !rx_form && !j_form) {
+            const int piv = (m[0] != 0 || m[1] != 0) ? 0 : 2;           /* first non-zero entry of the first row */
+            const double mag = hypot(m[piv], m[piv + 1]);
+            const double ur = m[piv] / mag, ui = m[piv + 1] / mag;     /* e^{i phi} */
+            double r[8], sc = 0;
+            for (int k = 0; k < 4; k++) {                              /* r = conj(u) * m */
+                r[2 * k] = m[2 * k] * ur + m[2 * k + 1] * ui;
+                r[2 * k + 1] = m[2 * k + 1] * ur - m[2 * k] * ui;
+                sc = fmax(sc, fmax(fabs(r[2 * k]), fabs(r[2 * k + 1])));
+            }
+            for (int k = 0; k < 8; k++) if (fabs(r[k]) <= 4e-16 * sc) r[k] = 0.0;
+            const bool r_real = r[1] == 0 && r[3] == 0 && r[5] == 0 && r[7] == 0;
+            const bool r_rx = r[1] == 0 && r[7] == 0 && r[2] == 0 && r[4] == 0;
+            if (r_real || r_rx) {
+                memcpy(c.m, r, sizeof c.m);
+                if (controls == 0) {
+                    const double gr = gphase[0] * ur - gphase[1] * ui, gi = gphase[0] * ui + gphase[1] * ur;
+                    gphase[0] = gr; gphase[1] = gi;
+                } else {
+                    COp ph; memset(&ph, 0, sizeof ph);
+                    ph.kind = C_PHASE; ph.ctrl = controls; ph.target = -1; ph.m[0] = ur; ph.m[1] = ui;
+                    out.push_back(ph);
+                }
+            }
+        }
         out.push_back(c);
     }
     return true;

@@ -218,3 +218,30 @@ def test_same_qubit_products(precision):
     fused = q.plan_dry_run(n, gates, precision=precision)
     plain = q.plan_dry_run(n, gates, precision=precision, reserved=[0, 0, 0, 0, 2])
     assert fused["device_ops"] < 0.9 * plain["device_ops"]
+
+
+def test_sx_runs_in_a_cheap_form():
+    """SX = e^{i pi/4} RX(pi/2) (quantum_simulator.c:187): the scalar is pulled out (global factor, or a phase gate on
+    the controls), the rest is an rx-form matrix -- no general complex op is left in the plan."""
+    n = 13
+    circ = [("sx", (k,), ()) for k in range(n)] + [("cx", (0, 5), ()), ("sx", (5,), ()), ("rz", (5,), (0.3,)), ("sx", (5,), ())]
+    gates = q.gates_from_circuit(circ)
+    # a controlled SX: phase on the control + controlled rx-form
+    g = q.Gate()
+    g.controls, g.target = 1 << 3, 7
+    for k, v in enumerate([0.5, 0.5, 0.5, -0.5, 0.5, -0.5, 0.5, 0.5]):
+        g.m[k] = v
+    arr = (q.Gate * (len(gates) + 1))(*list(gates), g)
+    want = helpers.oracle_run_circuit(circ, n)
+    idx = np.arange(1 << n)
+    sel = ((idx >> 3) & 1 == 1) & ((idx >> 7) & 1 == 0)
+    a, b = want[idx[sel]].copy(), want[idx[sel] | (1 << 7)].copy()
+    want[idx[sel]] = (0.5 + 0.5j) * a + (0.5 - 0.5j) * b
+    want[idx[sel] | (1 << 7)] = (0.5 - 0.5j) * a + (0.5 + 0.5j) * b
+    for precision in (32, 64):
+        for blob in (False, True):
+            helpers.hostcheck_use_blob(blob)
+            got, rep = helpers.hostcheck_run(arr, n, precision)
+            assert rep["bad_slots"] == 0
+            assert np.max(np.abs(got - want)) < (2e-6 if blob and precision == 32 else 1e-12)
+    helpers.hostcheck_use_blob(False)
