@@ -506,7 +506,15 @@ struct PassBuilder {
                         acc.push_back((int)i); ctrl_used |= cbits; creal_all |= creal;
                         if (commit) { done[i] = 1; left--; }
                         if (per_tb && o.target >= 0 && tile_of_qubit[o.target] != P && o.kind != C_X) (*per_tb)[tile_of_qubit[o.target]]++;
-                        if (o.kind == C_X && tile_of_qubit[o.target] != P) closed |= 1ULL << o.target;
+                        if (o.kind == C_X && tile_of_qubit[o.target] != P) {
+                            /* a deferred X is free but ends its qubit's turn in this round; in a chain of CX on one
+                             * target (Toffoli decompositions) that would cost a round per CX: run those as matrices */
+                            int chain = 0;
+                            const int need = 3;     /* 1 or 2 more CX on the target: the layered workloads, unchanged */
+                            for (size_t j = i + 1; j < n && j < i + 64 && chain < need; j++)
+                                if (!done[j] && ops[j].kind == C_X && ops[j].target == o.target) chain++;
+                            if (chain < need) closed |= 1ULL << o.target;
+                        }
                         /* a matrix with a small m00 (in either variant of a multiplexer) is cheapest as a pivoted unit
                          * form + deferred X (see emit): that needs it to be the last gate on its qubit in this round */
                         if ((o.kind == C_MAT || o.kind == C_MUX) && tile_of_qubit[o.target] != P &&

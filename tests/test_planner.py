@@ -245,3 +245,14 @@ def test_sx_runs_in_a_cheap_form():
             assert rep["bad_slots"] == 0
             assert np.max(np.abs(got - want)) < (2e-6 if blob and precision == 32 else 1e-12)
     helpers.hostcheck_use_blob(False)
+
+
+def test_cx_chains_on_one_target_share_a_round():
+    """A deferred X is free but closes its qubit for the round; a chain of CX on one target (the Toffoli
+    decompositions of grover_3_18.qasm) would then cost a round per CX.  Chains run their X as matrices instead:
+    the shipped Grover circuit needs a third of the rounds, the layered workloads keep their plans."""
+    circ, n, amps, _ = helpers.load_case(os.path.join(helpers.GOLDEN, "grover_3_18.npz"))
+    st = q.plan_dry_run(n, q.gates_from_circuit(circ), precision=32)
+    assert st["source_gates"] == 2445 and st["rounds"] < 450 and st["passes"] < 60        # was 1011 rounds in 140 passes
+    got, rep = helpers.hostcheck_run(q.gates_from_circuit(circ), n, 64)
+    assert rep["bad_slots"] == 0 and np.max(np.abs(got - amps)) < 1e-12
