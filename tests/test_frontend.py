@@ -214,3 +214,17 @@ def test_mutated_programs_never_yield_invalid_gates():
             failed += 1
             assert q.lib.qsb_last_error()
     assert parsed > 100 and failed > 100
+
+
+def test_cli_plan_only_needs_no_gpu(tmp_path):
+    import json
+    import subprocess
+    path = tmp_path / "c.qasm"
+    path.write_text(circuits.to_qasm(circuits.random_layered(30, 20, 12345), 30))
+    exe = os.path.join(helpers.ROOT, "gpu_quantum_simulator_b200", "bin", "qsim")
+    r = subprocess.run([exe, str(path), "--plan-only", "--gpus", "4"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout
+    d = json.loads(r.stdout)
+    assert d["qubits"] == 30 and d["gates"] == 900 and d["ranks"] == 4 and d["exchanges"] >= 1 and 0 < d["passes"] < 60
+    r = subprocess.run([exe, str(tmp_path / "missing.qasm"), "--plan-only"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "cannot open circuit file" in r.stdout
