@@ -3,7 +3,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqsim_b200%s.so" % os.environ.get("QSB_LIB_SUFFIX", ""))
+_SUFFIX = os.environ.get("QSB_LIB_SUFFIX", "")
+# A/B builds (make SUFFIX=_x EXTRA=...) live in csrc/_build_x/, never next to the product library
+LIB_PATH = os.path.join(_HERE, "csrc", "_build" + _SUFFIX, "libqsim_b200.so") if _SUFFIX else os.path.join(_HERE, "libqsim_b200.so")
 
 F32, F64 = 32, 64
 MODE_TILED, MODE_SWEEP = 0, 1
