@@ -241,7 +241,7 @@ struct GPass {
     uint64_t src_fixed;        /* constant source index bits (rank bits): predicates see them         */
     uint64_t n_tiles;
     uint32_t nloc, rounds_off16;
-    uint32_t n_cond, pad;
+    uint32_t n_cond, flags;    /* flags: QSB_PASS_SYNC_SCATTER */
     uint64_t cond[QSB_MAX_COND]; /* outer conditions: W bit i = (outer & cond[i]) == cond[i]          */
     uint64_t ld_thr[QSB_TB];   /* local BYTE offset of thread bit j, round-0 gather                   */
     uint64_t st_thr[QSB_TB];   /*                                    last-round scatter               */
@@ -253,6 +253,10 @@ struct GPass {
      * field is non-zero only in a fused-exchange pass (peer stores), whose kernel variant adds the fields
      * up and indexes the peer-pointer table with the result. */
 };
+/* An in-place pass whose only round relocates qubits inside the tile (the permutation pass in front of an NCCL /
+ * pipelined exchange) stores to addresses OTHER threads of the CTA gather from; with a single round there is no
+ * exchange barrier between the gather and the scatter, so the kernel must place one. */
+#define QSB_PASS_SYNC_SCATTER 1u
 #define QSB_RANK_SHIFT 48
 #define QSB_MAX_PEERS 16
 struct PeerTab { char *p[QSB_MAX_PEERS]; uint64_t shard_bytes; uint32_t world, pad; };

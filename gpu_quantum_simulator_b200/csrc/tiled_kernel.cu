@@ -448,6 +448,8 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     }
 
     /* ---- scatter ---- */
+    /* single-round in-place pass that moves qubits inside the tile: other threads gather what this one overwrites */
+    if (P.flags & QSB_PASS_SYNC_SCATTER) __syncthreads();
     {
         uint64_t off = outer * AMP + P.st_fixed, xoff = 0;
 #pragma unroll

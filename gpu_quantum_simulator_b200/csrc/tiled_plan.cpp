@@ -1008,6 +1008,12 @@ struct PassBuilder {
             gp.st_vec[v] = hp.fused_swap ? enc_dst(t) : (t & loc_mask) * AMP;
         }
         gp.st_fixed = hp.fused_swap ? (hp.hdr.dst_fixed & loc_mask) * AMP : 0;
+        if (nrounds == 1 && !hp.hdr.out_of_place) {   /* a thread's store set differs from its load set: barrier before the scatter */
+            bool moved = false;
+            for (int j = 0; j < QSB_TB; j++) moved |= gp.ld_thr[j] != gp.st_thr[j];
+            for (int v = 0; v < QSB_NV; v++) moved |= gp.ld_vec[v] != gp.st_vec[v];
+            if (moved) gp.flags |= QSB_PASS_SYNC_SCATTER;
+        }
 
         std::vector<GRound> gr(nrounds);
         std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds), angstream(nrounds);

@@ -213,6 +213,7 @@ def _hc():
     L.qsb_hostcheck_nloc.argtypes = [C.c_void_p]
     L.qsb_hostcheck_run_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.qsb_hostcheck_finish.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+    L.qsb_hostcheck_step_props.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -246,6 +247,13 @@ class ShardedHostRun:
         """new_shards: list of the P destination shards (complex128 arrays), written in place"""
         ptrs = (C.c_void_p * len(new_shards))(*[a.ctypes.data for a in new_shards])
         assert self.L.qsb_hostcheck_run_step_fused(self.h, i, self.shard.ctypes.data, ptrs) == 0
+
+    def props(self, i):
+        """pass i -> dict(rounds, out_of_place, moved, sync_scatter) or None for an exchange marker"""
+        o = (C.c_int * 4)()
+        if self.L.qsb_hostcheck_step_props(self.h, i, o):
+            return None
+        return dict(rounds=o[0], out_of_place=o[1], moved=o[2], sync_scatter=o[3])
 
     def chunks(self):
         return self.shard.reshape(self.world, -1)

@@ -284,6 +284,19 @@ extern "C" int qsb_hostcheck_run_step_fused(void *hv, int i, const double *state
     run_pass(hp, h->prec == QSB_F32, h->nloc, st, h->rep, (cd *const *)outs);
     return 0;
 }
+/* properties of pass i for the race test: out[0] rounds, out[1] out_of_place, out[2] 1 if the pass relocates a qubit
+ * inside its tile (tile_dst != tile_src), out[3] the QSB_PASS_SYNC_SCATTER flag of the serialised descriptor */
+extern "C" int qsb_hostcheck_step_props(void *hv, int i, int *out4)
+{
+    const HostPass &hp = ((HcPlan *)hv)->plan.passes[i];
+    if (hp.is_swap) return 1;
+    out4[0] = (int)hp.rounds.size(); out4[1] = (int)hp.hdr.out_of_place;
+    int moved = 0; for (int j = 0; j < hp.T; j++) moved |= hp.tile_src[j] != hp.tile_dst[j];
+    out4[2] = moved;
+    GPass gp; memcpy(&gp, hp.blob.data(), sizeof gp);
+    out4[3] = (int)(gp.flags & QSB_PASS_SYNC_SCATTER);
+    return 0;
+}
 extern "C" int qsb_hostcheck_num_steps(void *h) { return (int)((HcPlan *)h)->plan.passes.size(); }
 extern "C" int qsb_hostcheck_step_is_swap(void *h, int i) { return ((HcPlan *)h)->plan.passes[i].is_swap ? 1 : 0; }
 extern "C" int qsb_hostcheck_nloc(void *h) { return ((HcPlan *)h)->nloc; }

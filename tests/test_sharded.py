@@ -43,6 +43,26 @@ def test_sharded_superset_and_qft():
             assert np.max(np.abs(got - want)) < 1e-12
 
 
+def test_single_round_permutation_passes_synchronise_before_the_scatter():
+    """an in-place pass that relocates qubits inside its tile in ONE round has no exchange barrier
+    between gather and scatter; its descriptor must carry QSB_PASS_SYNC_SCATTER.  (The host double runs threads one
+    after the other and cannot see the race, so the flag is asserted on the plan.)"""
+    seen = 0
+    for seed in range(6):
+        for world, n in ((2, 19), (4, 20), (8, 21)):
+            circ = circuits.random_layered(n, depth=5, seed=seed)
+            r = helpers.ShardedHostRun(q.gates_from_circuit(circ), n, world, 0, 32)
+            for i in range(r.steps):
+                p = r.props(i)
+                if p is None:
+                    continue
+                risky = p["rounds"] == 1 and not p["out_of_place"] and p["moved"]
+                assert bool(p["sync_scatter"]) == bool(risky), (seed, world, i, p)
+                seen += risky
+            r.finish()
+    assert seen > 0, "no single-round permutation pass in the sample: the test checks nothing"
+
+
 def test_exchange_count_on_the_34_qubit_workload():
     circ = circuits.random_layered(34, 20, 12345)
     g = q.gates_from_circuit(circ)
