@@ -310,8 +310,19 @@ static int apply_gate(pctx_t *c, const char *name, const double *par, int np, co
         for (size_t i = 0; i < tmp.n; i++) gate_adjoint(&tmp.g[i]);
     }
     for (size_t i = 0; i < tmp.n; i++) {
-        if ((tmp.g[i].controls & cmask) || ((cmask >> tmp.g[i].target) & 1)) { free(tmp.g); PFAIL("gate %s: a control is also an operand of the gate", name); }
-        tmp.g[i].controls |= cmask;
+        qsb_gate_t *gi = &tmp.g[i];
+        /* a global phase inside a gate body (gphase: scalar * identity on a dummy target) has no operand of its own:
+         * under controls it becomes a phase gate on one control, controlled by the others */
+        const int scalar = gi->controls == 0 && gi->m[2] == 0 && gi->m[3] == 0 && gi->m[4] == 0 && gi->m[5] == 0 &&
+                           gi->m[0] == gi->m[6] && gi->m[1] == gi->m[7];
+        if (scalar && cmask) {
+            const double pr = gi->m[0], pi = gi->m[1];
+            gi->target = __builtin_ctzll(cmask); gi->controls = cmask & ~(1ULL << gi->target);
+            mat(gi->m, 1, 0, 0, 0, 0, 0, pr, pi);
+            continue;
+        }
+        if ((gi->controls & cmask) || ((cmask >> gi->target) & 1)) { free(tmp.g); PFAIL("gate %s: a control is also an operand of the gate", name); }
+        gi->controls |= cmask;
     }
     qsb_gate_t xg; memset(&xg, 0, sizeof xg); mat(xg.m, 0, 0, 1, 0, 1, 0, 0, 0);
     for (int i = 0; i < nctrl; i++) if ((negmask >> i) & 1) { xg.target = ops[i]; if (gv_push(&c->gv, &xg, 1)) { free(tmp.g); return QSB_ERR_NOMEM; } }
@@ -358,7 +369,7 @@ static int parse_block(pctx_t *c, const char *s, const char *end, const pbind_t 
         if (s[0] == '/' && s + 1 < end && s[1] == '*') { const char *e = strstr(s + 2, "*/"); s = (e && e < end) ? e + 2 : end; continue; }
 
         /* modifiers and gate name */
-        int nctrl = 0, inv = 0, power = 1; unsigned negmask = 0;
+        int nctrl = 0, inv = 0; long long power = 1; unsigned negmask = 0;
         char name[64];
         for (;;) {
             int len = 0;
@@ -376,7 +387,8 @@ static int parse_block(pctx_t *c, const char *s, const char *end, const pbind_t 
             if (!strcmp(name, "inv")) inv ^= 1;
             else if (!strcmp(name, "pow")) {
                 if (!has_arg || marg < 0 || marg != floor(marg) || marg > 1e6) PFAIL("pow(k) @ needs a non-negative integer k");
-                power *= (int)marg;
+                power *= (long long)marg;      /* 64-bit: stacked pow modifiers must not wrap */
+                if (power > 1000000) PFAIL("pow modifiers multiply to more than 1e6 repetitions");
             } else {
                 const int k = has_arg ? (int)marg : 1;
                 if (k < 1 || nctrl + k > 8 || marg != floor(marg)) PFAIL("%s(n) @ needs a small positive integer n", name);
@@ -388,7 +400,11 @@ static int parse_block(pctx_t *c, const char *s, const char *end, const pbind_t 
 
         { /* classical assignment (`c = measure q;`, `c[0] = measure q[0];`): ignored */
             const char *e = s; int is_assign = 0;
-            while (e < end && *e != ';' && *e != '\n' && *e != '{') { if (*e == '=') { is_assign = 1; break; } e++; }
+            while (e < end && *e != ';' && *e != '\n' && *e != '{') {
+                if (e[0] == '/' && e + 1 < end && (e[1] == '/' || e[1] == '*')) break;   /* a comment is not part of the statement */
+                if (*e == '=') { is_assign = 1; break; }
+                e++;
+            }
             if (is_assign) { while (s < end && *s != ';' && *s != '\n') s++; continue; }
         }
         if (!strcmp(name, "OPENQASM") || !strcmp(name, "include") || !strcmp(name, "barrier") ||
@@ -462,15 +478,26 @@ static int parse_block(pctx_t *c, const char *s, const char *end, const pbind_t 
          * of the enclosing gate or a whole register.  With a single register the register name is ignored, as in
          * the reference (:225-233). */
         int ops[16], nops = 0, whole[16], nwhole = 0, bsize = -1;
-        while (s < end && *s != ';' && *s != '\n') {
+        int after_comma = 0;
+        while (s < end && *s != ';') {
+            if (*s == '\n') {   /* a newline ends the statement unless the operand list continues (`cx q[0],\n q[1];`) */
+                if (after_comma) { s++; continue; }
+                break;
+            }
+            if (s[0] == '/' && s + 1 < end && s[1] == '/') { while (s < end && *s != '\n') s++; continue; }
+            if (s[0] == '/' && s + 1 < end && s[1] == '*') { const char *e = strstr(s + 2, "*/"); s = (e && e < end) ? e + 2 : end; continue; }
+            if (*s == ',') { after_comma = 1; s++; continue; }
+            if (!isspace((unsigned char)*s)) after_comma = 0;
             if (*s == '$') {
                 char *e; long v = strtol(s + 1, &e, 10);
                 if (e == s + 1) PFAIL("gate %s: bad operand", name);
+                if (v < 0 || v > 62) PFAIL("gate %s: operand index %ld out of range", name, v);
                 if (nops < 16) { whole[nops] = -1; ops[nops++] = (int)v; }
                 s = e;
             } else if (*s == '[') {   /* index without a usable name in front: reference behaviour */
                 char *e; long v = strtol(s + 1, &e, 10);
                 if (e == s + 1) PFAIL("gate %s: bad operand", name);
+                if (v < 0 || v > 62) PFAIL("gate %s: operand index %ld out of range", name, v);
                 if (nops < 16) { whole[nops] = -1; ops[nops++] = (int)v; }
                 s = e;
             } else if (is_id_start((unsigned char)*s)) {
@@ -485,6 +512,7 @@ static int parse_block(pctx_t *c, const char *s, const char *end, const pbind_t 
                         if (v < 0 || v >= c->regs[reg].size) PFAIL("operand %s[%ld] exceeds the register", id, v);
                         v += c->regs[reg].off;
                     }
+                    if (v < 0 || v > 62) PFAIL("gate %s: operand index %ld out of range", name, v);
                     if (nops < 16) { whole[nops] = -1; ops[nops++] = (int)v; }
                     s = e;
                 } else {
@@ -504,7 +532,7 @@ static int parse_block(pctx_t *c, const char *s, const char *end, const pbind_t 
         for (int r = 0; r < reps; r++) {
             int o2[16];
             for (int i = 0; i < nops; i++) o2[i] = whole[i] >= 0 ? c->regs[whole[i]].off + r : ops[i];
-            int rc = apply_gate(c, name, par, np, o2, nops, nctrl, negmask, inv, power, depth);
+            int rc = apply_gate(c, name, par, np, o2, nops, nctrl, negmask, inv, (int)power, depth);
             if (rc) return rc;
         }
     }
@@ -546,14 +574,27 @@ int qsb_parse_qasm_file(const char *path, int *num_qubits, qsb_gate_t **gates, s
     if (!path) { qsb_set_error("qsb_parse_qasm_file: null path"); return QSB_ERR_ARG; }
     FILE *f = fopen(path, "rb");
     if (!f) { qsb_set_error("ERROR: cannot open circuit file"); return QSB_ERR_IO; }
-    fseek(f, 0, SEEK_END);
-    long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    char *buf = (char *)malloc((size_t)sz + 1);
+    /* growing read loop: works for pipes / FIFOs / /dev/stdin as well (ftell() is -1 there), checks read errors */
+    size_t cap = 1 << 16, got = 0;
+    char *buf = (char *)malloc(cap + 1);
     if (!buf) { fclose(f); qsb_set_error("Malloc error"); return QSB_ERR_NOMEM; }
-    size_t got = fread(buf, 1, (size_t)sz, f);
+    for (;;) {
+        const size_t r = fread(buf + got, 1, cap - got, f);
+        got += r;
+        if (r == 0) {
+            if (ferror(f)) { fclose(f); free(buf); qsb_set_error("ERROR: cannot read circuit file"); return QSB_ERR_IO; }
+            break;
+        }
+        if (got == cap) {
+            if (cap > ((size_t)1 << 40)) { fclose(f); free(buf); qsb_set_error("circuit file too large"); return QSB_ERR_NOMEM; }
+            char *nb = (char *)realloc(buf, cap * 2 + 1);
+            if (!nb) { fclose(f); free(buf); qsb_set_error("Malloc error"); return QSB_ERR_NOMEM; }
+            buf = nb; cap *= 2;
+        }
+    }
     fclose(f);
     buf[got] = 0;
+    if (memchr(buf, 0, got)) { free(buf); qsb_set_error("circuit file contains a NUL byte"); return QSB_ERR_PARSE; }
     int rc = qsb_parse_qasm_string(buf, num_qubits, gates, n);
     free(buf);
     return rc;
