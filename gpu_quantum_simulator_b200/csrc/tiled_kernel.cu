@@ -94,6 +94,9 @@ template <> struct VT<double> {
 };
 
 #define NV QSB_NV
+#ifndef QSB_OPLOOP
+#define QSB_OPLOOP 0   /* op-loop flavour: 0 plain, 1 header + sets prefetched (uniform loads + selects), 2 header prefetched */
+#endif
 
 /* (xr, xi) *= (pr, pi) */
 template <typename R>
@@ -302,6 +305,34 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
              * fetched (uniform constant loads) before the body of record k runs. */
             const uint32_t n_ops = RD.n_ops;
             const uint4 *op = B + RD.ops_off16;
+#if QSB_OPLOOP == 2
+            /* like the plain loop, with the header of record k+1 fetched before the body of record k */
+            uint4 nh = op[0];
+            for (uint32_t i = 0; i < n_ops; i++) {
+                const uint4 h = nh;
+                const uint32_t code = h.x & 0xffu;
+                const bool pred = (tw & h.y) == h.y;
+                const bool sel = pred && code < K_UR1;          /* single-set records: every thread uses set 0 */
+                S c0, c1, c2, c3;
+                T::scalars4(op + 1 + (sel ? T::SET4 : 0), c0, c1, c2, c3);
+                xm ^= pred ? ((h.x >> 8) & 0xfu) : 0u;          /* deferred X merged into this record (or alone: K_NOP) */
+                const uint4 *cur = op;
+                op += h.x >> 16;
+                nh = op[0];
+#elif QSB_OPLOOP == 0
+            /* plain loop: the header is a uniform load, the coefficient set the thread needs ONE per-thread
+             * constant load (no select instructions); latencies are covered by the other resident warps */
+            for (uint32_t i = 0; i < n_ops; i++) {
+                const uint4 h = op[0];
+                const uint32_t code = h.x & 0xffu;
+                const bool pred = (tw & h.y) == h.y;
+                const bool sel = pred && code < K_UR1;          /* single-set records: every thread uses set 0 */
+                S c0, c1, c2, c3;
+                T::scalars4(op + 1 + (sel ? T::SET4 : 0), c0, c1, c2, c3);
+                xm ^= pred ? ((h.x >> 8) & 0xfu) : 0u;          /* deferred X merged into this record (or alone: K_NOP) */
+                const uint4 *cur = op;
+                op += h.x >> 16;
+#else
             uint4 nh = op[0];
             S n0[4], n1[4];
             T::scalars4(op + 1, n0[0], n0[1], n0[2], n0[3]);
@@ -318,6 +349,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 nh = op[0];
                 T::scalars4(op + 1, n0[0], n0[1], n0[2], n0[3]);
                 T::scalars4(op + 1 + T::SET4, n1[0], n1[1], n1[2], n1[3]);
+#endif
                 switch (code) {
 #define UCASE(VBI) \
                 case K_UR + VBI: case K_UR1 + VBI: unit_v<R, VBI, false>(re, im, c0, c1, c2); psr *= c3; psi *= c3; break; \
