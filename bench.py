@@ -182,7 +182,7 @@ def run_ours(args):
 
     def make_sim(n):
         sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local_rank, low_bits=args.low_bits,
-                          reserved=[0, args.no_lazy_diag, args.trim, args.cost_cap, 0, args.fused, args.no_sink])
+                          reserved=[0, args.no_lazy_diag, args.trim, args.cost_cap, args.res4, args.fused, args.no_sink])
         if world > 1:
             from gpu_quantum_simulator_b200 import dist as qdist
             qdist.init_comm(sim, dist)
@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--no-sink", type=int, default=0, help="planner A/B: 1 = do not sink thread-level phases to later rounds, 2 = first-come tile choice (no hill climbing)")
     ap.add_argument("--fused", type=int, default=0, help="multi-GPU A/B: exchange flavour, 0 = default (fused peer scatter; pipelined at 2 GPUs), 1 = fused peer scatter, 2 = NCCL all-to-all, 3 = pipelined copy-engine exchange")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--res4", type=int, default=0, help="planner A/B: qsb_options_t.reserved[4] (1 = vector-bit phases not deferred, 2 = no 2x2 products, 3 = no Hadamard-like slot form)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

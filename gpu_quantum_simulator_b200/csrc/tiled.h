@@ -54,7 +54,9 @@
 #define QSB_T_F32 (QSB_T_F64 + 1)      /* tile bits f32: pack + NVB + TB (12)        */
 #define QSB_SLOTS (1 << QSB_T_F64)     /* 16-byte shared-memory slots of a tile       */
 #define QSB_SMEM_BYTES (QSB_SLOTS * 16)
+#ifndef QSB_CTAS_PER_SM
 #define QSB_CTAS_PER_SM (512 / QSB_THREADS)
+#endif
 #define QSB_MAX_RUNS 16
 #define QSB_BLOB_SMALL 4000    /* pass descriptor sizes (kernel parameter)   */
 #define QSB_BLOB_MEDIUM 12000
@@ -143,60 +145,56 @@ template <int BYTES> struct PassBlob { uint4 q[BYTES / 16]; };
  * kernel reads, with everything that does not depend on the thread pre-computed:
  * byte offsets per vector for the global gather / scatter, shared-memory XOR
  * constants per vector, and predicates as ONE 32-bit mask over the per-thread
- * word  tw = threadIdx.x | W << QSB_TB,  where bit i of W says whether the CTA's outer
+ * word  tw = threadIdx.x | W << 8,  where bit i of W says whether the CTA's outer
  * index bits satisfy the i-th outer condition of the pass (GPass::cond).
  *
- * Round 2: the ops of a round are ONE FLAT STREAM of records in program order, walked on
- * the uniform datapath.  (Round 1 laid them out as segments of "groups" with one slot per
- * vector bit plus a generic list of "specials"; ncu showed 42 % of the issued instructions
- * and 54 % of the stall samples in the glue between the packed-FMA bodies --
- * profiles/r2/head_30q_*.txt -- i.e. ~70 glue instructions per 48-instruction gate.)
- * A record is a 16-byte header followed by its coefficient sets; the kernel fetches the
- * header and the first sets of record k+1 while the body of record k runs, computes the
- * predicate with one AND/compare, and jumps to one straight-line body per code.
- *
- *   header  x = code | xbits << 8 | vmask << 12 | size16 << 16
- *               xbits : vector bits whose deferred X toggles for the threads that pass (an OP_XDEF
- *                       merged into the gate it follows, or alone with code K_NOP)
- *               vmask : K_DIAG_GEN only
- *               size16: header + payload in 16-byte units (next record = this + size16)
- *           y = predicate mask over tw:  pred = (tw & y) == y
- *           z, w = 64-bit mask over the outer (per-CTA) source index bits, for the rare op whose outer
- *                  condition did not fit the pass-wide table W (K_* codes >= K_FULL only); pred &= (outer & zw) == zw
- *   payload: coefficient sets.  S = scalar of the state precision, V = 8 bytes (f32: (lo, hi) lanes, f64: one double).
- *            A 4-scalar set is 16 bytes in f32 and 32 bytes in f64 (QSB_SET16). */
-enum {
-    /* two 4-scalar sets: threads whose predicate fails use set 0 (the identity of a controlled gate, the
-     * control-off matrix of a multiplexer), the others set 1 */
-    K_UR = 0,        /* +vb  real unit form  a[[1,p],[q,r]]: x0 += p x1; x1 = k x1 + q x0      S: p q k a; the scale a
-                             goes to the pending scalar                                                      */
-    K_UI = 4,        /* +vb  rx unit form    a[[1,ip],[iq,r]]                                  S: p q k a    */
-    K_DG = 8,        /* +vb  phase on the vectors whose bit is set                             S: pr pi - -  */
-    /* ONE set, every thread; the scale is already folded into the pass scale (a == 1).  The predicate of such a
-     * record only governs its xbits. */
-    K_UR1 = 12,      /* +vb  real unit form                                                                  */
-    K_UI1 = 16,      /* +vb  rx unit form                                                                    */
-    K_UH1 = 20,      /* +vb  real unit form with q == 1 (Hadamard-like): x0 += p x1; x1 = k x1 + x0 -- 4 instead
-                             of 6 packed operations per vector pair                                          */
-    K_NOP = 24,      /* no arithmetic: a deferred X alone (xbits)                                             */
-    /* rare forms.  Bit 7 of the code (K_TWO): two coefficient sets follow and threads whose predicate fails use
-     * set 0; otherwise one set and threads whose predicate fails skip the op (a controlled gate).  Sets are
-     * padded to 16 bytes. */
-    K_FULL = 28,     /* +vb  complex 2x2             V: m00r m00i m01r m01i m10r m10i m11r m11i               */
-    K_DIAG_V = 32,   /* +vb  phase where vector bit vb is set (lane dependent)          V: pr pi              */
-    K_DIAG_ALL = 36, /* phase on every vector (lane dependent)                          V: pr pi              */
-    K_DIAG_GEN = 37, /* phase where (v & vmask) == vmask                                V: pr pi              */
-    K_MATP_R = 38,   /* pack-bit target, real (f32 only)                                V: A B                */
-    K_MATP_G = 39,   /* pack-bit target, complex (f32 only)                             V: Ar Ai Br Bi        */
-    K_NCODES = 40,
-    K_TWO = 0x80
+ * The ops of a round are laid out as SEGMENTS.  A segment is a (usually empty)
+ * list of SPECIAL ops, run by a generic interpreter, followed by GROUPS.  A
+ * group holds one SLOT per vector bit at a fixed position: slot j is the next
+ * op whose target is vector bit j (ops on different vector bits commute, their
+ * predicates never involve vector bits), so the common gates are dispatched
+ * with a uniform load at a static offset and a 5-way uniform branch instead of
+ * an op-stream walk.  Everything else (general complex or lane-dependent
+ * matrices, pack-bit targets, multi-vector-bit phases) is a special. */
+enum {              /* slot forms (one-hot bytes, so the kernel dispatches with bit tests); S = scalar of the state precision */
+    S_SKIP = 0,
+    S_UNIT_R = 1,   /* real unit form  a[[1,p],[q,r]]: x0 += p x1; x1 = k x1 + q x0     S: p q k a */
+    S_UNIT_I = 2,   /* rx unit form    a[[1,ip],[iq,r]]                                 S: p q k a */
+    S_UNIT_H = 4,   /* real unit form with q == 1 (Hadamard-like), unconditional, a == 1:
+                       x0 += p x1; x1 = k x1 + x0 -- 4 instead of 6 packed operations per vector pair   S: p 1 k 1 */
+    S_DIAG = 8,     /* phase on the vectors whose bit is set                           S: pr pi   */
+    S_XDEF = 16,    /* X (swap of the two halves) under the predicate, DEFERRED: the thread only
+                       flips bit j of its vector-index mask; the swap happens for free in the
+                       address of the next shared / global store.  Last op on its bit in a round. */
+    /* matrices that cannot take a unit form (rare after pivoting) run as G_FULL_G specials */
 };
+/* A group (16-byte units): [0] x = form of slot 0 | slot 1 << 8 | slot 2 << 16 | slot 3 << 24
+ *                          [1] the four predicate masks: (tw & pmask) == pmask
+ *                          then per slot two coefficient sets of 4 scalars: threads whose predicate
+ *                          fails use set 0 (the identity for a controlled gate, the control-off matrix
+ *                          for a multiplexer), the others set 1. */
 #define QSB_SET16(f32) ((f32) ? 1 : 2)             /* one 4-scalar coefficient set, 16-byte units */
-#define KOPK(code, xbits, vmask, size16) \
-    ((uint32_t)(code) | ((uint32_t)(xbits) << 8) | ((uint32_t)(vmask) << 12) | ((uint32_t)(size16) << 16))
-/* the kernel fetches this many 16-byte units past the header of the NEXT record before it knows its size:
- * the blob keeps that much slack behind the last record of a round */
-#define QSB_OP_PREFETCH16(f32) (1 + 2 * QSB_SET16(f32))
+#define QSB_GROUP16(f32) (2 + QSB_NVB * 2 * QSB_SET16(f32))
+
+enum {              /* special op codes (generic interpreter); V = 8 bytes (f32: (lo, hi) lanes, f64: one double) */
+    G_FULL_G = 16,   /* +vb: complex 2x2             V: m00r m00i m01r m01i m10r m10i m11r m11i */
+    G_DIAG_V = 20,   /* +vb: phase where vector bit vb is set          V: pr pi       */
+    G_DIAG_ALL = 24, /* phase on every vector (lane dependent)         V: pr pi       */
+    G_DIAG_GEN = 25, /* phase where (v & vmask) == vmask               V: pr pi       */
+    G_MATP_R = 26,   /* pack-bit target, real (f32 only)               V: A B         */
+    G_MATP_G = 27,   /* pack-bit target, complex (f32 only)            V: Ar Ai Br Bi */
+    G_NCODES = 28
+};
+/* Special op header (16 bytes):
+ *   x = code | two << 8 | skip << 9 | vmask << 12 | size16 << 16
+ *       two : a multiplexer -- two coefficient sets follow; threads whose predicate fails use set 0
+ *             (the control-off matrix), the others set 1.  Otherwise one set: threads whose predicate
+ *             fails skip the op (a controlled gate)
+ *       skip: informational, the op has a predicate and one set
+ *   y = 8-bit mask over threadIdx.x          z, w = 64-bit mask over the outer (per-CTA) index bits
+ * predicate = (tid & y) == y && (outer & zw) == zw.  Coefficient sets are padded to 16 bytes. */
+#define GOPK(code, two, skip, vmask, size16) \
+    ((uint32_t)(code) | ((uint32_t)(two) << 8) | ((uint32_t)(skip) << 9) | ((uint32_t)(vmask) << 12) | ((uint32_t)(size16) << 16))
 
 struct GTPhase {               /* thread-level phase, applied through the pending scalar (32 bytes) */
     uint32_t tmask, pad;
@@ -224,10 +222,15 @@ struct GTAngle {
 #define QSB_TANGLE_MIN_F64 24
 #endif
 
+struct GSegment {              /* 16 bytes */
+    uint32_t n_special, special_off16;
+    uint32_t n_groups, group_off16;
+};
+
 #define QSB_MAX_COND 24        /* distinct outer conditions a pass can name through W */
 
 struct alignas(16) GRound {    /* the kernel steps through the round array in 16-byte units */
-    uint32_t n_ops, ops_off16; /* op records, 16-byte units from the blob start                      */
+    uint32_t n_seg, seg_off16; /* GSegment array, 16-byte units from the blob start                  */
     uint32_t n_tph, tph_off16; /* GTPhase array                                                      */
     uint32_t flags, n_ang, pad[2]; /* flags bit0: apply the pending scalar at the end of the round; n_ang: GTAngle
                                   entries, stored right after the n_tph GTPhase entries                */

@@ -94,9 +94,6 @@ template <> struct VT<double> {
 };
 
 #define NV QSB_NV
-#ifndef QSB_OPLOOP
-#define QSB_OPLOOP 0   /* op-loop flavour: 0 plain, 1 header + sets prefetched (uniform loads + selects), 2 header prefetched */
-#endif
 
 /* (xr, xi) *= (pr, pi) */
 template <typename R>
@@ -238,6 +235,34 @@ template <> struct IO<double> {
     case (base) + 2: { enum { VB = 2 }; __VA_ARGS__ } break; \
     case (base) + 3: { enum { VB = 3 }; __VA_ARGS__ } break;
 
+/* One slot of a group = the op on vector bit VB: a one-hot form byte, a predicate mask and two
+ * 4-scalar coefficient sets.  Slots are software-pipelined: the coefficient loads of the next
+ * non-empty slot are issued before the current slot's packed FMAs, the header of the next group
+ * before the current group.  No per-thread branches: threads whose predicate fails use coefficient
+ * set 0 (the identity for a controlled gate, the control-off matrix for a multiplexer). */
+template <typename R> struct SlotC { typename VT<R>::S c[4], d[4]; };
+template <typename R>
+__device__ __forceinline__ void slot_fetch(const uint4 *cp, SlotC<R> &s)
+{
+    typedef VT<R> T;
+    T::scalars4(cp, s.c[0], s.c[1], s.c[2], s.c[3]);
+    T::scalars4(cp + T::SET4, s.d[0], s.d[1], s.d[2], s.d[3]);
+}
+template <typename R, int VB>
+__device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const SlotC<R> &s, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV],
+                                          uint32_t tw, typename VT<R>::S &psr, typename VT<R>::S &psi, uint32_t &xm)
+{
+    typedef VT<R> T; typedef typename T::S S;
+    const bool pred = (tw & pmask) == pmask;
+    const S c0 = pred ? s.d[0] : s.c[0], c1 = pred ? s.d[1] : s.c[1], c2 = pred ? s.d[2] : s.c[2], c3 = pred ? s.d[3] : s.c[3];
+    if (form & S_UNIT_R) { unit_v<R, VB, false>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
+    else if (form & S_UNIT_I) { unit_v<R, VB, true>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
+    else if (form & S_UNIT_H) unit_h<R, VB>(re, im, c0, c2);
+    else if (form & S_DIAG) diag_v<R, VB>(re, im, T::bc(c0), T::bc(c1));
+    /* S_XDEF alone, or merged into the gate it follows (the planner then gives both the same predicate) */
+    if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;
+}
+
 /* PEER: the scatter of a fused-exchange pass -- every amplitude goes straight into the shard of the rank
  * named by its victim bits (peer memory over NVLink), so the qubit exchange costs no extra sweep. */
 template <typename R, int BLOB, bool PEER>
@@ -281,6 +306,24 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
         const char *p = src + off;
 #pragma unroll
         for (int v = 0; v < NV; v++) IO<R>::gload(p + P.ld_vec[v], re[v], im[v]);
+#ifdef QSB_L2_PREFETCH
+        /* Pull the tile of the CTA that will take this one's place (QSB_L2_PREFETCH CTAs further on: the number
+         * resident on the chip) from HBM into L2 now: its gather then costs an L2 hit instead of a DRAM round trip.
+         * Threads 8k .. 8k+7 share 128-byte lines on the edge rounds (thread bits 0-2 are the physical bits next
+         * to the pack bit), so each of them asks for two of the 16 vectors.  A hint only: redundancy is harmless. */
+        {
+            uint64_t t2 = (uint64_t)blockIdx.x + tile_base + (uint64_t)QSB_L2_PREFETCH;
+            if (t2 < P.n_tiles) {
+                uint64_t o2 = 0;
+                const int nr = (int)P.n_runs;
+                for (int r = 0; r < nr; r++) { const int len = P.run_len[r]; o2 |= (t2 & ((1ULL << len) - 1)) << P.run_start[r]; t2 >>= len; }
+                const char *p2 = p + (o2 - outer) * AMP;
+                const int v0 = (tid & 7) * 2;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + P.ld_vec[v0]));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + P.ld_vec[v0 + 1]));
+            }
+        }
+#endif
     }
 
     uint32_t xm = 0;   /* deferred X: this thread's register v holds logical vector v ^ xm */
@@ -300,113 +343,84 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 
         /* ---- the fused gates of this round ---- */
         S psr = S(1), psi = S(0); /* per-thread pending scalar: unit-form scales and thread-level phases */
-        {
-            /* One flat record stream (tiled.h).  The header and the two leading coefficient sets of record k+1 are
-             * fetched (uniform constant loads) before the body of record k runs. */
-            const uint32_t n_ops = RD.n_ops;
-            const uint4 *op = B + RD.ops_off16;
-#if QSB_OPLOOP == 2
-            /* like the plain loop, with the header of record k+1 fetched before the body of record k */
-            uint4 nh = op[0];
+        const uint32_t n_seg = RD.n_seg;
+        const GSegment *seg = reinterpret_cast<const GSegment *>(B + RD.seg_off16);
+        for (uint32_t sg = 0; sg < n_seg; sg++) {
+            /* -- specials: generic interpreter -- */
+            const uint32_t n_ops = seg[sg].n_special;
+            const uint4 *op = B + seg[sg].special_off16;
             for (uint32_t i = 0; i < n_ops; i++) {
-                const uint4 h = nh;
-                const uint32_t code = h.x & 0xffu;
-                const bool pred = (tw & h.y) == h.y;
-                const bool sel = pred && code < K_UR1;          /* single-set records: every thread uses set 0 */
-                S c0, c1, c2, c3;
-                T::scalars4(op + 1 + (sel ? T::SET4 : 0), c0, c1, c2, c3);
-                xm ^= pred ? ((h.x >> 8) & 0xfu) : 0u;          /* deferred X merged into this record (or alone: K_NOP) */
-                const uint4 *cur = op;
+                const uint4 h = *op;
+                const uint4 *c = op + 1;
                 op += h.x >> 16;
-                nh = op[0];
-#elif QSB_OPLOOP == 0
-            /* plain loop: the header is a uniform load, the coefficient set the thread needs ONE per-thread
-             * constant load (no select instructions); latencies are covered by the other resident warps */
-            for (uint32_t i = 0; i < n_ops; i++) {
-                const uint4 h = op[0];
                 const uint32_t code = h.x & 0xffu;
-                const bool pred = (tw & h.y) == h.y;
-                const bool sel = pred && code < K_UR1;          /* single-set records: every thread uses set 0 */
-                S c0, c1, c2, c3;
-                T::scalars4(op + 1 + (sel ? T::SET4 : 0), c0, c1, c2, c3);
-                xm ^= pred ? ((h.x >> 8) & 0xfu) : 0u;          /* deferred X merged into this record (or alone: K_NOP) */
-                const uint4 *cur = op;
-                op += h.x >> 16;
-#else
-            uint4 nh = op[0];
-            S n0[4], n1[4];
-            T::scalars4(op + 1, n0[0], n0[1], n0[2], n0[3]);
-            T::scalars4(op + 1 + T::SET4, n1[0], n1[1], n1[2], n1[3]);
-            for (uint32_t i = 0; i < n_ops; i++) {
-                const uint4 h = nh;
-                const uint32_t code = h.x & 0xffu;
-                const bool pred = (tw & h.y) == h.y;
-                const bool sel = pred && code < K_UR1;          /* single-set records: every thread uses set 0 */
-                const S c0 = sel ? n1[0] : n0[0], c1 = sel ? n1[1] : n0[1], c2 = sel ? n1[2] : n0[2], c3 = sel ? n1[3] : n0[3];
-                xm ^= pred ? ((h.x >> 8) & 0xfu) : 0u;          /* deferred X merged into this record (or alone: K_NOP) */
-                const uint4 *cur = op;
-                op += h.x >> 16;
-                nh = op[0];
-                T::scalars4(op + 1, n0[0], n0[1], n0[2], n0[3]);
-                T::scalars4(op + 1 + T::SET4, n1[0], n1[1], n1[2], n1[3]);
-#endif
+                const uint64_t om = ((uint64_t)h.w << 32) | h.z;
+                const bool two = (h.x >> 8) & 1u;
+                const bool pred = ((src_outer & om) == om) && ((tid & h.y) == h.y);
+                if (!two && !pred) continue;   /* controlled gate: the other threads sit this op out */
+                const bool s1 = two && pred;   /* multiplexer: threads that pass use coefficient set 1 */
                 switch (code) {
-#define UCASE(VBI) \
-                case K_UR + VBI: case K_UR1 + VBI: unit_v<R, VBI, false>(re, im, c0, c1, c2); psr *= c3; psi *= c3; break; \
-                case K_UI + VBI: case K_UI1 + VBI: unit_v<R, VBI, true>(re, im, c0, c1, c2); psr *= c3; psi *= c3; break; \
-                case K_UH1 + VBI: unit_h<R, VBI>(re, im, c0, c2); break; \
-                case K_DG + VBI: diag_v<R, VBI>(re, im, T::bc(c0), T::bc(c1)); break;
-                UCASE(0) UCASE(1) UCASE(2) UCASE(3)
-#undef UCASE
-                case K_NOP: break;
-                default: {
-                    /* rare forms: lane-dependent or complex coefficients, pack-bit targets, multi-bit phases */
-                    const uint4 *c = cur + 1;
-                    const uint32_t rc = code & 0x7fu;
-                    const bool two = (code & K_TWO) != 0;
-                    const uint64_t om = ((uint64_t)h.w << 32) | h.z;
-                    const bool prd = pred && ((src_outer & om) == om);
-                    if (!two && !prd) break;       /* controlled gate: the other threads sit this op out */
-                    const bool s1 = two && prd;    /* multiplexer: threads that pass use coefficient set 1 */
-                    switch (rc) {
-                    CASE4(K_FULL, {
-                        const uint4 *cs = c + (s1 ? 4 : 0);     /* rare form: per-thread constant loads are fine */
-                        V m[8];
-                        T::vec2(cs, 0, m[0], m[1]); T::vec2(cs, 1, m[2], m[3]); T::vec2(cs, 2, m[4], m[5]); T::vec2(cs, 3, m[6], m[7]);
-                        gen_v<R, VB>(re, im, m);
-                    })
-                    CASE4(K_DIAG_V, {
-                        V pr, pi; load_phase<R>(c, two, s1, pr, pi);
-                        diag_v<R, VB>(re, im, pr, pi);
-                    })
-                    case K_DIAG_ALL: {
-                        V pr, pi; load_phase<R>(c, two, s1, pr, pi);
+                CASE4(G_FULL_G, {
+                    const uint4 *cs = c + (s1 ? 4 : 0);     /* rare form: per-thread constant loads are fine */
+                    V m[8];
+                    T::vec2(cs, 0, m[0], m[1]); T::vec2(cs, 1, m[2], m[3]); T::vec2(cs, 2, m[4], m[5]); T::vec2(cs, 3, m[6], m[7]);
+                    gen_v<R, VB>(re, im, m);
+                })
+                CASE4(G_DIAG_V, {
+                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
+                    diag_v<R, VB>(re, im, pr, pi);
+                })
+                case G_DIAG_ALL: {
+                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
 #pragma unroll
-                        for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi);
-                        break;
-                    }
-                    case K_DIAG_GEN: {
-                        const uint32_t vmask = (h.x >> 12) & 0xfu;   /* uniform: a compact predicated sweep, one code copy */
-                        V pr, pi; load_phase<R>(c, two, s1, pr, pi);
-#pragma unroll
-                        for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) cmul_inplace<R>(re[v], im[v], pr, pi);
-                        break;
-                    }
-                    case K_MATP_R: {
-                        V A, Bc; T::vec2(c + (s1 ? 1 : 0), 0, A, Bc);
-                        matp_r(re, im, A, Bc);
-                        break;
-                    }
-                    case K_MATP_G: {
-                        const uint4 *cs = c + (s1 ? 2 : 0);
-                        V Ar, Ai, Br, Bi; T::vec2(cs, 0, Ar, Ai); T::vec2(cs, 1, Br, Bi);
-                        matp_g(re, im, Ar, Ai, Br, Bi);
-                        break;
-                    }
+                    for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], pr, pi);
+                    break;
+                }
+                case G_DIAG_GEN: {
+                    const uint32_t vmask = (h.x >> 12) & 0xfu;
+                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
+                    switch (vmask) {   /* uniform: one static variant per mask, only the matching vectors are touched */
+#define DGEN(MASK) case MASK: diag_mask<R, MASK>(re, im, pr, pi); break;
+                    DGEN(3) DGEN(5) DGEN(6) DGEN(7) DGEN(9) DGEN(10) DGEN(11) DGEN(12) DGEN(13) DGEN(14) DGEN(15)
+#undef DGEN
                     default: break;
                     }
                     break;
                 }
+                case G_MATP_R: {
+                    V A, Bc; T::vec2(c + (s1 ? 1 : 0), 0, A, Bc);
+                    matp_r(re, im, A, Bc);
+                    break;
+                }
+                case G_MATP_G: {
+                    const uint4 *cs = c + (s1 ? 2 : 0);
+                    V Ar, Ai, Br, Bi; T::vec2(cs, 0, Ar, Ai); T::vec2(cs, 1, Br, Bi);
+                    matp_g(re, im, Ar, Ai, Br, Bi);
+                    break;
+                }
+                default: break;
+                }
+            }
+            /* -- groups: one slot per vector bit at a fixed position -- */
+            const uint32_t n_groups = seg[sg].n_groups;
+            const uint4 *gp = B + seg[sg].group_off16;
+            if (n_groups) {
+                const int G16 = QSB_GROUP16(sizeof(R) == 4), S16 = 2 * T::SET4;
+                uint4 nh = gp[0], nm = gp[1];
+                for (uint32_t g = 0; g < n_groups; g++, gp += G16) {
+                    const uint4 gh = nh, gm = nm;
+                    nh = gp[G16]; nm = gp[G16 + 1];            /* next group's header (or slack) */
+                    const uint32_t f0 = gh.x & 0xffu, f1 = (gh.x >> 8) & 0xffu, f2 = (gh.x >> 16) & 0xffu, f3 = gh.x >> 24;
+                    const uint4 *cp = gp + 2;
+                    SlotC<R> sa, sc;
+                    if (f0) slot_fetch<R>(cp, sa);
+                    if (f1) slot_fetch<R>(cp + S16, sc);
+                    if (f0) slot_exec<R, 0>(f0, gm.x, sa, re, im, tw, psr, psi, xm);
+                    if (f2) slot_fetch<R>(cp + 2 * S16, sa);
+                    if (f1) slot_exec<R, 1>(f1, gm.y, sc, re, im, tw, psr, psi, xm);
+                    if (f3) slot_fetch<R>(cp + 3 * S16, sc);
+                    if (f2) slot_exec<R, 2>(f2, gm.z, sa, re, im, tw, psr, psi, xm);
+                    if (f3) slot_exec<R, 3>(f3, gm.w, sc, re, im, tw, psr, psi, xm);
                 }
             }
         }

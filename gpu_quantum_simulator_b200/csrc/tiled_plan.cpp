@@ -135,7 +135,7 @@ const int QSB_PLAN_OVERFLOW = -100;   /* internal: serialise() could not fit the
 
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
-    bool f32, lazy_diag, defer_diag, sink_phases, tile_search;
+    bool f32, lazy_diag, defer_diag, sink_phases, tile_search, hform;
     int trim_thin, cost_cap;
     bool fused_exchange, force_top;
 };
@@ -1016,9 +1016,11 @@ struct PassBuilder {
         }
 
         std::vector<GRound> gr(nrounds);
-        std::vector<std::vector<uint8_t>> opstream(nrounds), tphstream(nrounds), angstream(nrounds);
-        std::vector<uint32_t> n_ops_round(nrounds, 0);
-        const int SET16 = QSB_SET16(f32);
+        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds), angstream(nrounds);
+        /* body offsets inside segstream entries are relative to the round's body; fixed up below */
+        struct SegRec { uint32_t n_special, special_rel, n_groups, group_rel; };
+        std::vector<std::vector<SegRec>> segrec(nrounds);
+        const int SET16 = QSB_SET16(f32), GROUP16 = QSB_GROUP16(f32);
         uint32_t n_cond = 0;
         for (int r = 0; r < nrounds; r++) {
             const DevRound &D = hp.rounds[r];
@@ -1058,15 +1060,22 @@ struct PassBuilder {
                 if ((hp.ops[k].kind & 0xff) == OP_TPHASE && is_unit_phase(hp.ops[k])) n_unit++;
             const bool use_angles = n_unit >= (f32 ? QSB_TANGLE_MIN_F32 : QSB_TANGLE_MIN_F64);
 
-            /* records of this round, in program order; last_rec[vb]: the latest record whose target is vector bit vb */
-            std::vector<std::vector<uint8_t>> recs;
-            struct RecInfo { int code; uint32_t pmask; bool single; bool uncond2; };   /* uncond2: two sets, no predicate, not a multiplexer: set 0 is never used */
-            std::vector<RecInfo> rinfo;
-            int last_rec[QSB_NVB] = {-1, -1, -1, -1};
-            auto set_hdr = [&](std::vector<uint8_t> &rec, uint32_t code, uint32_t xbits, uint32_t vmask, uint32_t pmask, uint64_t omask) {
-                const uint32_t hdr[4] = {KOPK(code, xbits, vmask, rec.size() / 16), pmask, (uint32_t)omask, (uint32_t)(omask >> 32)};
-                memcpy(rec.data(), hdr, 16);
+            /* segment under construction */
+            std::vector<uint8_t> specials; uint32_t n_special = 0;
+            std::vector<std::vector<uint8_t>> groups;       /* each QSB_GROUP16 * 16 bytes */
+            std::vector<std::array<bool, QSB_NVB>> slot_single;   /* slot holds an unconditional single-set gate */
+            int next_group[QSB_NVB] = {0, 0, 0, 0};
+            auto close_segment = [&]() {
+                if (!n_special && groups.empty()) return;
+                SegRec sr; sr.n_special = n_special; sr.special_rel = (uint32_t)bodystream[r].size();
+                bodystream[r].insert(bodystream[r].end(), specials.begin(), specials.end());
+                sr.n_groups = (uint32_t)groups.size(); sr.group_rel = (uint32_t)bodystream[r].size();
+                for (auto &g : groups) bodystream[r].insert(bodystream[r].end(), g.begin(), g.end());
+                segrec[r].push_back(sr);
+                specials.clear(); n_special = 0; groups.clear(); slot_single.clear();
+                for (int b = 0; b < QSB_NVB; b++) next_group[b] = 0;
             };
+
             for (uint32_t k = hp.round_op_begin[r]; k < hp.round_op_begin[r] + hp.round_op_count[r]; k++) {
                 const HostOp &h = hp.ops[k];
                 const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf, vmask = (h.kind >> 20) & 0xf;
@@ -1105,72 +1114,64 @@ struct PassBuilder {
                 auto lanes_equal = [&](int set) { for (int c = 0; c < h.n_coef; c++) if (h.c[set][c][0] != h.c[set][c][1]) return false; return true; };
                 const bool leq = lanes_equal(0) && (!mux || lanes_equal(1));
 
-                /* ---- scalar-coefficient forms ---- */
-                enum { F_NONE, F_UR, F_UI, F_DG, F_X };
-                int sform = F_NONE;
+                /* ---- slot forms ---- */
+                int sform = S_SKIP;
                 if (leq) switch (code) {
-                    case OP_MAT_U: sform = F_UR; break;
-                    case OP_MAT_UI: sform = F_UI; break;
-                    case OP_DIAG_V: sform = F_DG; break;
-                    case OP_XDEF: sform = F_X; break;
+                    case OP_MAT_U: sform = S_UNIT_R; break;
+                    case OP_MAT_UI: sform = S_UNIT_I; break;
+                    case OP_DIAG_V: sform = S_DIAG; break;
+                    case OP_XDEF: sform = S_XDEF; break;
                     default: break;
                 }
                 uint32_t wbits = 0;
-                if (sform != F_NONE && cond_bit(om, wbits)) {
-                    const uint32_t pm_new = tm8 | (wbits << QSB_TB);
-                    auto C = [&](int set, int c) { return h.c[set][c][1]; };
-                    auto put_set = [&](std::vector<uint8_t> &o, int set, bool identity) {
+                if (sform != S_SKIP && cond_bit(om, wbits)) {
+                    std::vector<uint8_t> slot;
+                    auto slot_set = [&](int set, bool identity) {
+                        auto C = [&](int c) { return h.c[set][c][1]; };
+                        std::vector<uint8_t> o;
                         switch (sform) {
-                        case F_UR: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(set, 0)); put_s(o, C(set, 1)); put_s(o, C(set, 2)); put_s(o, C(set, 3)); } break;
-                        case F_UI: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(set, 0)); put_s(o, C(set, 2)); put_s(o, C(set, 4)); put_s(o, C(set, 5)); } break;
-                        case F_DG: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 0); } else { put_s(o, C(set, 0)); put_s(o, C(set, 1)); put_s(o, 0); put_s(o, 0); } break;
-                        default: break;
+                        case S_UNIT_R: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(0)); put_s(o, C(1)); put_s(o, C(2)); put_s(o, C(3)); } break;
+                        case S_UNIT_I: if (identity) { put_s(o, 0); put_s(o, 0); put_s(o, 1); put_s(o, 1); } else { put_s(o, C(0)); put_s(o, C(2)); put_s(o, C(4)); put_s(o, C(5)); } break;
+                        case S_DIAG: if (identity) { put_s(o, 1); put_s(o, 0); put_s(o, 0); put_s(o, 0); } else { put_s(o, C(0)); put_s(o, C(1)); put_s(o, 0); put_s(o, 0); } break;
+                        default: put_s(o, 0); put_s(o, 0); put_s(o, 0); put_s(o, 0); break;
                         }
+                        slot.insert(slot.end(), o.begin(), o.end());
                     };
-                    if (sform == F_X) {
-                        /* merge a deferred X into the latest record on the same vector bit (ops on other vector bits
-                         * commute with it): same predicate, or a single-set record, whose predicate is unused so far */
-                        const int pr = last_rec[vb];
-                        if (pr >= 0) {
-                            uint32_t hdr[4]; memcpy(hdr, recs[pr].data(), 16);
-                            const bool no_x = ((hdr[0] >> 8) & 0xfu) == 0;
-                            if (no_x && rinfo[pr].code < K_NOP && (rinfo[pr].pmask == pm_new || rinfo[pr].single || rinfo[pr].uncond2)) {
-                                if (rinfo[pr].uncond2 && rinfo[pr].pmask != pm_new)   /* every thread keeps the gate: both sets identical */
-                                    memcpy(recs[pr].data() + 16, recs[pr].data() + 16 + (size_t)SET16 * 16, (size_t)SET16 * 16);
-                                hdr[0] |= (1u << vb) << 8; hdr[1] = pm_new;
-                                memcpy(recs[pr].data(), hdr, 16);
-                                rinfo[pr].pmask = pm_new; rinfo[pr].single = false; rinfo[pr].uncond2 = false;   /* the predicate is taken now */
-                                continue;
-                            }
+                    /* Hadamard-like: unconditional real unit form with q == 1 and the scale already in the pass scale */
+                    const bool hlike = sform == S_UNIT_R && !mux && !cond && h.c[0][1][1] == 1.0 && h.c[0][3][1] == 1.0 && M.hform;
+                    if (mux) { slot_set(0, false); slot_set(1, false); }
+                    else if (hlike) { slot_set(0, false); slot_set(0, false); }   /* both sets usable: an X merged later brings a predicate */
+                    else { slot_set(0, true); slot_set(0, false); }
+                    if (hlike) sform = S_UNIT_H;
+                    if ((int)slot.size() != 2 * SET16 * 16) { qsb_set_error("internal: slot of %zu bytes", slot.size()); return QSB_ERR_ARG; }
+                    const uint32_t pm_new = tm8 | (wbits << QSB_TB);
+                    if (sform == S_XDEF && next_group[vb] > 0) {
+                        /* merge a deferred X into the gate it follows on the same vector bit: same slot, same predicate.
+                         * An unconditional single-set gate takes the X's predicate (both coefficient sets identical). */
+                        uint8_t *Gp = groups[next_group[vb] - 1].data();
+                        const uint8_t pf = Gp[vb];
+                        uint32_t ppm; memcpy(&ppm, Gp + 16 + 4 * vb, 4);
+                        uint8_t *sets = Gp + 32 + (size_t)vb * 2 * SET16 * 16;
+                        const bool prev_uncond = ppm == 0 && slot_single[next_group[vb] - 1][vb];
+                        if ((pf & (S_UNIT_R | S_UNIT_I | S_UNIT_H | S_DIAG)) && !(pf & S_XDEF) && (ppm == pm_new || prev_uncond)) {
+                            if (ppm != pm_new) { memcpy(sets, sets + (size_t)SET16 * 16, (size_t)SET16 * 16); memcpy(Gp + 16 + 4 * vb, &pm_new, 4); }
+                            Gp[vb] = (uint8_t)(pf | S_XDEF);
+                            continue;
                         }
-                        std::vector<uint8_t> rec(16, 0);
-                        set_hdr(rec, K_NOP, 1u << vb, 0, pm_new, 0);
-                        recs.push_back(rec); rinfo.push_back({K_NOP, pm_new, false, false});
-                        last_rec[vb] = (int)recs.size() - 1;
-                        continue;
                     }
-                    std::vector<uint8_t> rec(16, 0);
-                    int kcode;
-                    const int ai = sform == F_UR ? 3 : 5;
-                    const bool single = !mux && !cond && (sform == F_DG || C(0, ai) == 1.0);
-                    if (single && sform != F_DG) {
-                        const bool hlike = sform == F_UR && C(0, 1) == 1.0;      /* q == 1: x1 = k x1 + x0 */
-                        kcode = (hlike ? K_UH1 : sform == F_UR ? K_UR1 : K_UI1) + vb;
-                        put_set(rec, 0, false);
-                    } else {
-                        kcode = (sform == F_UR ? K_UR : sform == F_UI ? K_UI : K_DG) + vb;
-                        if (mux) { put_set(rec, 0, false); put_set(rec, 1, false); }
-                        else { put_set(rec, 0, true); put_set(rec, 0, false); }
-                    }
-                    if (rec.size() % 16) { qsb_set_error("internal: op record of %zu bytes", rec.size()); return QSB_ERR_ARG; }
-                    set_hdr(rec, kcode, 0, 0, pm_new, 0);
-                    recs.push_back(rec); rinfo.push_back({kcode, pm_new, single && sform != F_DG, !(single && sform != F_DG) && !mux && !cond});
-                    last_rec[vb] = (int)recs.size() - 1;
+                    const int g = next_group[vb]++;
+                    if (g == (int)groups.size()) { groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0)); slot_single.push_back({{false, false, false, false}}); }
+                    slot_single[g][vb] = !mux && !cond;
+                    uint8_t *G0 = groups[g].data();
+                    G0[vb] = (uint8_t)sform;                                   /* form byte of slot vb */
+                    memcpy(G0 + 16 + 4 * vb, &pm_new, 4);                      /* predicate mask */
+                    memcpy(G0 + 32 + (size_t)vb * 2 * SET16 * 16, slot.data(), slot.size());
                     continue;
                 }
 
-                /* ---- rare forms ---- */
-                const int two = mux ? 1 : 0;
+                /* ---- specials (generic interpreter) ---- */
+                if (!groups.empty()) close_segment();     /* a special runs before the groups of its segment */
+                const int two = mux ? 1 : 0, skip = (!mux && cond) ? 1 : 0;
                 std::vector<uint8_t> sets[2];
                 int gcode = -1;
                 auto write_set = [&](std::vector<uint8_t> &o, int set) {
@@ -1182,7 +1183,7 @@ struct PassBuilder {
                     for (int c = 0; c < 8; c++) m[c][0] = m[c][1] = 0.0;
                     switch (code) {
                     case OP_MAT_U: case OP_MAT_UI: {   /* only when the outer-condition table is full */
-                        gcode = K_FULL + vb;
+                        gcode = G_FULL_G + vb;
                         for (int l = 0; l < 2; l++) {
                             if (code == OP_MAT_U) {
                                 const double pp = h.c[set][0][l], q = h.c[set][1][l], kk = h.c[set][2][l], a = h.c[set][3][l];
@@ -1196,30 +1197,30 @@ struct PassBuilder {
                         break;
                     }
                     case OP_XDEF:
-                        gcode = K_FULL + vb;
+                        gcode = G_FULL_G + vb;
                         m[2][0] = m[2][1] = 1.0; m[4][0] = m[4][1] = 1.0;
                         put_gen(m);
                         break;
                     case OP_MAT_R:
-                        gcode = K_FULL + vb;
+                        gcode = G_FULL_G + vb;
                         put_v(o, L(2)); put_v(o, zero); put_v(o, L(0)); put_v(o, zero); put_v(o, L(1)); put_v(o, zero); put_v(o, L(3)); put_v(o, zero);
                         break;
                     case OP_MAT_I:
-                        gcode = K_FULL + vb;
+                        gcode = G_FULL_G + vb;
                         put_v(o, L(4)); put_v(o, zero); put_v(o, zero); put_v(o, L(1)); put_v(o, zero); put_v(o, L(3)); put_v(o, L(5)); put_v(o, zero);
                         break;
                     case OP_MAT_G:
-                        gcode = K_FULL + vb;
+                        gcode = G_FULL_G + vb;
                         put_v(o, L(6)); put_v(o, L(0)); put_v(o, L(1)); put_v(o, L(2)); put_v(o, L(3)); put_v(o, L(4)); put_v(o, L(7)); put_v(o, L(5));
                         break;
                     case OP_MATP_R:
-                        gcode = K_MATP_R; put_v(o, L(0)); put_v(o, L(1));
+                        gcode = G_MATP_R; put_v(o, L(0)); put_v(o, L(1));
                         break;
                     case OP_MATP_G:
-                        gcode = K_MATP_G; put_v(o, L(0)); put_v(o, L(1)); put_v(o, L(2)); put_v(o, L(3));
+                        gcode = G_MATP_G; put_v(o, L(0)); put_v(o, L(1)); put_v(o, L(2)); put_v(o, L(3));
                         break;
                     case OP_DIAG_V: case OP_DIAG_ALL: case OP_DIAG_GEN:
-                        gcode = code == OP_DIAG_V ? K_DIAG_V + vb : code == OP_DIAG_ALL ? K_DIAG_ALL : K_DIAG_GEN;
+                        gcode = code == OP_DIAG_V ? G_DIAG_V + vb : code == OP_DIAG_ALL ? G_DIAG_ALL : G_DIAG_GEN;
                         put_v(o, L(0)); put_v(o, L(1));
                         break;
                     default: break;
@@ -1230,30 +1231,33 @@ struct PassBuilder {
                 if (mux) write_set(sets[1], 1);
                 if (gcode < 0) { qsb_set_error("internal: op code %d cannot be lowered", code); return QSB_ERR_ARG; }
                 /* an unconditional unit-form op that fell through keeps its scale in the matrix: nothing else to do.
-                 * A conditional XDEF / unit op lowered to K_FULL is a plain controlled gate (skip when the predicate fails). */
-                std::vector<uint8_t> rec(16, 0);
-                rec.insert(rec.end(), sets[0].begin(), sets[0].end());
-                rec.insert(rec.end(), sets[1].begin(), sets[1].end());
-                set_hdr(rec, (uint32_t)gcode | (two ? K_TWO : 0), 0, vmask, tm8, om);
-                recs.push_back(rec); rinfo.push_back({gcode, tm8, false, false});
-                if (code != OP_DIAG_ALL && code != OP_DIAG_GEN && code != OP_MATP_R && code != OP_MATP_G) last_rec[vb] = (int)recs.size() - 1;
-                else for (int b2 = 0; b2 < QSB_NVB; b2++) last_rec[b2] = (int)recs.size() - 1;   /* touches every vector: no X merges across it */
+                 * A conditional XDEF / unit op lowered to FULL_G is a plain controlled gate (skip when the predicate fails). */
+                const size_t bytes = 16 + sets[0].size() + sets[1].size();
+                uint32_t hdr[4] = {GOPK(gcode, two, skip, vmask, bytes / 16), tm8, (uint32_t)om, (uint32_t)(om >> 32)};
+                const uint8_t *q = (const uint8_t *)hdr; specials.insert(specials.end(), q, q + 16);
+                specials.insert(specials.end(), sets[0].begin(), sets[0].end());
+                specials.insert(specials.end(), sets[1].begin(), sets[1].end());
+                n_special++;
             }
-            for (auto &rc : recs) opstream[r].insert(opstream[r].end(), rc.begin(), rc.end());
-            n_ops_round[r] = (uint32_t)recs.size();
-            G.n_tph = n_tph; G.n_ang = n_ang; G.n_ops = n_ops_round[r];
+            close_segment();
+            G.n_tph = n_tph; G.n_ang = n_ang; G.n_seg = (uint32_t)segrec[r].size();
         }
         gp.n_cond = n_cond;
         size_t off = al16(sizeof(GPass));
         gp.rounds_off16 = (uint32_t)(off / 16);
         off += al16(sizeof(GRound) * nrounds);
         for (int r = 0; r < nrounds; r++) {
-            gr[r].ops_off16 = (uint32_t)(off / 16);
-            off += opstream[r].size();
+            gr[r].seg_off16 = (uint32_t)(off / 16);
+            const size_t body0 = off + segrec[r].size() * sizeof(GSegment);
+            for (const SegRec &sr : segrec[r]) {
+                GSegment gs; gs.n_special = sr.n_special; gs.special_off16 = (uint32_t)((body0 + sr.special_rel) / 16);
+                gs.n_groups = sr.n_groups; gs.group_off16 = (uint32_t)((body0 + sr.group_rel) / 16);
+                const uint8_t *q = (const uint8_t *)&gs; segstream[r].insert(segstream[r].end(), q, q + sizeof gs);
+            }
+            off = body0 + bodystream[r].size();
+            gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size() + angstream[r].size();
         }
-        off += 16 * QSB_OP_PREFETCH16(f32);   /* slack: the op loop fetches the head of one record past the last */
-        for (int r = 0; r < nrounds; r++) { gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size() + angstream[r].size(); }
-        const size_t total = off + 16;
+        const size_t total = off + 64;   /* slack: the group loop prefetches one group header past the last group */
         if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_PLAN_OVERFLOW; }
         hp.hdr.blob_bytes = (uint32_t)total;
         std::vector<uint8_t> &b = hp.blob;
@@ -1261,7 +1265,10 @@ struct PassBuilder {
         memcpy(&b[0], &gp, sizeof gp);
         memcpy(&b[(size_t)gp.rounds_off16 * 16], gr.data(), sizeof(GRound) * nrounds);
         for (int r = 0; r < nrounds; r++) {
-            if (!opstream[r].empty()) memcpy(&b[(size_t)gr[r].ops_off16 * 16], opstream[r].data(), opstream[r].size());
+            size_t at = (size_t)gr[r].seg_off16 * 16;
+            if (!segstream[r].empty()) memcpy(&b[at], segstream[r].data(), segstream[r].size());
+            at += segstream[r].size();
+            if (!bodystream[r].empty()) memcpy(&b[at], bodystream[r].data(), bodystream[r].size());
             if (!tphstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16], tphstream[r].data(), tphstream[r].size());
             if (!angstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16 + tphstream[r].size()], angstream[r].data(), angstream[r].size());
         }
@@ -1280,6 +1287,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.lazy_diag = opt && opt->reserved[1] == 2;      /* reserved[1] = 2: keep the qubits of phase gates thread-level (A/B runs;
                                                         same speed on random circuits, 2.4x more rounds on QFT) */
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
+    M.hform = !(opt && opt->reserved[4] == 3);       /* reserved[4] = 3: no Hadamard-like slot form S_UNIT_H (A/B runs) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.force_top = g > 0 && opt && opt->reserved[5] == 3;        /* reserved[5] = 3: NCCL-style plan executed as a pipelined exchange */
     M.fused_exchange = g > 0 && opt && opt->reserved[5] == 1;   /* reserved[5] = 1: exchanges fused into the preceding pass (peer stores) */

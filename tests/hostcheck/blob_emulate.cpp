@@ -1,6 +1,6 @@
 /*
  * blob_emulate.cpp -- TEST DOUBLE, never shipped: a host interpreter of the DEVICE ENCODING of a pass
- * (the kernel-parameter blob: GPass, GRound, the flat op-record stream, thread-phase lists),
+ * (the kernel-parameter blob: GPass, GRound, segments, groups of slots, specials, thread-phase lists),
  * statement by statement what k_tile_pass in tiled_kernel.cu does with it.  emulate.cpp checks the
  * planner's logical tables; this file checks their lowering (PassBuilder::serialise), so that the
  * bytes the GPU reads are verified against the oracle on the CPU as well.
@@ -38,7 +38,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
     const uint8_t *B = hp.blob.data();
     Rd rd{B, f32};
     GPass P; memcpy(&P, B, sizeof P);
-    const int SET16 = QSB_SET16(f32);
+    const int SET16 = QSB_SET16(f32), G16 = QSB_GROUP16(f32);
     const uint64_t loc_bytes = ((uint64_t)1 << nloc) * AMP;
     std::vector<cd> regs((size_t)QSB_THREADS * QSB_NV * L), smem((size_t)QSB_SLOTS * L);
     std::vector<uint32_t> xm(QSB_THREADS);
@@ -80,78 +80,73 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                     if (!imag) { x0 += p * x1; x1 = k * x1 + q * x0; } else { x0 += cd(0, p) * x1; x1 = k * x1 + cd(0, q) * x0; }
                 }
             };
-            /* the flat record stream, record by record, thread by thread (tiled.h) */
-            const uint8_t *op = B + (size_t)RD.ops_off16 * 16;
-            for (uint32_t i = 0; i < RD.n_ops; i++) {
-                uint32_t h[4]; memcpy(h, op, 16);
-                const uint8_t *c = op + 16;
-                const uint32_t size16 = h[0] >> 16;
-                if (size16 == 0 || (size_t)(op - B) + (size_t)size16 * 16 > hp.blob.size()) { bad++; break; }
-                op += (size_t)size16 * 16;
-                const uint32_t code = h[0] & 0xff, xbits = (h[0] >> 8) & 0xf, vmask = (h[0] >> 12) & 0xf;
-                const uint64_t om = ((uint64_t)h[3] << 32) | h[2];
-                if (code <= K_NOP) {
-                    if (om) bad++;                 /* scalar-coefficient records test outer bits through W only */
-                    const int vb = code & 3;
-                    const bool single = code >= K_UR1 && code < K_NOP;
-                    const size_t need = code == K_NOP ? 1 : single ? 1 + SET16 : 1 + 2 * SET16;
-                    if (size16 != need) bad++;
-                    const uint8_t *c0 = c, *c1 = c + (size_t)SET16 * 16;
+            const GSegment *seg = (const GSegment *)(B + (size_t)RD.seg_off16 * 16);
+            for (uint32_t sg = 0; sg < RD.n_seg; sg++) {
+                GSegment SG; memcpy(&SG, &seg[sg], sizeof SG);
+                const uint8_t *op = B + (size_t)SG.special_off16 * 16;
+                for (uint32_t i = 0; i < SG.n_special; i++) {
+                    uint32_t h[4]; memcpy(h, op, 16);
+                    const uint8_t *c = op + 16;
+                    op += (size_t)(h[0] >> 16) * 16;
+                    const uint32_t code = h[0] & 0xff, vmask = (h[0] >> 12) & 0xf; const bool two = (h[0] >> 8) & 1;
+                    const uint64_t om = ((uint64_t)h[3] << 32) | h[2];
                     for (int tid = 0; tid < QSB_THREADS; tid++) {
-                        const uint32_t tw = (uint32_t)tid | (W << QSB_TB);
-                        const bool pred = (tw & h[1]) == h[1];
-                        if (pred) xm[tid] ^= xbits;
-                        if (code == K_NOP) continue;
-                        const uint8_t *cs = (pred && !single) ? c1 : c0;
-                        const double a0 = rd.S(cs, 0), a1 = rd.S(cs, 1), a2 = rd.S(cs, 2), a3 = rd.S(cs, 3);
-                        if (code < K_UI) { unit(tid, vb, false, a0, a1, a2); pend[tid] *= a3; }
-                        else if (code < K_DG) { unit(tid, vb, true, a0, a1, a2); pend[tid] *= a3; }
-                        else if (code < K_UR1) {
-                            cd *R = &regs[(size_t)tid * QSB_NV * L];
-                            for (int v = 0; v < QSB_NV; v++) if ((v >> vb) & 1) for (int l = 0; l < L; l++) R[v * L + l] *= cd(a0, a1);
-                        }
-                        else if (code < K_UI1) { if (a3 != 1.0) bad++; unit(tid, vb, false, a0, a1, a2); }
-                        else if (code < K_UH1) { if (a3 != 1.0) bad++; unit(tid, vb, true, a0, a1, a2); }
-                        else { if (a3 != 1.0 || a1 != 1.0) bad++; unit(tid, vb, false, a0, 1.0, a2); }   /* K_UH1: q == 1 */
+                        const bool pred = ((src_outer & om) == om) && (((uint32_t)tid & h[1]) == h[1]);
+                        if (!two && !pred) continue;
+                        const bool s1 = two && pred;
+                        cd *R = &regs[(size_t)tid * QSB_NV * L];
+                        if (code >= G_FULL_G && code < G_FULL_G + 4) {
+                            const int vb = code - G_FULL_G; const uint8_t *cs = c + (s1 ? 64 : 0);
+                            double m[8][2]; for (int k = 0; k < 8; k++) rd.V(cs, k, m[k]);
+                            for (int v = 0; v < QSB_NV; v++) if (!((v >> vb) & 1)) for (int l = 0; l < L; l++) {
+                                const int ll = f32 ? l : 1;
+                                cd m00(m[0][ll], m[1][ll]), m01(m[2][ll], m[3][ll]), m10(m[4][ll], m[5][ll]), m11(m[6][ll], m[7][ll]);
+                                cd x0 = R[v * L + l], x1 = R[(v | (1 << vb)) * L + l];
+                                R[v * L + l] = m00 * x0 + m01 * x1; R[(v | (1 << vb)) * L + l] = m10 * x0 + m11 * x1;
+                            }
+                        } else if ((code >= G_DIAG_V && code < G_DIAG_V + 4) || code == G_DIAG_ALL || code == G_DIAG_GEN) {
+                            double pr[2], pi[2]; const uint8_t *cs = c + (s1 ? 16 : 0);
+                            rd.V(cs, 0, pr); rd.V(cs, 1, pi);
+                            for (int v = 0; v < QSB_NV; v++) {
+                                if (code != G_DIAG_ALL && code != G_DIAG_GEN && !((v >> (code - G_DIAG_V)) & 1)) continue;
+                                if (code == G_DIAG_GEN && (v & vmask) != vmask) continue;
+                                for (int l = 0; l < L; l++) { const int ll = f32 ? l : 1; R[v * L + l] *= cd(pr[ll], pi[ll]); }
+                            }
+                        } else if (code == G_MATP_R || code == G_MATP_G) {
+                            if (!f32) { bad++; continue; }
+                            double A[2][2] = {{0, 0}, {0, 0}}, Bc[2][2] = {{0, 0}, {0, 0}};   /* [re/im][lane] */
+                            if (code == G_MATP_R) { const uint8_t *cs = c + (s1 ? 16 : 0); rd.V(cs, 0, A[0]); rd.V(cs, 1, Bc[0]); }
+                            else { const uint8_t *cs = c + (s1 ? 32 : 0); rd.V(cs, 0, A[0]); rd.V(cs, 1, A[1]); rd.V(cs, 2, Bc[0]); rd.V(cs, 3, Bc[1]); }
+                            for (int v = 0; v < QSB_NV; v++) {
+                                cd x0 = R[v * L], x1 = R[v * L + 1];
+                                R[v * L] = cd(A[0][0], A[1][0]) * x0 + cd(Bc[0][0], Bc[1][0]) * x1;
+                                R[v * L + 1] = cd(A[0][1], A[1][1]) * x1 + cd(Bc[0][1], Bc[1][1]) * x0;
+                            }
+                        } else bad++;
                     }
-                    continue;
                 }
-                if (xbits) bad++;
-                const uint32_t rc = code & 0x7f; const bool two = (code & K_TWO) != 0;
-                for (int tid = 0; tid < QSB_THREADS; tid++) {
-                    const bool pred = ((src_outer & om) == om) && (((uint32_t)tid & h[1]) == h[1]);
-                    if (h[1] >> QSB_TB) bad++;     /* rare forms carry thread bits only in y */
-                    if (!two && !pred) continue;
-                    const bool s1 = two && pred;
-                    cd *R = &regs[(size_t)tid * QSB_NV * L];
-                    if (rc >= K_FULL && rc < K_FULL + 4) {
-                        const int vb = rc - K_FULL; const uint8_t *cs = c + (s1 ? 64 : 0);
-                        double m[8][2]; for (int k = 0; k < 8; k++) rd.V(cs, k, m[k]);
-                        for (int v = 0; v < QSB_NV; v++) if (!((v >> vb) & 1)) for (int l = 0; l < L; l++) {
-                            const int ll = f32 ? l : 1;
-                            cd m00(m[0][ll], m[1][ll]), m01(m[2][ll], m[3][ll]), m10(m[4][ll], m[5][ll]), m11(m[6][ll], m[7][ll]);
-                            cd x0 = R[v * L + l], x1 = R[(v | (1 << vb)) * L + l];
-                            R[v * L + l] = m00 * x0 + m01 * x1; R[(v | (1 << vb)) * L + l] = m10 * x0 + m11 * x1;
+                const uint8_t *gp = B + (size_t)SG.group_off16 * 16;
+                for (uint32_t g = 0; g < SG.n_groups; g++, gp += (size_t)G16 * 16) {
+                    uint32_t pm[4]; memcpy(pm, gp + 16, 16);
+                    for (int vb = 0; vb < QSB_NVB; vb++) {
+                        const uint32_t form = gp[vb];
+                        if (!form) continue;
+                        const uint8_t *c0 = gp + 32 + (size_t)vb * 2 * SET16 * 16, *c1 = c0 + (size_t)SET16 * 16;
+                        for (int tid = 0; tid < QSB_THREADS; tid++) {
+                            const uint32_t tw = (uint32_t)tid | (W << QSB_TB);
+                            const bool pred = (tw & pm[vb]) == pm[vb];
+                            const uint8_t *cs = pred ? c1 : c0;
+                            const double a0 = rd.S(cs, 0), a1 = rd.S(cs, 1), a2 = rd.S(cs, 2), a3 = rd.S(cs, 3);
+                            if (form & S_UNIT_R) { unit(tid, vb, false, a0, a1, a2); pend[tid] *= a3; }
+                            else if (form & S_UNIT_I) { unit(tid, vb, true, a0, a1, a2); pend[tid] *= a3; }
+                            else if (form & S_UNIT_H) { if (a1 != 1.0 || a3 != 1.0) bad++; unit(tid, vb, false, a0, 1.0, a2); }
+                            else if (form & S_DIAG) {
+                                cd *R = &regs[(size_t)tid * QSB_NV * L];
+                                for (int v = 0; v < QSB_NV; v++) if ((v >> vb) & 1) for (int l = 0; l < L; l++) R[v * L + l] *= cd(a0, a1);
+                            } else if (!(form & S_XDEF)) bad++;
+                            if ((form & S_XDEF) && pred) xm[tid] ^= 1u << vb;
                         }
-                    } else if ((rc >= K_DIAG_V && rc < K_DIAG_V + 4) || rc == K_DIAG_ALL || rc == K_DIAG_GEN) {
-                        double pr[2], pi[2]; const uint8_t *cs = c + (s1 ? 16 : 0);
-                        rd.V(cs, 0, pr); rd.V(cs, 1, pi);
-                        for (int v = 0; v < QSB_NV; v++) {
-                            if (rc != K_DIAG_ALL && rc != K_DIAG_GEN && !((v >> (rc - K_DIAG_V)) & 1)) continue;
-                            if (rc == K_DIAG_GEN && (v & vmask) != vmask) continue;
-                            for (int l = 0; l < L; l++) { const int ll = f32 ? l : 1; R[v * L + l] *= cd(pr[ll], pi[ll]); }
-                        }
-                    } else if (rc == K_MATP_R || rc == K_MATP_G) {
-                        if (!f32) { bad++; continue; }
-                        double A[2][2] = {{0, 0}, {0, 0}}, Bc[2][2] = {{0, 0}, {0, 0}};   /* [re/im][lane] */
-                        if (rc == K_MATP_R) { const uint8_t *cs = c + (s1 ? 16 : 0); rd.V(cs, 0, A[0]); rd.V(cs, 1, Bc[0]); }
-                        else { const uint8_t *cs = c + (s1 ? 32 : 0); rd.V(cs, 0, A[0]); rd.V(cs, 1, A[1]); rd.V(cs, 2, Bc[0]); rd.V(cs, 3, Bc[1]); }
-                        for (int v = 0; v < QSB_NV; v++) {
-                            cd x0 = R[v * L], x1 = R[v * L + 1];
-                            R[v * L] = cd(A[0][0], A[1][0]) * x0 + cd(Bc[0][0], Bc[1][0]) * x1;
-                            R[v * L + 1] = cd(A[0][1], A[1][1]) * x1 + cd(Bc[0][1], Bc[1][1]) * x0;
-                        }
-                    } else bad++;
+                    }
                 }
             }
             const uint8_t *e = B + (size_t)RD.tph_off16 * 16;
