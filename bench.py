@@ -83,11 +83,44 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
+def load_circuits():
+    """The circuit generators WITHOUT importing the package: the reference arm must not map libqsim_b200.so
+    (the package __init__ loads the library as an import side effect)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("qsb_circuits", os.path.join(ROOT, "gpu_quantum_simulator_b200", "circuits.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_full_depth(n_workload, n_s=22):
+    """The UNMODIFIED reference program on the WHOLE depth-20 circuit at n_s qubits (about 20 s of one core at 22 q):
+    a real run, not a one-layer sample; gates/s at the workload size is that figure scaled by 2^(n_s - n) and
+    labelled extrapolated (one sweep per gate: cost is linear in the state size)."""
+    circuits = load_circuits()
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cexe")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/ref_cexe missing (build it in the container: make -C oracle)")
+    circ = circuits.random_layered(n_s, DEPTH, SEED)
+    ref, _ = circuits.to_reference_gates(circ)
+    with tempfile.TemporaryDirectory() as d:
+        p1 = os.path.join(d, "full.qasm")
+        open(p1, "w").write(circuits.to_qasm(ref, n_s))
+        t = float(subprocess.run([exe, p1, "0"], capture_output=True, text=True, check=True).stdout.split()[0])
+    measured = len(circ) / t
+    return {"value": measured * 2.0 ** (n_s - n_workload), "unit": "gates/s", "cores": 1, "kind": "reference",
+            "sample": (f"full depth-{DEPTH} random_layered({n_s}q, seed {SEED}): {len(circ)} source gates = {len(ref)} reference-set gates "
+                       f"through oracle/_ref/ref_cexe (unmodified quantum_simulator.c, gcc -O2, 1 thread), its own stdout line; "
+                       f"value = measured gates/s scaled by 2^({n_s}-{n_workload}) to the {n_workload}q workload (extrapolated)"),
+            "measured": {"qubits": n_s, "seconds": t, "gates_per_sec": measured},
+            "host_cores_available": os.cpu_count(), "sample_seconds": t, "sample_qubits": n_s}, t
+
+
 def reference_sample(n_workload, step_budget_s, reps=1):
     """Time the UNMODIFIED reference program on the first layer of random_layered at the largest
     n_s <= n_workload that fits the budget; scale gates/s by 2^(n_s - n_workload) (cost is linear in
     the state size: one sweep per gate)."""
-    from gpu_quantum_simulator_b200 import circuits
+    circuits = load_circuits()
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_cexe")
     kind = "reference"
     if not os.path.exists(exe):
@@ -128,6 +161,40 @@ def reference_sample(n_workload, step_budget_s, reps=1):
             "host_cores_available": os.cpu_count(), "sample_seconds": t, "sample_qubits": n_s}, t
 
 
+def run_reference_gpu(circuits, sizes=(28, 30)):
+    """oracle/_ref/ref_4x4 = /root/reference/quantum_simulator_4x4.cu, UNMODIFIED, nvcc -arch=sm_100a (oracle/Makefile): the reference's
+    fastest CUDA variant on the same B200, fed the reference-gate spelling of the same circuits in its own "<num_q> <num_g>" format
+    (quantum_simulator_4x4.cu:293-529).  Its one stdout line is end to end (parse, malloc, cudaMalloc, kernels, D2H of both planes);
+    launches are counted by an LD_PRELOAD shim (oracle/launch_count.c).  It drops fused gates within 1e-3 of identity and is not a
+    numerical oracle: only its time is reported."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_4x4")
+    shim = os.path.join(ROOT, "oracle", "_ref", "liblaunchcount.so")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_4x4 missing (built by make -C oracle where /root/reference and nvcc exist)"}
+    out = {"program": "oracle/_ref/ref_4x4 (unmodified quantum_simulator_4x4.cu, nvcc -arch=sm_100a -O2)", "runs": {}}
+    for n in sizes:
+        circ = circuits.random_layered(n, DEPTH, SEED)
+        ref, _ = circuits.to_reference_gates(circ)
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "c.txt")
+            open(p, "w").write(circuits.to_cuda_variant_text(ref, n))
+            env = dict(os.environ)
+            if os.path.exists(shim):
+                env["LD_PRELOAD"] = shim
+            try:
+                r = subprocess.run([exe, p], capture_output=True, text=True, env=env, timeout=300)
+                secs = float(r.stdout.split()[0])
+                launches = None
+                for ln in r.stderr.splitlines():
+                    if ln.startswith("launches="):
+                        launches = int(ln.split("=")[1])
+                out["runs"][f"{n}q"] = {"seconds_end_to_end": secs, "gates_per_sec": len(circ) / secs, "source_gates": len(circ),
+                                        "reference_set_gates": len(ref), "kernel_launches": launches}
+            except Exception as e:
+                out["runs"][f"{n}q"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,7 +203,7 @@ def run_reference_arm(args):
     budget = max(1.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     vals, secs, base = [], [], None
     for i in range(args.warmup + args.steps):
-        base, t = reference_sample(n, budget)
+        base, t = reference_full_depth(n) if budget >= 19.0 else reference_sample(n, budget)
         if i >= args.warmup:
             vals.append(base["value"]); secs.append(t)
     value = sum(vals) / len(vals)
@@ -180,7 +247,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def make_sim(n):
+    def make_sim(n, prec=prec):
         sim = q.Simulator(n, precision=prec, rank=rank, world_size=world, device=local_rank, low_bits=args.low_bits,
                           reserved=[0, args.no_lazy_diag, args.trim, args.cost_cap, args.res4, args.fused, args.no_sink])
         if world > 1:
@@ -188,11 +255,12 @@ def run_ours(args):
             qdist.init_comm(sim, dist)
         return sim
 
-    def measure(n, steps, warmup, with_clocks):
+    def measure(n, steps, warmup, with_clocks, prec=prec, workload=args.workload):
         """-> dict with the device-timed numbers of random_layered(n) and the live objects (sim, plan, circ)."""
-        circ = circuits.random_layered(n, DEPTH, SEED) if args.workload == "layered" else circuits.qft(n)
+        amp_bytes = 16 if prec == q.F64 else 8
+        circ = circuits.random_layered(n, DEPTH, SEED) if workload == "layered" else circuits.qft(n)
         gates = q.gates_from_circuit(circ)
-        sim = make_sim(n)
+        sim = make_sim(n, prec)
         plan = sim.plan(gates)
         pst = plan.stats()
         for _ in range(max(warmup, 3)):
@@ -226,7 +294,7 @@ def run_ours(args):
         if os.path.exists(tfile):
             try:
                 tj = json.load(open(tfile))
-                traffic = tj.get(f"{n}q_f{args.precision}_{world}gpu")
+                traffic = tj.get(f"{n}q_f{32 if prec == q.F32 else 64}_{world}gpu_{workload}") or tj.get(f"{n}q_f{32 if prec == q.F32 else 64}_{world}gpu")
                 if traffic is None and "dram_over_algorithmic" in tj:
                     traffic = tj["dram_over_algorithmic"] * bytes_per_launch
             except Exception:
@@ -249,6 +317,34 @@ def run_ours(args):
         return {"n": n, "circ": circ, "sim": sim, "plan": plan, "pst": pst, "ms_per_step": ms_per_step,
                 "value": len(circ) / (ms_per_step * 1e-3), "wall_ms": wall_ms, "xch_ms": xch_ms, "clocks": clocks,
                 "roofline": roofline, "n_loc_amps": n_loc_amps}
+
+    # ---- world > 1: correctness of the sharded path at this revision, BEFORE anything is timed (task 1a)
+    parity = None
+    if world > 1:
+        from gpu_quantum_simulator_b200 import dist as qdist
+        pn, pdepth, pseed, tol = 24, 8, 777, 1e-5
+        pcirc = circuits.random_layered(pn, pdepth, pseed)
+        pg = q.gates_from_circuit(pcirc)
+        ssim = make_sim(pn)                                  # default exchange flavour of this world size
+        pst = ssim.apply(pg)
+        got = qdist.gather_state(ssim, dist)                 # logical order, every rank
+        ssim.close()
+        err = 0.0
+        if rank == 0:
+            with q.Simulator(pn, precision=prec, device=local_rank) as one:   # the same circuit unsharded, same GPU
+                one.apply(pg)
+                err = float(np.max(np.abs(got - one.state())))
+        et = torch.tensor([err], dtype=torch.float64, device="cuda")
+        dist.broadcast(et, 0)
+        err = float(et.cpu()[0])
+        parity = {"n": pn, "depth": pdepth, "seed": pseed, "what": "sharded run (default exchange flavour) vs the same circuit on one GPU, full state",
+                  "exchanges": int(pst["swaps"]), "max_abs_err": err, "tol": tol, "ok": bool(err <= tol)}
+        del got
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": "gates_per_sec", "value": None, "n_gpus": world, "parity": parity, "error": "sharded parity failed"}))
+            dist.barrier(); dist.destroy_process_group()
+            raise SystemExit(3)
 
     # workload: 34 q at every N (strong scaling); smaller only if the state does not fit
     n = args.qubits or 34
@@ -287,7 +383,12 @@ def run_ours(args):
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.cpu()[0])
-        assert abs(norm * world - 1.0) < 1e-2 or world > 1, norm
+        tn = torch.tensor([norm], dtype=torch.float64, device="cuda")     # per-rank partial of sum |a|^2
+        if dist is not None:
+            dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        norm_total = float(tn.cpu()[0])
+        if abs(norm_total - 1.0) > 1e-3:
+            raise SystemExit(f"norm check failed after the e2e run: sum |a|^2 = {norm_total}")
         e2e = {"value": len(circ) / e2e_s, "unit": "gates/s",
                "h2d_bytes_per_step": int(len(text) + pst["passes"] * 4000),
                "d2h_bytes_per_step": int(head * 16 + 148 * 4 * 32), "seconds_per_step": e2e_s,
@@ -313,12 +414,61 @@ def run_ours(args):
                                         "passes": ms["pst"]["passes"], "rounds": ms["pst"]["rounds"], "roofline": ms["roofline"]}
             plan, sim = ms["plan"], ms["sim"]
 
+    # ---- N = 1: every BASELINE.json configuration gets a driver-timed number in the same run (task 6)
+    configs = e2e_full = reference_gpu = None
+    if world == 1 and not args.qubits and not args.no_30q and not args.no_extras:
+        plan.close(); sim.close()
+        configs = {}
+        for name, cn, cprec, cwl in (("random_layered_28q_f32", 28, q.F32, "layered"), ("qft_30q_f32", 30, q.F32, "qft"),
+                                     ("qft_30q_f64", 30, q.F64, "qft"), ("random_layered_30q_f64", 30, q.F64, "layered"),
+                                     ("random_layered_32q_f32", 32, q.F32, "layered")):
+            try:
+                mc = measure(cn, 3, 3, False, prec=cprec, workload=cwl)
+            except q.QsbError as e:
+                configs[name] = {"error": str(e)}
+                continue
+            configs[name] = {"ms_per_step": mc["ms_per_step"], "value": mc["value"], "unit": "gates/s", "source_gates": len(mc["circ"]),
+                             "passes": mc["pst"]["passes"], "rounds": mc["pst"]["rounds"], "frac": mc["roofline"]["frac"],
+                             "achieved_GBps": mc["roofline"]["achieved"], "dtype": "f32" if cprec == q.F32 else "f64", "steps": 3, "warmup": 3}
+            mc["plan"].close(); mc["sim"].close()
+        # ---- honest e2e at 30 q: QASM text in, the ENTIRE state (2^30 amplitudes, device dtype) out to pinned host memory,
+        #      as the reference programs copy the whole state back (naive.cu:193-194, 4x4.cu:512-513)
+        try:
+            c30 = circuits.random_layered(30, DEPTH, SEED)
+            text30 = circuits.to_qasm(c30, 30)
+            host = torch.empty(2 << 30, dtype=torch.float32, pin_memory=True).numpy()
+            s30 = make_sim(30, q.F32)
+            secs, dl = [], []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                nq, g30 = q.parse_qasm_string(text30)
+                s30.reset()
+                p30 = s30.plan(g30)
+                s30.execute(p30)
+                t1 = time.perf_counter()
+                s30.state_native(out=host)                      # qsb_download_native: double-buffered export + D2H
+                t2 = time.perf_counter()
+                p30.close()
+                secs.append(t2 - t0); dl.append(t2 - t1)
+            nrm = float(np.dot(host[: 1 << 24].astype(np.float64), host[: 1 << 24].astype(np.float64)))
+            e2e_full = {"workload": f"random_layered_30q_d{DEPTH}", "value": len(c30) / min(secs), "unit": "gates/s", "seconds_per_step": min(secs),
+                        "h2d_bytes_per_step": len(text30), "d2h_bytes_per_step": int(host.nbytes), "download_seconds": min(dl),
+                        "download_GBps": host.nbytes / min(dl) / 1e9, "head_norm_check": nrm,
+                        "what": "qsb_parse_qasm_string + qsb_plan_create + qsb_reset + qsb_execute + qsb_download_native of all 2^30 amplitudes (8 GiB, f32) into pinned host memory"}
+            s30.close(); del host
+        except Exception as e:   # e.g. not enough pinned host memory on the box
+            e2e_full = {"error": str(e)}
+        # ---- the reference's own fastest CUDA variant on this GPU (BASELINE.md section 3 "courtesy baseline")
+        reference_gpu = run_reference_gpu(circuits)
+        sim = make_sim(20); plan = sim.plan(q.gates_from_circuit(circuits.random_layered(20, 2, 1)))   # placeholders for the common close below
+
     line = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
             try:
-                cpu, _ = reference_sample(n, 12.0)
+                cpu, _ = reference_full_depth(n)
             except Exception as e:   # keep the bench line even if the checker binary is missing
                 cpu = {"value": None, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
         line = {"metric": "gates_per_sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
@@ -330,7 +480,8 @@ def run_ours(args):
                            "parallelism": f"shard{world}" if world > 1 else "single"},
                 "effective_gate_GBps": len(circ) * 2 * (1 << n) * amp_bytes / (ms_per_step * 1e-3) / 1e9,
                 "wall_ms_per_step": wall_ms / args.steps, "exchange_ms_per_step": xch_ms / args.steps,
-                "roofline": roofline, "at_30q": at_30q, "cpu_baseline": cpu, "e2e": e2e,
+                "roofline": roofline, "at_30q": at_30q, "configs": configs, "e2e_full_30q": e2e_full, "reference_gpu": reference_gpu,
+                "parity": parity, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(pst["kernel_launches"]) * args.steps, "clocks": clocks,
                 "lib": q.lib.qsb_version().decode()}
         print(json.dumps(line))
@@ -352,6 +503,7 @@ def main():
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-30q", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the per-config lines, the full-state e2e and the reference-GPU run")
     ap.add_argument("--no-lazy-diag", type=int, default=0, help="planner A/B: 2 = lazy diagonals on")
     ap.add_argument("--trim", type=int, default=0, help="planner A/B: k+1 = trim tail rounds with < k gates (1 = off)")
     ap.add_argument("--cost-cap", type=int, default=0, help="fusion-depth sweep: SM cost cap per pass in gate units")

@@ -112,24 +112,30 @@ __device__ __forceinline__ uint64_t to_phys(uint64_t logical, const PermArg &P)
     return r;
 }
 
-/* export amplitudes [first, first+count) in logical order as fp64 (re, im) */
-template <typename R>
-__global__ void k_export(const R *st, double *out, uint64_t first, uint64_t count, PermArg P, uint64_t loc_mask)
+/* Export kernels: a block handles runs of 256 consecutive logical indices.  Only the low byte of the index varies
+ * inside a run, so the physical index is  hi(run) | lo(thread):  the per-thread part is mapped once per kernel, the
+ * per-run part is uniform (round 1 walked up to 40 permutation entries for EVERY amplitude). */
+__device__ __forceinline__ uint64_t to_phys_bits(uint64_t logical, const PermArg &P, int q0, int q1)
 {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    uint64_t i = to_phys(first + k, P) & loc_mask;
-    out[2 * k] = (double)st[Lay<R>::re(i)];
-    out[2 * k + 1] = (double)st[Lay<R>::im(i)];
+    uint64_t r = 0;
+    for (int q = q0; q < q1 && q < P.n; q++) r |= ((logical >> q) & 1ULL) << P.pos[q];
+    return r;
 }
-template <typename R>
-__global__ void k_export_native(const R *st, R *out, uint64_t first, uint64_t count, PermArg P, uint64_t loc_mask)
+/* export amplitudes [first, first+count) in logical order as O = double (fp64 re, im) or the state precision */
+template <typename R, typename O>
+__global__ void k_export(const R *st, O *out, uint64_t first, uint64_t count, PermArg P, uint64_t loc_mask)
 {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    uint64_t i = to_phys(first + k, P) & loc_mask;
-    out[2 * k] = st[Lay<R>::re(i)];
-    out[2 * k + 1] = st[Lay<R>::im(i)];
+    const uint64_t n_runs = (count + (first & 255) + 255) / 256;
+    const uint64_t lo = to_phys_bits(threadIdx.x, P, 0, 8);
+    for (uint64_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
+        const uint64_t base = (first & ~255ULL) + run * 256;       /* logical index of the run's first element */
+        const uint64_t idx = base + threadIdx.x;
+        if (idx < first || idx >= first + count) continue;
+        const uint64_t i = (to_phys_bits(base, P, 8, 64) | lo) & loc_mask;
+        const uint64_t k = idx - first;
+        out[2 * k] = (O)st[Lay<R>::re(i)];
+        out[2 * k + 1] = (O)st[Lay<R>::im(i)];
+    }
 }
 template <typename R>
 __global__ void k_import(R *st, const double *in, uint64_t first, uint64_t count, PermArg P, uint64_t loc_mask)
@@ -239,7 +245,7 @@ extern "C" int qsb_create(qsb_t **out, int num_qubits, const qsb_options_t *opt_
     s->n = num_qubits; s->prec = opt.precision; s->rank = opt.rank; s->world = opt.world_size;
     s->g = ilog2(opt.world_size);
     if (opt.device >= 0) { s->device = opt.device; } else { cudaGetDevice(&s->device); }
-    QSB_CUDA(cudaSetDevice(s->device));
+    if (cudaSetDevice(s->device) != cudaSuccess) { qsb_set_error("cannot select CUDA device %d", s->device); (void)cudaGetLastError(); delete s; return QSB_ERR_CUDA; }
     const int min_loc = tiled_min_local_bits(s->prec, &s->opt);
     if (s->g > 0 && num_qubits - s->g < min_loc + s->g) {
         qsb_set_error("%d qubits are too few to shard over %d ranks", num_qubits, s->world); delete s; return QSB_ERR_ARG;
@@ -252,12 +258,21 @@ extern "C" int qsb_create(qsb_t **out, int num_qubits, const qsb_options_t *opt_
         qsb_set_error("Malloc error: cudaMalloc of %zu bytes failed (%s)", s->state_bytes, cudaGetErrorString(e));
         (void)cudaGetLastError(); delete s; return QSB_ERR_NOMEM;
     }
-    QSB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    QSB_CUDA(cudaEventCreate(&s->ev0)); QSB_CUDA(cudaEventCreate(&s->ev1));
-    QSB_CUDA(cudaEventCreate(&s->evx0)); QSB_CUDA(cudaEventCreate(&s->evx1));
+    /* every failure from here on releases the handle and the state buffer */
+#define QSB_CREATE_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        qsb_set_error("%s in %s at line %d", cudaGetErrorString(e_), __FILE__, __LINE__); (void)cudaGetLastError(); qsb_destroy(s); return QSB_ERR_CUDA; } } while (0)
+    QSB_CREATE_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    QSB_CREATE_CUDA(cudaStreamCreateWithFlags(&s->dl_stream, cudaStreamNonBlocking));
+    QSB_CREATE_CUDA(cudaEventCreate(&s->ev0)); QSB_CREATE_CUDA(cudaEventCreate(&s->ev1));
+    QSB_CREATE_CUDA(cudaEventCreate(&s->evx0)); QSB_CREATE_CUDA(cudaEventCreate(&s->evx1));
+    for (int b = 0; b < 2; b++) {
+        QSB_CREATE_CUDA(cudaEventCreateWithFlags(&s->dl_filled[b], cudaEventDisableTiming));
+        QSB_CREATE_CUDA(cudaEventCreateWithFlags(&s->dl_copied[b], cudaEventDisableTiming));
+    }
     s->staging_bytes = (size_t)64 << 20;
-    QSB_CUDA(cudaMalloc(&s->staging, s->staging_bytes));
-    QSB_CUDA(cudaMalloc(&s->d_scratch, 1 << 20));
+    QSB_CREATE_CUDA(cudaMalloc(&s->staging, s->staging_bytes));
+    QSB_CREATE_CUDA(cudaMalloc(&s->d_scratch, 1 << 20));
+#undef QSB_CREATE_CUDA
     int rc = qsb_reset(s);
     if (rc) { qsb_destroy(s); return rc; }
     *out = s;
@@ -277,6 +292,8 @@ extern "C" void qsb_destroy(qsb_t *s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->evx0) cudaEventDestroy(s->evx0);
     if (s->evx1) cudaEventDestroy(s->evx1);
+    for (int b = 0; b < 2; b++) { if (s->dl_filled[b]) cudaEventDestroy(s->dl_filled[b]); if (s->dl_copied[b]) cudaEventDestroy(s->dl_copied[b]); }
+    if (s->dl_stream) cudaStreamDestroy(s->dl_stream);
     for (int i = 0; i < 4; i++) if (s->copy_stream[i]) cudaStreamDestroy(s->copy_stream[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -509,20 +526,42 @@ static bool range_is_local(const qsb_sim *s, uint64_t first, uint64_t count)
     return ((first + count - 1) & lmask) == want;
 }
 
-template <typename R>
-static int download_impl(qsb_sim *s, double *dst, uint64_t first, uint64_t count)
+/* Readout pipeline: the staging buffer is used as two halves; the export kernel fills one half on the compute
+ * stream while the copy engine drains the other to the host on dl_stream.  With a pinned destination the copy is
+ * a direct DMA at PCIe speed; pageable memory is staged by the runtime and is correspondingly slower. */
+template <typename F>
+static int pipelined_d2h(qsb_sim *s, char *dst, uint64_t count, size_t item_bytes, F fill /* (void *staging, uint64_t off, uint64_t c) -> int */)
 {
-    const uint64_t chunk = s->staging_bytes / 16;
-    PermArg P = perm_arg(s);
-    const uint64_t loc_mask = (1ULL << s->nloc) - 1;
-    for (uint64_t off = 0; off < count; off += chunk) {
-        uint64_t c = std::min(chunk, count - off);
-        k_export<R><<<(unsigned)((c + 255) / 256), 256, 0, s->stream>>>((const R *)s->state, (double *)s->staging, first + off, c, P, loc_mask);
-        QSB_CUDA(cudaGetLastError());
-        QSB_CUDA(cudaMemcpyAsync(dst + 2 * off, s->staging, c * 16, cudaMemcpyDeviceToHost, s->stream));
-        QSB_CUDA(cudaStreamSynchronize(s->stream));
+    const size_t half = s->staging_bytes / 2;
+    const uint64_t chunk = half / item_bytes;
+    bool used[2] = {false, false};
+    int b = 0;
+    for (uint64_t off = 0; off < count; off += chunk, b ^= 1) {
+        const uint64_t c = std::min(chunk, count - off);
+        char *stg = (char *)s->staging + (size_t)b * half;
+        if (used[b]) QSB_CUDA(cudaStreamWaitEvent(s->stream, s->dl_copied[b], 0));   /* this half has reached the host */
+        int rc = fill(stg, off, c);
+        if (rc) { cudaStreamSynchronize(s->dl_stream); return rc; }
+        QSB_CUDA(cudaEventRecord(s->dl_filled[b], s->stream));
+        QSB_CUDA(cudaStreamWaitEvent(s->dl_stream, s->dl_filled[b], 0));
+        QSB_CUDA(cudaMemcpyAsync(dst + off * item_bytes, stg, c * item_bytes, cudaMemcpyDeviceToHost, s->dl_stream));
+        QSB_CUDA(cudaEventRecord(s->dl_copied[b], s->dl_stream));
+        used[b] = true;
     }
+    QSB_CUDA(cudaStreamSynchronize(s->dl_stream));
+    QSB_CUDA(cudaStreamSynchronize(s->stream));
     return QSB_OK;
+}
+static inline unsigned export_grid(uint64_t c) { return (unsigned)std::min<uint64_t>((c + 511) / 256, 148 * 16); }
+
+template <typename R, typename O>
+static int download_impl(qsb_sim *s, O *dst, uint64_t first, uint64_t count, const PermArg &P, uint64_t loc_mask)
+{
+    return pipelined_d2h(s, (char *)dst, count, 2 * sizeof(O), [&](void *stg, uint64_t off, uint64_t c) -> int {
+        k_export<R, O><<<export_grid(c), 256, 0, s->stream>>>((const R *)s->state, (O *)stg, first + off, c, P, loc_mask);
+        QSB_CUDA(cudaGetLastError());
+        return QSB_OK;
+    });
 }
 
 extern "C" int qsb_download(qsb_t *s, double *re_im, uint64_t first, uint64_t count)
@@ -532,23 +571,10 @@ extern "C" int qsb_download(qsb_t *s, double *re_im, uint64_t first, uint64_t co
     if (rc) return rc;
     if (!range_is_local(s, first, count)) { qsb_set_error("range is not owned by rank %d", s->rank); return QSB_ERR_ARG; }
     QSB_CUDA(cudaSetDevice(s->device));
-    return s->prec == QSB_F32 ? download_impl<float>(s, re_im, first, count) : download_impl<double>(s, re_im, first, count);
-}
-
-template <typename R>
-static int download_native_impl(qsb_sim *s, R *dst, uint64_t first, uint64_t count)
-{
-    const uint64_t chunk = s->staging_bytes / (2 * sizeof(R));
-    PermArg P = perm_arg(s);
+    const PermArg P = perm_arg(s);
     const uint64_t loc_mask = (1ULL << s->nloc) - 1;
-    for (uint64_t off = 0; off < count; off += chunk) {
-        uint64_t c = std::min(chunk, count - off);
-        k_export_native<R><<<(unsigned)((c + 255) / 256), 256, 0, s->stream>>>((const R *)s->state, (R *)s->staging, first + off, c, P, loc_mask);
-        QSB_CUDA(cudaGetLastError());
-        QSB_CUDA(cudaMemcpyAsync(dst + 2 * off, s->staging, c * 2 * sizeof(R), cudaMemcpyDeviceToHost, s->stream));
-        QSB_CUDA(cudaStreamSynchronize(s->stream));
-    }
-    return QSB_OK;
+    return s->prec == QSB_F32 ? download_impl<float, double>(s, re_im, first, count, P, loc_mask)
+                              : download_impl<double, double>(s, re_im, first, count, P, loc_mask);
 }
 
 extern "C" int qsb_download_native(qsb_t *s, void *dst, uint64_t first, uint64_t count)
@@ -558,8 +584,10 @@ extern "C" int qsb_download_native(qsb_t *s, void *dst, uint64_t first, uint64_t
     if (rc) return rc;
     if (!range_is_local(s, first, count)) { qsb_set_error("range is not owned by rank %d", s->rank); return QSB_ERR_ARG; }
     QSB_CUDA(cudaSetDevice(s->device));
-    return s->prec == QSB_F32 ? download_native_impl<float>(s, (float *)dst, first, count)
-                              : download_native_impl<double>(s, (double *)dst, first, count);
+    const PermArg P = perm_arg(s);
+    const uint64_t loc_mask = (1ULL << s->nloc) - 1;
+    return s->prec == QSB_F32 ? download_impl<float, float>(s, (float *)dst, first, count, P, loc_mask)
+                              : download_impl<double, double>(s, (double *)dst, first, count, P, loc_mask);
 }
 
 extern "C" int qsb_get_layout(const qsb_t *s, int8_t *perm64, int *nloc)
@@ -579,16 +607,8 @@ extern "C" int qsb_download_physical(qsb_t *s, double *re_im, uint64_t first, ui
     PermArg P; memset(&P, 0, sizeof P);
     P.n = s->nloc;
     for (int q = 0; q < s->nloc; q++) P.pos[q] = (int8_t)q;   /* identity: physical order */
-    const uint64_t chunk = s->staging_bytes / 16;
-    for (uint64_t off = 0; off < count; off += chunk) {
-        uint64_t c = std::min(chunk, count - off);
-        if (s->prec == QSB_F32) k_export<float><<<(unsigned)((c + 255) / 256), 256, 0, s->stream>>>((const float *)s->state, (double *)s->staging, first + off, c, P, nl - 1);
-        else k_export<double><<<(unsigned)((c + 255) / 256), 256, 0, s->stream>>>((const double *)s->state, (double *)s->staging, first + off, c, P, nl - 1);
-        QSB_CUDA(cudaGetLastError());
-        QSB_CUDA(cudaMemcpyAsync(re_im + 2 * off, s->staging, c * 16, cudaMemcpyDeviceToHost, s->stream));
-        QSB_CUDA(cudaStreamSynchronize(s->stream));
-    }
-    return QSB_OK;
+    return s->prec == QSB_F32 ? download_impl<float, double>(s, re_im, first, count, P, nl - 1)
+                              : download_impl<double, double>(s, re_im, first, count, P, nl - 1);
 }
 
 extern "C" int qsb_upload(qsb_t *s, const double *re_im, uint64_t first, uint64_t count)

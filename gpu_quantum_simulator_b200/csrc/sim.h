@@ -19,7 +19,9 @@ struct qsb_sim {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};   /* pipelined exchange: peer copies on the copy engines */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
-    void *staging = nullptr; /* device staging for readout                      */
+    void *staging = nullptr; /* device staging for readout (two halves, double-buffered by the downloads) */
+    cudaStream_t dl_stream = nullptr;                        /* device -> host copies of the readout pipeline */
+    cudaEvent_t dl_filled[2] = {nullptr, nullptr}, dl_copied[2] = {nullptr, nullptr};
     size_t staging_bytes = 0;
     void *d_scratch = nullptr; /* small device scratch (reductions)             */
     qsb_run_stats_t last{};
