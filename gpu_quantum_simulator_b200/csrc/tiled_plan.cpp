@@ -130,6 +130,9 @@ namespace {
 /* keeps a pass descriptor below QSB_BLOB_LARGE: in the worst case (every op on the same vector bit)
  * each op occupies a whole group, 160 bytes in f32 and 288 bytes in f64 */
 inline int max_pass_ops(bool f32) { return f32 ? 120 : 72; }
+#ifndef QSB_FUSED_OP_DIV
+#define QSB_FUSED_OP_DIV 1   /* fused-exchange passes: op budget = max_pass_ops / this (round 1: 3) */
+#endif
 const int MAX_PASS_ROUNDS = 32;
 const int QSB_PLAN_OVERFLOW = -100;   /* internal: serialise() could not fit the pass into QSB_BLOB_LARGE */
 
@@ -1473,10 +1476,10 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             for (int q = 0; q < n; q++) if ((forced >> perm.pos[q]) & 1) { if (!((S0 >> q) & 1)) S0 |= 1ULL << q; }
             n0 += popc(forced);   /* forced positions are >= a: each takes a slot, qubit or padding */
             /* a fused-exchange pass also carries the peer table as a kernel parameter: keep its descriptor in the medium class */
-            collect(S0, n0, mine, mine_idx, S, fuse ? max_pass_ops(M.f32) / 3 : 0);
+            collect(S0, n0, mine, mine_idx, S, fuse ? max_pass_ops(M.f32) / QSB_FUSED_OP_DIV : 0);
             int rc = emit_pass(S, forced, pos_map, mine, mine_idx, true, fuse);
             if (rc == QSB_PLAN_OVERFLOW) {
-                strict_count = true; collect(S0, n0, mine, mine_idx, S, fuse ? max_pass_ops(M.f32) / 3 : 0); strict_count = false;
+                strict_count = true; collect(S0, n0, mine, mine_idx, S, fuse ? max_pass_ops(M.f32) / QSB_FUSED_OP_DIV : 0); strict_count = false;
                 rc = emit_pass(S, forced, pos_map, mine, mine_idx, true, fuse);
             }
             if (rc) return rc == QSB_PLAN_OVERFLOW ? QSB_ERR_ARG : rc;
