@@ -135,6 +135,11 @@ struct DevPass {
     uint64_t n_tiles;
     uint32_t rounds_off16;      /* DevRound array, 16-byte units from the blob start */
     uint32_t blob_bytes;
+    /* Fused exchange with victims OUTSIDE the tile (round 2): outer index bit xo_pos[k] of the source does not keep
+     * its place -- it selects bit xo_rank[k] of the DESTINATION rank (the whole tile of a CTA then goes to one peer),
+     * and the writer's own rank bit sits at that local position of the destination (part of dst_fixed). */
+    uint32_t n_xo;
+    uint8_t xo_pos[8], xo_rank[8];
 };
 
 template <int BYTES> struct PassBlob { uint4 q[BYTES / 16]; };
@@ -252,7 +257,10 @@ struct GPass {
     uint64_t ld_vec[QSB_NV];   /* local BYTE offset of vector v                                       */
     uint64_t st_vec[QSB_NV];
     uint64_t st_fixed;         /* constant part of the scatter offset (fused exchange: the writer's rank
-                                  on the top local positions)                                         */
+                                  bits on the local positions the victims leave)                      */
+    uint64_t xo_mask;          /* outer bits that leave the local index in a fused exchange (DevPass::xo_pos) */
+    uint32_t n_xo, xo_pad;
+    uint8_t xo_pos[8], xo_rank[8];
     /* Scatter offsets are  local byte offset | destination-rank contribution << QSB_RANK_SHIFT.  The rank
      * field is non-zero only in a fused-exchange pass (peer stores), whose kernel variant adds the fields
      * up and indexes the peer-pointer table with the result. */

@@ -485,6 +485,11 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     if (P.flags & QSB_PASS_SYNC_SCATTER) __syncthreads();
     {
         uint64_t off = outer * AMP + P.st_fixed, xoff = 0;
+        if (PEER) {   /* victims outside the tile: their outer bits leave the local index and name bits of the destination rank (uniform) */
+            off = (outer & ~P.xo_mask) * AMP + P.st_fixed;
+            const int nx = (int)P.n_xo;
+            for (int k = 0; k < nx; k++) off += ((outer >> P.xo_pos[k]) & 1ULL) << (QSB_RANK_SHIFT + P.xo_rank[k]);
+        }
 #pragma unroll
         for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) off += P.st_thr[j];
 #pragma unroll

@@ -140,7 +140,7 @@ struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
     bool f32, lazy_diag, defer_diag, sink_phases, tile_search, hform;
     int trim_thin, cost_cap;
-    bool fused_exchange, force_top;
+    bool fused_exchange, force_top, fused_direct;
 };
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
@@ -396,13 +396,22 @@ struct PassBuilder {
     /* choose the tile from the set of resident logical qubits (+ positions that must be resident);
      * pos_map, if given, relocates physical positions inside the tile (in-tile qubit permutation:
      * free, because the tile is gathered and scattered anyway). */
-    void set_tile(uint64_t resident, uint64_t forced_pos = 0, const int8_t *pos_map = nullptr, bool fuse_exchange = false)
+    void set_tile(uint64_t resident, uint64_t forced_pos = 0, const int8_t *pos_map = nullptr, bool fuse_exchange = false,
+                  const int *victim_pos = nullptr)
     {
-        /* fuse_exchange: the pass also performs the global <-> local qubit exchange -- after the in-tile
-         * permutation the top g local positions trade places with the rank bits, i.e. every amplitude is
-         * scattered straight into the shard of the rank named by its victim bits (peer memory over NVLink),
-         * at the local address whose top g bits are the WRITER's rank. */
-        auto exch = [&](int p) { return (fuse_exchange && p >= M.nloc - M.g && p < M.nloc) ? p + M.g : p; };
+        /* fuse_exchange: the pass also performs the global <-> local qubit exchange: every amplitude is scattered
+         * straight into the shard of the rank named by its victim bits (peer memory over NVLink).
+         *   round 1 flavour (victim_pos == null): an in-tile permutation first moves the victims to the top g local
+         *     positions, which then trade places with the rank bits; the writer's rank lands on the top positions.
+         *   direct flavour (victim_pos[k] = local position whose qubit becomes rank bit k): position victim_pos[k]
+         *     trades places with rank bit k, wherever it is.  A victim inside the tile is a tile bit whose destination
+         *     is a rank bit; a victim OUTSIDE the tile is an outer bit, i.e. constant per CTA, so the whole tile goes to
+         *     one peer and the pass needs no tile slot for the exchange at all. */
+        auto exch = [&](int p) {
+            if (!fuse_exchange) return p;
+            if (victim_pos) { for (int k = 0; k < M.g; k++) if (victim_pos[k] == p) return M.nloc + k; return p; }
+            return (p >= M.nloc - M.g && p < M.nloc) ? p + M.g : p;
+        };
         uint64_t posmask = forced_pos;
         for (int q = 0; q < M.n; q++) if ((resident >> q) & 1) posmask |= 1ULL << perm.pos[q];
         for (int p = 0; p < M.a; p++) posmask |= 1ULL << p;              /* contiguous low segment */
@@ -435,8 +444,17 @@ struct PassBuilder {
         hp.hdr.out_of_place = 0;
         hp.fused_swap = fuse_exchange;
         if (fuse_exchange) {
-            hp.hdr.dst_fixed = (uint64_t)M.rank << (M.nloc - M.g);   /* the old rank bits land on the top local positions */
             hp.hdr.out_of_place = 1;
+            if (!victim_pos) hp.hdr.dst_fixed = (uint64_t)M.rank << (M.nloc - M.g);   /* the old rank bits land on the top local positions */
+            else {
+                hp.hdr.dst_fixed = 0;
+                for (int k = 0; k < M.g; k++) {
+                    hp.hdr.dst_fixed |= (uint64_t)((M.rank >> k) & 1) << victim_pos[k];   /* the writer's rank bit k moves in */
+                    if (!((posmask >> victim_pos[k]) & 1)) {                              /* victim outside the tile */
+                        hp.hdr.xo_pos[hp.hdr.n_xo] = (uint8_t)victim_pos[k]; hp.hdr.xo_rank[hp.hdr.n_xo] = (uint8_t)k; hp.hdr.n_xo++;
+                    }
+                }
+            }
         }
     }
 
@@ -1011,6 +1029,8 @@ struct PassBuilder {
             gp.st_vec[v] = hp.fused_swap ? enc_dst(t) : (t & loc_mask) * AMP;
         }
         gp.st_fixed = hp.fused_swap ? (hp.hdr.dst_fixed & loc_mask) * AMP : 0;
+        gp.n_xo = hp.hdr.n_xo;
+        for (uint32_t k = 0; k < hp.hdr.n_xo; k++) { gp.xo_pos[k] = hp.hdr.xo_pos[k]; gp.xo_rank[k] = hp.hdr.xo_rank[k]; gp.xo_mask |= 1ULL << hp.hdr.xo_pos[k]; }
         if (nrounds == 1 && !hp.hdr.out_of_place) {   /* a thread's store set differs from its load set: barrier before the scatter */
             bool moved = false;
             for (int j = 0; j < QSB_TB; j++) moved |= gp.ld_thr[j] != gp.st_thr[j];
@@ -1293,7 +1313,9 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.hform = !(opt && opt->reserved[4] == 3);       /* reserved[4] = 3: no Hadamard-like slot form S_UNIT_H (A/B runs) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.force_top = g > 0 && opt && opt->reserved[5] == 3;        /* reserved[5] = 3: NCCL-style plan executed as a pipelined exchange */
-    M.fused_exchange = g > 0 && opt && opt->reserved[5] == 1;   /* reserved[5] = 1: exchanges fused into the preceding pass (peer stores) */
+    M.fused_exchange = g > 0 && opt && (opt->reserved[5] == 1 || opt->reserved[5] == 4);   /* reserved[5] = 1 / 4: exchanges fused into a pass (peer stores) */
+    M.fused_direct = g > 0 && opt && opt->reserved[5] == 1;     /* 1: victims trade places with the rank bits wherever they are (round 2); 4: round 1
+                                                                   flavour, victims moved to the top local positions first (A/B) */
     M.tile_search = !(opt && opt->reserved[6] == 2);   /* reserved[6] = 2: first-come tile choice (A/B runs) */
     M.sink_phases = !(opt && opt->reserved[6] == 1);   /* reserved[6] = 1: keep thread-level phases in the round that accepted them (A/B) */
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
@@ -1384,9 +1406,9 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         return S;
     };
     auto emit_pass = [&](uint64_t S, uint64_t forced_pos, const int8_t *pos_map, const std::vector<COp> &mine,
-                         const std::vector<size_t> &mine_idx, bool allow_empty, bool fuse_exchange = false) -> int {
+                         const std::vector<size_t> &mine_idx, bool allow_empty, bool fuse_exchange = false, const int *victim_pos = nullptr) -> int {
         PassBuilder pb(M, perm);
-        pb.set_tile(S, forced_pos, pos_map, fuse_exchange);
+        pb.set_tile(S, forced_pos, pos_map, fuse_exchange, victim_pos);
         std::vector<char> used;
         int rc = pb.build_rounds(mine, used, !allow_empty && mine_idx.size() < left);
         if (rc) return rc;
@@ -1413,9 +1435,9 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             if (S2 != S) collect(S2, M.T, mine, mine_idx, S);
         }
 
-        bool want_swap = false;
-        if (g > 0) {
-            int nd = 0; for (const COp &o : mine) if (o.target >= 0) nd++;
+        /* is the schedule about to starve behind a gate on a global qubit?  (few gates left that run without an exchange) */
+        auto starving = [&](const std::vector<COp> &avail) {
+            int nd = 0; for (const COp &o : avail) if (o.target >= 0) nd++;
             bool blocked_global = false;
             size_t seen = 0;
             for (size_t i = first_open; i < N && seen < (size_t)8 * n; i++) {
@@ -1423,7 +1445,55 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                 seen++;
                 if (cops[i].target >= 0 && perm.pos[cops[i].target] >= nloc) { blocked_global = true; break; }
             }
-            if (blocked_global && nd < SWAP_MIN_OPS) want_swap = true;
+            return blocked_global && nd < SWAP_MIN_OPS;
+        };
+        bool want_swap = g > 0 && starving(mine);
+        if (M.fused_direct) {
+            /* Direct fused exchange (round 2): victims trade places with the rank bits wherever they are, so the
+             * exchange needs no tile slot and ANY pass can carry it.  Take the last pass that still has a full load of
+             * gates: if the schedule would starve once this pass is through, this pass scatters into the peers. */
+            bool fuse_now = want_swap;
+            for (size_t k : mine_idx) done[k] = 1;            /* look past this pass */
+            if (!fuse_now && !mine.empty()) {
+                std::vector<COp> m2; std::vector<size_t> i2; uint64_t S2 = 0;
+                collect(lowS, M.a, m2, i2, S2);
+                fuse_now = starving(m2);
+            }
+            int victim_pos[8]; std::vector<int> cand;
+            if (fuse_now) {
+                std::vector<size_t> next_use(n, N + 1);
+                std::vector<char> seenq(n, 0); int found = 0;
+                for (size_t i = first_open; i < N && found < n; i++) {
+                    if (done[i] || cops[i].target < 0) continue;
+                    const int qq = cops[i].target;
+                    if (!seenq[qq]) { seenq[qq] = 1; next_use[qq] = i; found++; }
+                }
+                for (int qq = 0; qq < n; qq++) if (perm.pos[qq] >= M.a && perm.pos[qq] < nloc) cand.push_back(qq);
+                std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) {
+                    if (next_use[x] != next_use[y]) return next_use[x] > next_use[y];
+                    return perm.pos[x] > perm.pos[y];
+                });
+            }
+            for (size_t k : mine_idx) done[k] = 0;
+            if (fuse_now) {
+                if ((int)cand.size() < g) { qsb_set_error("not enough local qubits to exchange"); return QSB_ERR_ARG; }
+                for (int k = 0; k < g; k++) victim_pos[k] = perm.pos[cand[k]];
+                int rc = emit_pass(S, 0, nullptr, mine, mine_idx, true, true, victim_pos);
+                if (rc == QSB_PLAN_OVERFLOW) {
+                    strict_count = true; collect(lowS, M.a, mine, mine_idx, S); strict_count = false;
+                    rc = emit_pass(S, 0, nullptr, mine, mine_idx, true, true, victim_pos);
+                }
+                if (rc) return rc == QSB_PLAN_OVERFLOW ? QSB_ERR_ARG : rc;
+                for (int qq = 0; qq < n; qq++) {          /* position victim_pos[k] <-> rank bit k */
+                    const int pp = perm.pos[qq];
+                    for (int k = 0; k < g; k++) {
+                        if (pp == victim_pos[k]) perm.pos[qq] = (int8_t)(nloc + k);
+                        else if (pp == nloc + k) perm.pos[qq] = (int8_t)victim_pos[k];
+                    }
+                }
+                continue;
+            }
+            want_swap = false;
         }
         if (!want_swap) {
             if (mine.empty()) { qsb_set_error("scheduler made no progress (gate on a non-local qubit?)"); return QSB_ERR_ARG; }

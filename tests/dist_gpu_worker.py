@@ -58,8 +58,8 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     worst = 0.0
     # exchange flavours (qsb_options_t.reserved[5]): 0 = default by world size, 1 = fused peer scatter, 2 = NCCL all-to-all,
-    # 3 = pipelined copy-engine exchange
-    configs = ((q.F32, 1e-5, 0), (q.F64, 1e-12, 0), (q.F32, 1e-5, 1), (q.F64, 1e-12, 1), (q.F32, 1e-5, 2), (q.F32, 1e-5, 3), (q.F64, 1e-12, 3))
+    # 3 = pipelined copy-engine exchange, 4 = round-1 fused flavour (victims moved to the top local positions first)
+    configs = ((q.F32, 1e-5, 0), (q.F64, 1e-12, 0), (q.F32, 1e-5, 1), (q.F64, 1e-12, 1), (q.F32, 1e-5, 2), (q.F32, 1e-5, 3), (q.F64, 1e-12, 3), (q.F32, 1e-5, 4))
     sizes = ((22, 8, 7), (23, 5, 8))
     if os.environ.get("QSB_DIST_QUICK"):       # readout-only run: default exchange flavour, one small circuit per precision
         configs, sizes = configs[:2], ((22, 5, 7),)

@@ -193,7 +193,8 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
         }
         /* scatter */
         for (int tid = 0; tid < QSB_THREADS; tid++) {
-            uint64_t off = outer * AMP + P.st_fixed, xoff = 0;
+            uint64_t off = (outer & ~P.xo_mask) * AMP + P.st_fixed, xoff = 0;
+            for (uint32_t k = 0; k < P.n_xo; k++) off += ((outer >> P.xo_pos[k]) & 1ULL) << (QSB_RANK_SHIFT + P.xo_rank[k]);
             for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) off += P.st_thr[j];
             for (int b = 0; b < QSB_NVB; b++) if ((xm[tid] >> b) & 1) xoff ^= P.st_vec[1 << b];
             for (int v = 0; v < QSB_NV; v++) {

@@ -158,6 +158,11 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
             if (rd == nr - 1) {
                 for (int tid = 0; tid < QSB_THREADS; tid++) {
                     uint64_t d = outer | hp.hdr.dst_fixed;
+                    for (uint32_t k = 0; k < hp.hdr.n_xo; k++) {   /* victims outside the tile: the outer bit names a bit of the destination rank */
+                        const uint64_t bit = (outer >> hp.hdr.xo_pos[k]) & 1ULL;
+                        d = (d & ~(1ULL << hp.hdr.xo_pos[k])) | hp.hdr.dst_fixed & (1ULL << hp.hdr.xo_pos[k]);
+                        d |= bit << (nloc + hp.hdr.xo_rank[k]);
+                    }
                     for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) d |= hp.hdr.dst_thr[j];
                     for (int v = 0; v < QSB_NV; v++) {
                         uint64_t gi = d;

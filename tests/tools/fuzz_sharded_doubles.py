@@ -8,6 +8,8 @@ import numpy as np
 import helpers
 import gpu_quantum_simulator_b200 as q
 from gpu_quantum_simulator_b200 import circuits
+BLOB = os.environ.get("QSB_FUZZ_BLOB") == "1"   # interpret the device encoding (what the kernel reads) instead of the logical tables
+helpers.hostcheck_use_blob(BLOB)
 t_end = time.time() + float(sys.argv[1]); seed = int(sys.argv[2]); runs = bad = 0
 while time.time() < t_end:
     rng = np.random.RandomState(seed)
@@ -24,7 +26,7 @@ while time.time() < t_end:
     try:
         got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, prec, swap_min_ops=smo, fused=fused)
         want = helpers.oracle_run_circuit(circ, n)
-        err = float(np.max(np.abs(got - want))); ok = err < 1e-11 and rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+        err = float(np.max(np.abs(got - want))); ok = err < (3e-6 if BLOB and prec == 32 else 1e-11) and rep["bad_slots"] == 0 and rep["max_conflict"] == 1
     except Exception as e:
         ok, err, rep = False, repr(e), {}
     runs += 1
