@@ -8,7 +8,7 @@ _SUFFIX = os.environ.get("QSB_LIB_SUFFIX", "")
 LIB_PATH = os.path.join(_HERE, "csrc", "_build" + _SUFFIX, "libqsim_b200.so") if _SUFFIX else os.path.join(_HERE, "libqsim_b200.so")
 
 F32, F64 = 32, 64
-MODE_TILED, MODE_SWEEP = 0, 1
+MODE_TILED, MODE_SWEEP, MODE_DENSE = 0, 1, 2
 
 
 class QsbError(RuntimeError):

@@ -340,6 +340,13 @@ static int build_plan(int n, int prec, int g, int nloc, int rank, const qsb_opti
         uint64_t b = 0;
         for (auto &c : p->cops) b += (c.kind == C_X && c.ctrl) ? pass_bytes / 2 : pass_bytes; /* a bare CX touches half the state */
         p->stats.bytes_moved = b;
+    } else if (p->mode == QSB_MODE_DENSE) {
+        if (g > 0) { qsb_set_error("DENSE mode is single-GPU only"); delete p; return QSB_ERR_ARG; }
+        rc = dense_fuse(p->cops, p->gphase, n, opt->tile_bits > 0 ? opt->tile_bits : 4, p->dense);
+        if (rc) { delete p; return rc; }
+        p->stats.device_ops = p->dense.size();
+        p->stats.passes = p->stats.kernel_launches = (uint32_t)p->dense.size();
+        p->stats.bytes_moved = p->dense.size() * pass_bytes;
     } else {
         rc = tiled_plan_build(n, prec, g, nloc, rank, opt, start, p->cops, p->gphase, with_device, &p->tiled, &p->stats);
         if (rc) { delete p; return rc; }
@@ -464,6 +471,7 @@ extern "C" int qsb_execute(qsb_t *s, qsb_plan_t *p)
         else tiled_plan_end_perm(p->tiled, &s->perm);
     }
     else if (p->mode == QSB_MODE_SWEEP) rc = (s->prec == QSB_F32) ? sweep_execute<float>(s, p) : sweep_execute<double>(s, p);
+    else if (p->mode == QSB_MODE_DENSE) rc = dense_execute(s, p->dense);
     else rc = tiled_execute(s, p->tiled);
     if (rc) { cudaStreamSynchronize(s->stream); (void)cudaGetLastError(); return rc; }
     QSB_CUDA(cudaEventRecord(s->ev1, s->stream));

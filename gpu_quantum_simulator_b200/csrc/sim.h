@@ -1,6 +1,7 @@
 /* sim.h -- host-side objects behind the opaque handles of qsim_b200.h. */
 #pragma once
 #include "common.cuh"
+#include "dense.h"
 
 struct TiledPlan; /* tiled.h */
 
@@ -38,6 +39,7 @@ struct qsb_plan {
     std::vector<COp> cops;   /* canonical ops in source order (sweep mode executes these) */
     double gphase[2] = {1.0, 0.0}; /* global scalar factored out of diagonal gates */
     TiledPlan *tiled = nullptr;
+    std::vector<DenseBlock> dense;   /* QSB_MODE_DENSE (experiment): one dense k-qubit unitary per sweep */
     qsb_run_stats_t stats{};
     /* qsb_options_t.use_graph: the pass launches of this plan captured once, replayed by every later qsb_execute */
     cudaGraphExec_t graph_exec = nullptr;

@@ -155,11 +155,13 @@ extern "C" int qsb_comm_init(qsb_t *s, const void *id128)
             (void)cudaGetLastError();
         }
     }
-    /* exchange flavour of the plans made from now on: 1 = fused peer scatter, 3 = pipelined copy-engine exchange,
-     * 2 = plain NCCL all-to-all (also the fallback when the peer shards cannot be mapped).  Measured on 34 q
-     * (DESIGN.md section 6): pipelined wins with one peer (2 GPUs: 1585 vs 1640 ms), the fused scatter with
-     * several (4 GPUs: 847 vs 977 ms, 8 GPUs: 482 vs 585 ms) -- the copy engines do not spread over 7 peers. */
-    if (s->peers_ok && s->opt.reserved[5] == 0) s->opt.reserved[5] = s->world <= 2 ? 3 : 1;
+    /* exchange flavour of the plans made from now on: 1 = fused peer scatter (direct: the victims trade places with the
+     * rank bits wherever they are), 4 = the round-1 fused flavour (victims moved to the top local positions first),
+     * 3 = pipelined copy-engine exchange, 2 = plain NCCL all-to-all (also the fallback when the peer shards cannot be
+     * mapped).  Measured on 34 q: round 1 preferred the pipelined exchange with one peer
+     * (2 GPUs: 1585 vs 1640 ms); the direct fused exchange needs no extra pass and wins there too (round 2, same box:
+     * 1275 ms vs 1355 pipelined vs 1347 round-1 fused), so it is the default at every world size. */
+    if (s->peers_ok && s->opt.reserved[5] == 0) s->opt.reserved[5] = 1;
     if (!s->peers_ok) s->opt.reserved[5] = 2;
     return QSB_OK;
 }

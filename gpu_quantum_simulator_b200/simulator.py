@@ -67,7 +67,7 @@ def gates_from_circuit(circ):
     return (Gate * len(out)).from_buffer(arr) if out else (Gate * 0)()
 
 
-def _options(precision, mode, low_bits, rank, world_size, device, reserved=None, use_graph=False):
+def _options(precision, mode, low_bits, rank, world_size, device, reserved=None, use_graph=False, dense_k=0):
     """reserved: planner tuning knobs (qsb_options_t.reserved): [0] min gates before a qubit exchange,
     [1] 2 = lazy diagonals on, [2] k+1 = trim tail rounds with < k gates (1 = off), [3] fusion-depth cost cap."""
     o = Options()
@@ -81,13 +81,14 @@ def _options(precision, mode, low_bits, rank, world_size, device, reserved=None,
     o.world_size = world_size
     o.device = device
     o.use_graph = 1 if use_graph else 0
+    o.tile_bits = dense_k          # MODE_DENSE: fusion width k (2..5)
     return o
 
 
-def plan_dry_run(num_qubits, gates, precision=F32, low_bits=0, world_size=1, rank=0, reserved=None):
+def plan_dry_run(num_qubits, gates, precision=F32, low_bits=0, world_size=1, rank=0, reserved=None, mode=MODE_TILED, dense_k=0):
     """Host-only scheduling statistics (no GPU needed)."""
     arr, n = _gate_array(gates)
-    o = _options(precision, MODE_TILED, low_bits, rank, world_size, -1, reserved)
+    o = _options(precision, mode, low_bits, rank, world_size, -1, reserved, False, dense_k)
     st = RunStats()
     check(lib.qsb_plan_dry_run(num_qubits, C.byref(o), arr, n, C.byref(st)))
     return st.as_dict()
@@ -112,9 +113,9 @@ class Plan:
 
 class Simulator:
     def __init__(self, num_qubits, precision=F32, mode=MODE_TILED, low_bits=0, rank=0, world_size=1, device=-1, reserved=None,
-                 use_graph=False):
+                 use_graph=False, dense_k=0):
         self._h = C.c_void_p()
-        o = _options(precision, mode, low_bits, rank, world_size, device, reserved, use_graph)
+        o = _options(precision, mode, low_bits, rank, world_size, device, reserved, use_graph, dense_k)
         check(lib.qsb_create(C.byref(self._h), num_qubits, C.byref(o)))
         self.num_qubits, self.precision = num_qubits, precision
         self.rank, self.world_size = rank, world_size

@@ -60,13 +60,19 @@ typedef struct qsb_gate {
 /* Execution modes.  SWEEP = one full pass over the state per gate, the
  * reference's own schedule (naive.cu:163-189) kept as a cross-check and as the
  * "unfused" baseline; TILED = the fused tile-pass schedule (the product). */
-enum { QSB_MODE_TILED = 0, QSB_MODE_SWEEP = 1 };
+enum { QSB_MODE_TILED = 0, QSB_MODE_SWEEP = 1,
+       /* DENSE = experiment of BASELINE.json configuration 4: gates merged greedily into dense k-qubit unitaries
+        * (k = tile_bits, 2..5; the reference's 4x4 accumulator of quantum_simulator_4x4.cu:327-501 generalised), one
+        * sweep per block like kernel_gate_4 (:109-146).  Single GPU.  Measured slower than TILED at every k
+        * (DESIGN.md section 3.1); kept for the k sweep and the tensor-core check, not as a product path. */
+       QSB_MODE_DENSE = 2 };
 
 typedef struct qsb_options {
     int32_t precision;    /* QSB_F32 | QSB_F64 (state dtype on the device)    */
     int32_t device;       /* CUDA ordinal, -1 = current                       */
     int32_t mode;         /* QSB_MODE_*                                       */
-    int32_t tile_bits;    /* reserved: the tile is 2^12 (f32) / 2^11 (f64) amplitudes (build-time, csrc/tiled.h) */
+    int32_t tile_bits;    /* TILED: reserved, the tile is 2^12 (f32) / 2^11 (f64) amplitudes (build-time, csrc/tiled.h);
+                           * DENSE: the fusion width k, 2..5 (0 = 4) */
     int32_t low_bits;     /* contiguous low index bits every tile keeps, 0 = default (4 f32 / 3 f64) */
     int32_t rank;         /* this process' shard, 0..world-1                  */
     int32_t world_size;   /* power of two; state sharded on the top log2(world) qubits */

@@ -10,7 +10,7 @@ import pytest
 
 import helpers
 import gpu_quantum_simulator_b200 as q
-from gpu_quantum_simulator_b200 import circuits, F32, F64, MODE_TILED, MODE_SWEEP
+from gpu_quantum_simulator_b200 import circuits, F32, F64, MODE_TILED, MODE_SWEEP, MODE_DENSE
 
 pytestmark = pytest.mark.gpu
 
@@ -346,3 +346,19 @@ def test_a_plan_is_refused_from_another_layout():
         assert np.array_equal(s.state(), first)
         s.apply(gates)                                       # plans from the current layout: always fine
         plan.close()
+
+
+@pytest.mark.parametrize("precision", [F32, F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
+def test_dense_block_mode_vs_oracle(k, precision):
+    """QSB_MODE_DENSE (the k = 2..5 fusion experiment of BASELINE.json configuration 4): greedy dense k-qubit blocks,
+    one sweep per block, must give the oracle's state -- otherwise the k sweep in profiles/ compares nothing."""
+    for circ, n in ((circuits.random_layered(18, depth=6, seed=40 + k), 18), (circuits.random_superset(16, 200, 50 + k), 16),
+                    (circuits.qft(15), 15)):
+        if k < 3 and any(name == "ccx" for name, _, _ in circ):
+            circ = [g for g in circ if g[0] != "ccx"]          # a Toffoli is wider than k = 2
+        want = helpers.oracle_run_circuit(circ, n)
+        with q.Simulator(n, precision=precision, mode=MODE_DENSE, dense_k=k) as s:
+            st = s.apply(q.gates_from_circuit(circ))
+            assert np.max(np.abs(s.state() - want)) <= TOL[precision]
+            assert st["passes"] < len(circ)
