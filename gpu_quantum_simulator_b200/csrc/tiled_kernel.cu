@@ -24,8 +24,6 @@
  * Reference kernels replaced: kernel_gate / kernel_gate_2 (naive.cu:72-95),
  * kernel_cnot (naive.cu:97-122), kernel_gate_4 (4x4.cu:109-146).
  */
-#include <algorithm>
-#include <stdlib.h>
 #include "sim.h"
 #include "tiled.h"
 
@@ -265,24 +263,11 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
     if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;
 }
 
-/* tile id -> outer index bits: the id's bits are dealt to the runs of consecutive outer positions (uniform datapath) */
-__device__ __forceinline__ uint64_t tile_outer(const GPass &P, uint64_t tile)
-{
-    uint64_t outer = 0;
-    const int nr = (int)P.n_runs;
-    for (int r = 0; r < nr; r++) {
-        const int len = P.run_len[r];
-        outer |= (tile & ((1ULL << len) - 1)) << P.run_start[r];
-        tile >>= len;
-    }
-    return outer;
-}
-
 /* PEER: the scatter of a fused-exchange pass -- every amplitude goes straight into the shard of the rank
  * named by its victim bits (peer memory over NVLink), so the qubit exchange costs no extra sweep. */
 template <typename R, int BLOB, bool PEER>
 __global__ void __launch_bounds__(QSB_THREADS, QSB_CTAS_PER_SM)
-k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst, const __grid_constant__ PeerTab peers, uint64_t tile_base, uint64_t tile_end)
+k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst, const __grid_constant__ PeerTab peers, uint32_t tile_base)
 {
     typedef VT<R> T; typedef typename T::V V; typedef typename T::S S;
     static_assert(QSB_NVB == 4, "the interpreter is written for 4 vector bits");
@@ -292,24 +277,16 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     const uint32_t tid = threadIdx.x;
     const uint64_t AMP = sizeof(R) * 2;
 
-    const int n_rounds = (int)P.n_rounds;
-    /* thread part of the gather / scatter offsets.  Recomputed where needed (a dozen predicated adds) rather than
-     * kept across the tile loop: the f32 kernel sits at the 128-register limit of four CTAs per SM. */
-    auto thread_ld_off = [&]() { uint64_t o = 0;
-#pragma unroll
-        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) o += P.ld_thr[j];
-        return o; };
-    /* staging slots of this thread in the exchange buffer (prefetched tile): vector v at v * THREADS * 16 + tid * 16 --
-     * written by the thread's own cp.async and read back by the same thread, 128-bit and bank-conflict free */
-
-    /* PERSISTENT tile loop (round 2): a CTA walks tiles blockIdx.x, + gridDim.x, ...  While the last round of tile k
-     * computes and its result is scattered, the gather of tile k+1 is already in flight as cp.async copies
-     * (LDGSTS, no registers held) into the exchange buffer, which is idle from the last exchange of a tile to the
-     * first exchange of the next.  The HBM latency of the gather, the CTA launch and the drain of the scatter at
-     * CTA exit -- all dead time for a quarter of the SM's registers in round 1 -- are off the critical path. */
-    bool staged = false;
-    for (uint64_t tile_id = (uint64_t)blockIdx.x + tile_base; tile_id < tile_end; tile_id += gridDim.x) {
-    uint64_t outer = tile_outer(P, tile_id);              /* tile id -> outer index bits (uniform) */
+    /* tile id -> outer index bits (uniform) */
+    uint64_t tile = (uint64_t)blockIdx.x + tile_base, outer = 0;   /* tile_base: a pass may be launched in slices (pipelined exchange) */
+    {
+        const int nr = (int)P.n_runs;
+        for (int r = 0; r < nr; r++) {
+            const int len = P.run_len[r];
+            outer |= (tile & ((1ULL << len) - 1)) << P.run_start[r];
+            tile >>= len;
+        }
+    }
     const uint64_t src_outer = outer | P.src_fixed;   /* what the outer predicates test */
     /* per-thread predicate word: tid in bits 0..7, the CTA's outer-condition bits above */
     uint32_t tw = tid;
@@ -317,33 +294,37 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
         const int nc = (int)P.n_cond;
         for (int i = 0; i < nc; i++) { const uint64_t m = P.cond[i]; if ((src_outer & m) == m) tw |= (uint32_t)QSB_THREADS << i; }
     }
-    const bool have_next = tile_id + gridDim.x < tile_end;
+    const int n_rounds = (int)P.n_rounds;
 
     V re[NV], im[NV];
 
     /* ---- gather ---- */
-    if (staged) {
-        asm volatile("cp.async.wait_all;" ::: "memory");
+    {
+        uint64_t off = outer * AMP;
 #pragma unroll
-        for (int v = 0; v < NV; v++) IO<R>::sload(smem, tid * 16u + (uint32_t)v * (QSB_THREADS * 16u), re[v], im[v]);
-        __syncthreads();   /* everybody has its tile before the first exchange (or the next prefetch) overwrites the buffer */
-    } else {
-        const char *p = src + outer * AMP + thread_ld_off();
+        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) off += P.ld_thr[j];
+        const char *p = src + off;
 #pragma unroll
         for (int v = 0; v < NV; v++) IO<R>::gload(p + P.ld_vec[v], re[v], im[v]);
+#ifdef QSB_L2_PREFETCH
+        /* Pull the tile of the CTA that will take this one's place (QSB_L2_PREFETCH CTAs further on: the number
+         * resident on the chip) from HBM into L2 now: its gather then costs an L2 hit instead of a DRAM round trip.
+         * Threads 8k .. 8k+7 share 128-byte lines on the edge rounds (thread bits 0-2 are the physical bits next
+         * to the pack bit), so each of them asks for two of the 16 vectors.  A hint only: redundancy is harmless. */
+        {
+            uint64_t t2 = (uint64_t)blockIdx.x + tile_base + (uint64_t)QSB_L2_PREFETCH;
+            if (t2 < P.n_tiles) {
+                uint64_t o2 = 0;
+                const int nr = (int)P.n_runs;
+                for (int r = 0; r < nr; r++) { const int len = P.run_len[r]; o2 |= (t2 & ((1ULL << len) - 1)) << P.run_start[r]; t2 >>= len; }
+                const char *p2 = p + (o2 - outer) * AMP;
+                const int v0 = (tid & 7) * 2;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + P.ld_vec[v0]));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + P.ld_vec[v0 + 1]));
+            }
+        }
+#endif
     }
-    /* the gather of the NEXT tile starts as soon as the exchange buffer is idle: here if the pass has one round
-     * (the staged loads above are behind a barrier), otherwise after the last exchange (below) */
-    auto prefetch_next = [&]() {
-        const uint64_t o2 = tile_outer(P, tile_id + gridDim.x);
-        const char *p2 = src + o2 * AMP + thread_ld_off();
-        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem) + tid * 16u;
-#pragma unroll
-        for (int v = 0; v < NV; v++)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + (uint32_t)v * (QSB_THREADS * 16u)), "l"(p2 + P.ld_vec[v]) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (n_rounds == 1 && have_next) prefetch_next();
 
     uint32_t xm = 0;   /* deferred X: this thread's register v holds logical vector v ^ xm */
     const uint4 *rp = B + P.rounds_off16;
@@ -358,7 +339,6 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 #pragma unroll
             for (int v = 0; v < NV; v++) IO<R>::sload(smem, sl ^ RD.vld_x[v], re[v], im[v]);
             __syncthreads(); /* every thread has its registers before anyone overwrites the tile */
-            if (rd == n_rounds - 1 && have_next) prefetch_next();   /* the buffer is idle until the next tile's first exchange */
         }
 
         /* ---- the fused gates of this round ---- */
@@ -534,8 +514,6 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
             }
         }
     }
-    staged = have_next;
-    }   /* tile loop */
 }
 
 /* ------------------------------------------------------------------ launching */
@@ -557,18 +535,10 @@ static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst
 {
     int rc = ensure_smem_optin<R, BLOB, PEER>(s->device);
     if (rc) return rc;
+    if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
     if (ntile == 0) { tile0 = 0; ntile = hp.hdr.n_tiles; }
     const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
-    /* persistent CTAs: as many as are resident on the chip (QSB_CTAS_PER_SM per SM), each walks tiles with that stride */
-    static int n_sm[64] = {0};
-    const int dev = s->device & 63;
-    if (!n_sm[dev]) { QSB_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, s->device)); }
-    const uint64_t resident = (uint64_t)n_sm[dev] * QSB_CTAS_PER_SM;
-    static int persist = -1;                             /* QSB_PERSIST=0: one CTA per tile, no prefetch (A/B runs) */
-    if (persist < 0) { const char *e = getenv("QSB_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
-    if (!persist && ntile > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
-    const unsigned grid = (unsigned)(persist ? std::min<uint64_t>(ntile, resident) : ntile);
-    k_tile_pass<R, BLOB, PEER><<<grid, QSB_THREADS, QSB_SMEM_BYTES, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, tile0, tile0 + ntile);
+    k_tile_pass<R, BLOB, PEER><<<(unsigned)ntile, QSB_THREADS, QSB_SMEM_BYTES, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, (uint32_t)tile0);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
 }

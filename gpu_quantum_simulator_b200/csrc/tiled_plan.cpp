@@ -138,7 +138,7 @@ const int QSB_PLAN_OVERFLOW = -100;   /* internal: serialise() could not fit the
 
 struct Machine {
     int n, prec, g, nloc, rank, T, a, nb;
-    bool f32, lazy_diag, defer_diag, sink_phases, tile_search, hform;
+    bool f32, lazy_diag, defer_diag, sink_phases, tile_search, hform, diaga;
     int trim_thin, cost_cap;
     bool fused_exchange, force_top, fused_direct;
 };
@@ -1039,7 +1039,7 @@ struct PassBuilder {
         }
 
         std::vector<GRound> gr(nrounds);
-        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds), angstream(nrounds);
+        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds), angstream(nrounds), dgastream(nrounds);
         /* body offsets inside segstream entries are relative to the round's body; fixed up below */
         struct SegRec { uint32_t n_special, special_rel, n_groups, group_rel; };
         std::vector<std::vector<SegRec>> segrec(nrounds);
@@ -1083,12 +1083,62 @@ struct PassBuilder {
                 if ((hp.ops[k].kind & 0xff) == OP_TPHASE && is_unit_phase(hp.ops[k])) n_unit++;
             const bool use_angles = n_unit >= (f32 ? QSB_TANGLE_MIN_F32 : QSB_TANGLE_MIN_F64);
 
+            /* S_DIAGA pre-scan: runs of mergeable controlled phases per vector bit.  A run ends at any other op on that
+             * vector bit and at anything that may become a special (which closes the segment). */
+            const uint32_t rb = hp.round_op_begin[r], rn = hp.round_op_count[r];
+            std::vector<int> run_len(rn, 0);
+            {
+                auto lanes_eq = [](const HostOp &h) { for (int c = 0; c < h.n_coef; c++) if (h.c[0][c][0] != h.c[0][c][1]) return false; return true; };
+                auto mergeable = [&](const HostOp &h) {
+                    if ((h.kind & 0xff) != OP_DIAG_V || ((h.kind >> 16) & 1) || !lanes_eq(h)) return false;
+                    const double pr = h.c[0][0][1], pi = h.c[0][1][1];
+                    return fabs(pr * pr + pi * pi - 1.0) <= 1e-15;
+                };
+                std::vector<uint32_t> open_run[QSB_NVB];
+                auto close_run = [&](int b) { for (uint32_t k : open_run[b]) run_len[k] = (int)open_run[b].size(); open_run[b].clear(); };
+                for (uint32_t k = 0; k < rn; k++) {
+                    const HostOp &h = hp.ops[rb + k];
+                    const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf;
+                    if (code == OP_TPHASE) continue;
+                    if (mergeable(h)) { open_run[vb].push_back(k); continue; }
+                    if ((code == OP_MAT_U || code == OP_MAT_UI || code == OP_XDEF || code == OP_DIAG_V) && lanes_eq(h) && (!((h.kind >> 16) & 1) || [&] { for (int c = 0; c < h.n_coef; c++) if (h.c[1][c][0] != h.c[1][c][1]) return false; return true; }()))
+                        close_run(vb);                       /* a slot op on this vector bit only */
+                    else for (int b = 0; b < QSB_NVB; b++) close_run(b);   /* a special: the segment closes */
+                }
+                for (int b = 0; b < QSB_NVB; b++) close_run(b);
+            }
+            const int dga_min = M.diaga ? (f32 ? QSB_DIAGA_MIN_F32 : QSB_DIAGA_MIN_F64) : (1 << 30);
+            struct DgaOpen { int group = -1; std::vector<uint8_t> entries; uint32_t n = 0; };
+            DgaOpen dga[QSB_NVB];
+            auto angle_entry = [&](const HostOp &h, uint32_t tm8, uint64_t om, std::vector<uint8_t> &o) {
+                GTAngle e; memset(&e, 0, sizeof e);
+                e.tmask = tm8; e.omask = om;
+                const double pr = h.c[0][0][1], pi = h.c[0][1][1];
+                long double turns = (long double)atan2(pi, pr) / (2.0L * 3.14159265358979323846264338327950288L);
+                if (pi == 0.0) turns = pr > 0 ? 0.0L : 0.5L;
+                else if (pr == 0.0) turns = pi > 0 ? 0.25L : 0.75L;
+                turns -= floorl(turns);
+                long double scaled = roundl(ldexpl(turns, 64));
+                if (scaled >= ldexpl(1.0L, 64)) scaled = 0.0L;
+                e.ang64 = (uint64_t)scaled;
+                e.ang32 = (uint32_t)((e.ang64 + 0x80000000ULL) >> 32);
+                const uint8_t *q = (const uint8_t *)&e; o.insert(o.end(), q, q + (f32 ? 16 : 32));
+            };
             /* segment under construction */
             std::vector<uint8_t> specials; uint32_t n_special = 0;
             std::vector<std::vector<uint8_t>> groups;       /* each QSB_GROUP16 * 16 bytes */
             std::vector<std::array<bool, QSB_NVB>> slot_single;   /* slot holds an unconditional single-set gate */
             int next_group[QSB_NVB] = {0, 0, 0, 0};
+            auto finish_dga = [&](int b) {   /* the run on vector bit b is complete: entry list + its place in the slot */
+                if (dga[b].group < 0) return;
+                uint8_t *sets = groups[dga[b].group].data() + 32 + (size_t)b * 2 * SET16 * 16;
+                const uint32_t w[2] = {dga[b].n, (uint32_t)(dgastream[r].size() / 16)};
+                memcpy(sets, w, 8);
+                dgastream[r].insert(dgastream[r].end(), dga[b].entries.begin(), dga[b].entries.end());
+                dga[b] = DgaOpen();
+            };
             auto close_segment = [&]() {
+                for (int b = 0; b < QSB_NVB; b++) finish_dga(b);
                 if (!n_special && groups.empty()) return;
                 SegRec sr; sr.n_special = n_special; sr.special_rel = (uint32_t)bodystream[r].size();
                 bodystream[r].insert(bodystream[r].end(), specials.begin(), specials.end());
@@ -1146,6 +1196,20 @@ struct PassBuilder {
                     case OP_XDEF: sform = S_XDEF; break;
                     default: break;
                 }
+                if (sform == S_DIAG && run_len[k - rb] >= dga_min) {
+                    /* member of a run of controlled phases on this vector bit: one S_DIAGA slot for the whole run; the
+                     * entries carry their own outer mask, so the run takes no place in the outer-condition table W */
+                    if (dga[vb].group < 0) {
+                        const int g = next_group[vb]++;
+                        if (g == (int)groups.size()) { groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0)); slot_single.push_back({{false, false, false, false}}); }
+                        groups[g][vb] = (uint8_t)S_DIAGA;
+                        dga[vb].group = g;
+                    }
+                    angle_entry(h, tm8, om, dga[vb].entries);
+                    dga[vb].n++;
+                    continue;
+                }
+                if (sform != S_SKIP) finish_dga(vb);     /* any other slot op on this vector bit ends the run before it */
                 uint32_t wbits = 0;
                 if (sform != S_SKIP && cond_bit(om, wbits)) {
                     std::vector<uint8_t> slot;
@@ -1279,6 +1343,7 @@ struct PassBuilder {
             }
             off = body0 + bodystream[r].size();
             gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size() + angstream[r].size();
+            gr[r].dga_off16 = (uint32_t)(off / 16); off += dgastream[r].size();
         }
         const size_t total = off + 64;   /* slack: the group loop prefetches one group header past the last group */
         if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_PLAN_OVERFLOW; }
@@ -1294,6 +1359,7 @@ struct PassBuilder {
             if (!bodystream[r].empty()) memcpy(&b[at], bodystream[r].data(), bodystream[r].size());
             if (!tphstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16], tphstream[r].data(), tphstream[r].size());
             if (!angstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16 + tphstream[r].size()], angstream[r].data(), angstream[r].size());
+            if (!dgastream[r].empty()) memcpy(&b[(size_t)gr[r].dga_off16 * 16], dgastream[r].data(), dgastream[r].size());
         }
         return QSB_OK;
     }
@@ -1310,6 +1376,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.lazy_diag = opt && opt->reserved[1] == 2;      /* reserved[1] = 2: keep the qubits of phase gates thread-level (A/B runs;
                                                         same speed on random circuits, 2.4x more rounds on QFT) */
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
+    M.diaga = !(opt && opt->reserved[4] == 4);       /* reserved[4] = 4: no merged controlled phases S_DIAGA (A/B runs) */
     M.hform = !(opt && opt->reserved[4] == 3);       /* reserved[4] = 3: no Hadamard-like slot form S_UNIT_H (A/B runs) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.force_top = g > 0 && opt && opt->reserved[5] == 3;        /* reserved[5] = 3: NCCL-style plan executed as a pipelined exchange */
