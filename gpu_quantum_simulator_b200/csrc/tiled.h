@@ -168,12 +168,6 @@ enum {              /* slot forms (one-hot bytes, so the kernel dispatches with 
     S_UNIT_H = 4,   /* real unit form with q == 1 (Hadamard-like), unconditional, a == 1:
                        x0 += p x1; x1 = k x1 + x0 -- 4 instead of 6 packed operations per vector pair   S: p 1 k 1 */
     S_DIAG = 8,     /* phase on the vectors whose bit is set                           S: pr pi   */
-    S_DIAGA = 32,   /* MERGED controlled phases on one vector bit (QFT ladders, round 2): e^{2 pi i A} on the vectors whose
-                       bit is set, A = sum of the fixed-point angles of the list entries this thread satisfies
-                       (GTAngle entries: thread mask + outer mask + angle).  One sincospi + one packed complex
-                       multiply of half the vectors for the whole run instead of one per gate.
-                       Coefficient area: word 0 = number of entries, word 1 = first entry, in 16-byte units from
-                       GRound::dga_off16.  No predicate, no merged X. */
     S_XDEF = 16,    /* X (swap of the two halves) under the predicate, DEFERRED: the thread only
                        flips bit j of its vector-index mask; the swap happens for free in the
                        address of the next shared / global store.  Last op on its bit in a round. */
@@ -194,7 +188,12 @@ enum {              /* special op codes (generic interpreter); V = 8 bytes (f32:
     G_DIAG_GEN = 25, /* phase where (v & vmask) == vmask               V: pr pi       */
     G_MATP_R = 26,   /* pack-bit target, real (f32 only)               V: A B         */
     G_MATP_G = 27,   /* pack-bit target, complex (f32 only)            V: Ar Ai Br Bi */
-    G_NCODES = 28
+    G_DIAGA = 28,    /* +vb: MERGED controlled phases on one vector bit (QFT ladders, round 2): e^{2 pi i A} on the vectors
+                        whose bit vb is set, A = the sum of the fixed-point angles of the entries this thread satisfies.
+                        One sincospi + one packed complex multiply of half the vectors for the whole run, instead of a
+                        multiply (+ dispatch) per gate.  Payload: 16 bytes {n_entries, -, -, -}, then n_entries GTAngle
+                        entries (thread mask, outer mask, angle; 16 bytes f32 / 32 bytes f64).  No predicate of its own. */
+    G_NCODES = 32
 };
 /* Special op header (16 bytes):
  *   x = code | two << 8 | skip << 9 | vmask << 12 | size16 << 16
@@ -232,8 +231,8 @@ struct GTAngle {
 #define QSB_TANGLE_MIN_F32 8
 #define QSB_TANGLE_MIN_F64 24
 #endif
-/* S_DIAGA: a run of controlled phases on one vector bit is merged from this length on (a plain S_DIAG slot costs
- * ~32 packed operations + dispatch per gate; the merged form one multiply + one sincospi (~40 f32 / ~150 f64
+/* G_DIAGA: a run of controlled phases on one vector bit is merged from this length on (a plain phase slot costs ~32
+ * packed operations + dispatch per gate; the merged form one multiply + one sincospi (~40 f32 / ~150 f64
  * instructions) + ~5 per entry) */
 #define QSB_DIAGA_MIN_F32 3
 #define QSB_DIAGA_MIN_F64 6
@@ -248,7 +247,7 @@ struct GSegment {              /* 16 bytes */
 struct alignas(16) GRound {    /* the kernel steps through the round array in 16-byte units */
     uint32_t n_seg, seg_off16; /* GSegment array, 16-byte units from the blob start                  */
     uint32_t n_tph, tph_off16; /* GTPhase array                                                      */
-    uint32_t flags, n_ang, dga_off16, pad; /* dga_off16: entry lists of the S_DIAGA slots of this round; flags bit0: apply the pending scalar at the end of the round; n_ang: GTAngle
+    uint32_t flags, n_ang, pad[2]; /* flags bit0: apply the pending scalar at the end of the round; n_ang: GTAngle
                                   entries, stored right after the n_tph GTPhase entries                */
     uint32_t thr_x[QSB_TB];    /* smem byte XOR per thread bit: load side | store side << 16         */
     uint32_t vld_x[QSB_NV];    /* smem byte XOR per vector, load side                                */

@@ -370,6 +370,20 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                     V pr, pi; load_phase<R>(c, two, s1, pr, pi);
                     diag_v<R, VB>(re, im, pr, pi);
                 })
+                CASE4(G_DIAGA, {
+                    /* merged controlled phases: integer angle sum over the entries this thread satisfies, one sincospi, one multiply */
+                    const uint32_t n_e = c[0].x;
+                    const uint4 *e = c + 1;
+                    typename T::A acc = 0;
+                    for (uint32_t k = 0; k < n_e; k++, e += T::ANG16) {
+                        const uint4 eh = e[0];
+                        const uint64_t eom = ((uint64_t)eh.w << 32) | eh.z;
+                        if ((src_outer & eom) != eom) continue;          /* uniform */
+                        acc += ((tid & eh.x) == eh.x) ? T::ang(eh, e) : (typename T::A)0;
+                    }
+                    S apr, api; T::turn(acc, apr, api);
+                    diag_v<R, VB>(re, im, T::bc(apr), T::bc(api));
+                })
                 case G_DIAG_ALL: {
                     V pr, pi; load_phase<R>(c, two, s1, pr, pi);
 #pragma unroll

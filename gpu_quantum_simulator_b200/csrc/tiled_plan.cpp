@@ -1039,7 +1039,7 @@ struct PassBuilder {
         }
 
         std::vector<GRound> gr(nrounds);
-        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds), angstream(nrounds), dgastream(nrounds);
+        std::vector<std::vector<uint8_t>> segstream(nrounds), bodystream(nrounds), tphstream(nrounds), angstream(nrounds);
         /* body offsets inside segstream entries are relative to the round's body; fixed up below */
         struct SegRec { uint32_t n_special, special_rel, n_groups, group_rel; };
         std::vector<std::vector<SegRec>> segrec(nrounds);
@@ -1083,10 +1083,12 @@ struct PassBuilder {
                 if ((hp.ops[k].kind & 0xff) == OP_TPHASE && is_unit_phase(hp.ops[k])) n_unit++;
             const bool use_angles = n_unit >= (f32 ? QSB_TANGLE_MIN_F32 : QSB_TANGLE_MIN_F64);
 
-            /* S_DIAGA pre-scan: runs of mergeable controlled phases per vector bit.  A run ends at any other op on that
-             * vector bit and at anything that may become a special (which closes the segment). */
+            /* G_DIAGA pre-scan: runs of mergeable controlled phases per vector bit.  Everything between two members of a
+             * run commutes with them (ops on other vector bits never name this one as a control; phases are diagonal), so
+             * the whole run is lowered at its first member.  A run ends at any other op whose target is that vector bit. */
             const uint32_t rb = hp.round_op_begin[r], rn = hp.round_op_count[r];
-            std::vector<int> run_len(rn, 0);
+            std::vector<int> run_of(rn, -1);                    /* op -> run id, or -1 */
+            std::vector<std::vector<uint32_t>> runs;
             {
                 auto lanes_eq = [](const HostOp &h) { for (int c = 0; c < h.n_coef; c++) if (h.c[0][c][0] != h.c[0][c][1]) return false; return true; };
                 auto mergeable = [&](const HostOp &h) {
@@ -1094,51 +1096,26 @@ struct PassBuilder {
                     const double pr = h.c[0][0][1], pi = h.c[0][1][1];
                     return fabs(pr * pr + pi * pi - 1.0) <= 1e-15;
                 };
-                std::vector<uint32_t> open_run[QSB_NVB];
-                auto close_run = [&](int b) { for (uint32_t k : open_run[b]) run_len[k] = (int)open_run[b].size(); open_run[b].clear(); };
+                int open_run[QSB_NVB] = {-1, -1, -1, -1};
                 for (uint32_t k = 0; k < rn; k++) {
                     const HostOp &h = hp.ops[rb + k];
                     const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf;
-                    if (code == OP_TPHASE) continue;
-                    if (mergeable(h)) { open_run[vb].push_back(k); continue; }
-                    if ((code == OP_MAT_U || code == OP_MAT_UI || code == OP_XDEF || code == OP_DIAG_V) && lanes_eq(h) && (!((h.kind >> 16) & 1) || [&] { for (int c = 0; c < h.n_coef; c++) if (h.c[1][c][0] != h.c[1][c][1]) return false; return true; }()))
-                        close_run(vb);                       /* a slot op on this vector bit only */
-                    else for (int b = 0; b < QSB_NVB; b++) close_run(b);   /* a special: the segment closes */
+                    if (code == OP_TPHASE || code == OP_DIAG_ALL || code == OP_DIAG_GEN || code == OP_MATP_R || code == OP_MATP_G) continue;
+                    if (mergeable(h)) {
+                        if (open_run[vb] < 0) { open_run[vb] = (int)runs.size(); runs.emplace_back(); }
+                        runs[open_run[vb]].push_back(k); run_of[k] = open_run[vb];
+                    } else open_run[vb] = -1;
                 }
-                for (int b = 0; b < QSB_NVB; b++) close_run(b);
+                const size_t dga_min = M.diaga ? (f32 ? QSB_DIAGA_MIN_F32 : QSB_DIAGA_MIN_F64) : ((size_t)1 << 30);
+                for (auto &rr : runs) if (rr.size() < dga_min) { for (uint32_t k : rr) run_of[k] = -1; rr.clear(); }
             }
-            const int dga_min = M.diaga ? (f32 ? QSB_DIAGA_MIN_F32 : QSB_DIAGA_MIN_F64) : (1 << 30);
-            struct DgaOpen { int group = -1; std::vector<uint8_t> entries; uint32_t n = 0; };
-            DgaOpen dga[QSB_NVB];
-            auto angle_entry = [&](const HostOp &h, uint32_t tm8, uint64_t om, std::vector<uint8_t> &o) {
-                GTAngle e; memset(&e, 0, sizeof e);
-                e.tmask = tm8; e.omask = om;
-                const double pr = h.c[0][0][1], pi = h.c[0][1][1];
-                long double turns = (long double)atan2(pi, pr) / (2.0L * 3.14159265358979323846264338327950288L);
-                if (pi == 0.0) turns = pr > 0 ? 0.0L : 0.5L;
-                else if (pr == 0.0) turns = pi > 0 ? 0.25L : 0.75L;
-                turns -= floorl(turns);
-                long double scaled = roundl(ldexpl(turns, 64));
-                if (scaled >= ldexpl(1.0L, 64)) scaled = 0.0L;
-                e.ang64 = (uint64_t)scaled;
-                e.ang32 = (uint32_t)((e.ang64 + 0x80000000ULL) >> 32);
-                const uint8_t *q = (const uint8_t *)&e; o.insert(o.end(), q, q + (f32 ? 16 : 32));
-            };
+            std::vector<char> run_done(runs.size(), 0);
             /* segment under construction */
             std::vector<uint8_t> specials; uint32_t n_special = 0;
             std::vector<std::vector<uint8_t>> groups;       /* each QSB_GROUP16 * 16 bytes */
             std::vector<std::array<bool, QSB_NVB>> slot_single;   /* slot holds an unconditional single-set gate */
             int next_group[QSB_NVB] = {0, 0, 0, 0};
-            auto finish_dga = [&](int b) {   /* the run on vector bit b is complete: entry list + its place in the slot */
-                if (dga[b].group < 0) return;
-                uint8_t *sets = groups[dga[b].group].data() + 32 + (size_t)b * 2 * SET16 * 16;
-                const uint32_t w[2] = {dga[b].n, (uint32_t)(dgastream[r].size() / 16)};
-                memcpy(sets, w, 8);
-                dgastream[r].insert(dgastream[r].end(), dga[b].entries.begin(), dga[b].entries.end());
-                dga[b] = DgaOpen();
-            };
             auto close_segment = [&]() {
-                for (int b = 0; b < QSB_NVB; b++) finish_dga(b);
                 if (!n_special && groups.empty()) return;
                 SegRec sr; sr.n_special = n_special; sr.special_rel = (uint32_t)bodystream[r].size();
                 bodystream[r].insert(bodystream[r].end(), specials.begin(), specials.end());
@@ -1182,6 +1159,39 @@ struct PassBuilder {
                     n_tph++;
                     continue;
                 }
+                if (run_of[k - rb] >= 0) {
+                    /* member of a run of controlled phases on vector bit vb: the whole run is ONE special, lowered at its first member */
+                    const int run = run_of[k - rb];
+                    if (run_done[run]) continue;
+                    run_done[run] = 1;
+                    if (!groups.empty()) close_segment();
+                    std::vector<uint8_t> body(16, 0);
+                    const uint32_t n_e = (uint32_t)runs[run].size();
+                    memcpy(body.data(), &n_e, 4);
+                    for (uint32_t km : runs[run]) {
+                        const HostOp &hm = hp.ops[rb + km];
+                        uint32_t tmm; uint64_t omm; split_mask(hm.tmask, tmm, omm);
+                        GTAngle e; memset(&e, 0, sizeof e);
+                        e.tmask = tmm; e.omask = omm;
+                        const double pr = hm.c[0][0][1], pi = hm.c[0][1][1];
+                        long double turns = (long double)atan2(pi, pr) / (2.0L * 3.14159265358979323846264338327950288L);
+                        if (pi == 0.0) turns = pr > 0 ? 0.0L : 0.5L;
+                        else if (pr == 0.0) turns = pi > 0 ? 0.25L : 0.75L;
+                        turns -= floorl(turns);
+                        long double scaled = roundl(ldexpl(turns, 64));
+                        if (scaled >= ldexpl(1.0L, 64)) scaled = 0.0L;
+                        e.ang64 = (uint64_t)scaled;
+                        e.ang32 = (uint32_t)((e.ang64 + 0x80000000ULL) >> 32);
+                        const uint8_t *q = (const uint8_t *)&e; body.insert(body.end(), q, q + (f32 ? 16 : 32));
+                    }
+                    const size_t bytes = 16 + body.size();
+                    if (bytes / 16 > 0xffff) { qsb_set_error("internal: merged phase run too long"); return QSB_ERR_ARG; }
+                    uint32_t hdr[4] = {GOPK(G_DIAGA + vb, 0, 0, 0, bytes / 16), 0, 0, 0};
+                    const uint8_t *q = (const uint8_t *)hdr; specials.insert(specials.end(), q, q + 16);
+                    specials.insert(specials.end(), body.begin(), body.end());
+                    n_special++;
+                    continue;
+                }
                 const bool cond = (tm8 | om) != 0;
                 /* lanes differ (a control on the pack qubit): scalar-coefficient forms cannot express it */
                 auto lanes_equal = [&](int set) { for (int c = 0; c < h.n_coef; c++) if (h.c[set][c][0] != h.c[set][c][1]) return false; return true; };
@@ -1196,20 +1206,6 @@ struct PassBuilder {
                     case OP_XDEF: sform = S_XDEF; break;
                     default: break;
                 }
-                if (sform == S_DIAG && run_len[k - rb] >= dga_min) {
-                    /* member of a run of controlled phases on this vector bit: one S_DIAGA slot for the whole run; the
-                     * entries carry their own outer mask, so the run takes no place in the outer-condition table W */
-                    if (dga[vb].group < 0) {
-                        const int g = next_group[vb]++;
-                        if (g == (int)groups.size()) { groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0)); slot_single.push_back({{false, false, false, false}}); }
-                        groups[g][vb] = (uint8_t)S_DIAGA;
-                        dga[vb].group = g;
-                    }
-                    angle_entry(h, tm8, om, dga[vb].entries);
-                    dga[vb].n++;
-                    continue;
-                }
-                if (sform != S_SKIP) finish_dga(vb);     /* any other slot op on this vector bit ends the run before it */
                 uint32_t wbits = 0;
                 if (sform != S_SKIP && cond_bit(om, wbits)) {
                     std::vector<uint8_t> slot;
@@ -1343,7 +1339,6 @@ struct PassBuilder {
             }
             off = body0 + bodystream[r].size();
             gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size() + angstream[r].size();
-            gr[r].dga_off16 = (uint32_t)(off / 16); off += dgastream[r].size();
         }
         const size_t total = off + 64;   /* slack: the group loop prefetches one group header past the last group */
         if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_PLAN_OVERFLOW; }
@@ -1359,7 +1354,6 @@ struct PassBuilder {
             if (!bodystream[r].empty()) memcpy(&b[at], bodystream[r].data(), bodystream[r].size());
             if (!tphstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16], tphstream[r].data(), tphstream[r].size());
             if (!angstream[r].empty()) memcpy(&b[(size_t)gr[r].tph_off16 * 16 + tphstream[r].size()], angstream[r].data(), angstream[r].size());
-            if (!dgastream[r].empty()) memcpy(&b[(size_t)gr[r].dga_off16 * 16], dgastream[r].data(), dgastream[r].size());
         }
         return QSB_OK;
     }
@@ -1376,7 +1370,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     M.lazy_diag = opt && opt->reserved[1] == 2;      /* reserved[1] = 2: keep the qubits of phase gates thread-level (A/B runs;
                                                         same speed on random circuits, 2.4x more rounds on QFT) */
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
-    M.diaga = !(opt && opt->reserved[4] == 4);       /* reserved[4] = 4: no merged controlled phases S_DIAGA (A/B runs) */
+    M.diaga = !(opt && opt->reserved[4] == 4);       /* reserved[4] = 4: no merged controlled phases G_DIAGA (A/B runs) */
     M.hform = !(opt && opt->reserved[4] == 3);       /* reserved[4] = 3: no Hadamard-like slot form S_UNIT_H (A/B runs) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.force_top = g > 0 && opt && opt->reserved[5] == 3;        /* reserved[5] = 3: NCCL-style plan executed as a pipelined exchange */

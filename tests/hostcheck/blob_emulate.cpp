@@ -90,6 +90,27 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                     op += (size_t)(h[0] >> 16) * 16;
                     const uint32_t code = h[0] & 0xff, vmask = (h[0] >> 12) & 0xf; const bool two = (h[0] >> 8) & 1;
                     const uint64_t om = ((uint64_t)h[3] << 32) | h[2];
+                    if (code >= G_DIAGA && code < G_DIAGA + 4) {   /* merged controlled phases: per-thread fixed-point angle sum, one phase */
+                        const int vb = code - G_DIAGA;
+                        uint32_t n_e; memcpy(&n_e, c, 4);
+                        const size_t stride = f32 ? 16 : 32;
+                        if (two || h[1] || om || (size_t)(h[0] >> 16) != 2 + (size_t)n_e * (stride / 16)) bad++;
+                        for (int tid = 0; tid < QSB_THREADS; tid++) {
+                            uint64_t acc = 0;
+                            for (uint32_t i = 0; i < n_e; i++) {
+                                GTAngle T; memset(&T, 0, sizeof T); memcpy(&T, c + 16 + i * stride, stride);
+                                if ((src_outer & T.omask) != T.omask) continue;
+                                if (T.tmask >> QSB_TB) bad++;
+                                if (((uint32_t)tid & T.tmask) == T.tmask) acc += f32 ? (uint64_t)T.ang32 : T.ang64;
+                            }
+                            const double half_turns = f32 ? (double)(int32_t)(uint32_t)acc / 2147483648.0 : (double)(int64_t)acc / 9223372036854775808.0;
+                            const double PI_ = 3.14159265358979323846;
+                            const cd ph(cos(PI_ * half_turns), sin(PI_ * half_turns));
+                            cd *R = &regs[(size_t)tid * QSB_NV * L];
+                            for (int v = 0; v < QSB_NV; v++) if ((v >> vb) & 1) for (int l = 0; l < L; l++) R[v * L + l] *= ph;
+                        }
+                        continue;
+                    }
                     for (int tid = 0; tid < QSB_THREADS; tid++) {
                         const bool pred = ((src_outer & om) == om) && (((uint32_t)tid & h[1]) == h[1]);
                         if (!two && !pred) continue;
@@ -132,27 +153,6 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                         const uint32_t form = gp[vb];
                         if (!form) continue;
                         const uint8_t *c0 = gp + 32 + (size_t)vb * 2 * SET16 * 16, *c1 = c0 + (size_t)SET16 * 16;
-                        if (form & S_DIAGA) {   /* merged controlled phases: per-thread fixed-point angle sum, then one phase */
-                            if (form != S_DIAGA || pm[vb]) bad++;
-                            uint32_t w[2]; memcpy(w, c0, 8);
-                            const size_t stride = f32 ? 16 : 32;
-                            const uint8_t *e0 = B + (size_t)RD.dga_off16 * 16 + (size_t)w[1] * 16;
-                            for (int tid = 0; tid < QSB_THREADS; tid++) {
-                                uint64_t acc = 0;
-                                for (uint32_t i = 0; i < w[0]; i++) {
-                                    GTAngle T; memset(&T, 0, sizeof T); memcpy(&T, e0 + i * stride, stride);
-                                    if ((src_outer & T.omask) != T.omask) continue;
-                                    if (T.tmask >> QSB_TB) bad++;
-                                    if (((uint32_t)tid & T.tmask) == T.tmask) acc += f32 ? (uint64_t)T.ang32 : T.ang64;
-                                }
-                                const double half_turns = f32 ? (double)(int32_t)(uint32_t)acc / 2147483648.0 : (double)(int64_t)acc / 9223372036854775808.0;
-                                const double PI_ = 3.14159265358979323846;
-                                const cd ph(cos(PI_ * half_turns), sin(PI_ * half_turns));
-                                cd *R = &regs[(size_t)tid * QSB_NV * L];
-                                for (int v = 0; v < QSB_NV; v++) if ((v >> vb) & 1) for (int l = 0; l < L; l++) R[v * L + l] *= ph;
-                            }
-                            continue;
-                        }
                         for (int tid = 0; tid < QSB_THREADS; tid++) {
                             const uint32_t tw = (uint32_t)tid | (W << QSB_TB);
                             const bool pred = (tw & pm[vb]) == pm[vb];
