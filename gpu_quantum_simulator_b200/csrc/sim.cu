@@ -366,10 +366,12 @@ extern "C" int qsb_plan_create(qsb_t *s, const qsb_gate_t *gates, size_t n, qsb_
 extern "C" int qsb_plan_dry_run(int num_qubits, const qsb_options_t *opt_in, const qsb_gate_t *gates, size_t n, qsb_run_stats_t *out)
 {
     if (!out || (n && !gates)) { qsb_set_error("qsb_plan_dry_run: null argument"); return QSB_ERR_ARG; }
+    if (num_qubits < 1 || num_qubits > 40) { qsb_set_error("num_qubits %d out of range 1..40", num_qubits); return QSB_ERR_ARG; }
     qsb_options_t opt;
     if (opt_in) opt = *opt_in; else qsb_options_default(&opt);
     if (opt.precision == 0) opt.precision = QSB_F32;
     if (opt.world_size <= 0) opt.world_size = 1;
+    if (opt.world_size & (opt.world_size - 1)) { qsb_set_error("world_size must be a power of two"); return QSB_ERR_ARG; }
     int g = ilog2(opt.world_size);
     int nloc = std::max(num_qubits - g, tiled_min_local_bits(opt.precision, &opt));
     BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;

@@ -38,7 +38,10 @@
 
 #include "common.cuh"
 
-#define QSB_NVB 4              /* vector bits per round: 16 vectors per thread (8 per thread measured slower, round 1a) */
+#ifndef QSB_NVB
+#define QSB_NVB 4              /* vector bits per round: 16 vectors per thread (8 per thread measured slower, round 1a; 32 per thread,
+                                  -DQSB_NVB=5 -DQSB_TB=6, is the round-2 experiment of profiles/r2/nvb5_experiment.md) */
+#endif
 #define QSB_NV (1 << QSB_NVB)  /* vectors per thread                         */
 /* Thread bits.  Build-time geometry switch, A/B measured on B200 (profiles/r1h_tile_geometry_ab.txt):
  *   QSB_TB = 8: 256 threads, two CTAs per SM, tiles of 2^13 (f32) / 2^12 (f64) amplitudes
@@ -88,6 +91,7 @@ enum {
  *   mux   : thread-level multiplexer: threads whose tmask test fails use
  *           coefficient set 0 instead of skipping (set 1 follows set 0)       */
 #define OPK(op, vb, mux, vmask) ((uint32_t)(op) | ((uint32_t)(vb) << 8) | ((uint32_t)(mux) << 16) | ((uint32_t)(vmask) << 20))
+#define OPK_VMASK(kind) (((kind) >> 20) & 0xffu)
 
 /* Op stream element: 16-byte header followed by the coefficient payload.
  * Payload entries are 8 bytes in both precisions: f32 = (lo lane, hi lane)
@@ -179,24 +183,27 @@ enum {              /* slot forms (one-hot bytes, so the kernel dispatches with 
  *                          fails use set 0 (the identity for a controlled gate, the control-off matrix
  *                          for a multiplexer), the others set 1. */
 #define QSB_SET16(f32) ((f32) ? 1 : 2)             /* one 4-scalar coefficient set, 16-byte units */
+/* byte offsets inside a group: form byte of slot j = byte j of unit [0]; predicate mask of slot j = word j of unit [1]
+ * for j < 4, word 2 + (j - 4) of unit [0] beyond (QSB_NVB = 5) */
+#define QSB_GROUP_MASK_OFF(j) ((j) < 4 ? 16 + 4 * (j) : 8 + 4 * ((j) - 4))
 #define QSB_GROUP16(f32) (2 + QSB_NVB * 2 * QSB_SET16(f32))
 
 enum {              /* special op codes (generic interpreter); V = 8 bytes (f32: (lo, hi) lanes, f64: one double) */
     G_FULL_G = 16,   /* +vb: complex 2x2             V: m00r m00i m01r m01i m10r m10i m11r m11i */
-    G_DIAG_V = 20,   /* +vb: phase where vector bit vb is set          V: pr pi       */
-    G_DIAG_ALL = 24, /* phase on every vector (lane dependent)         V: pr pi       */
-    G_DIAG_GEN = 25, /* phase where (v & vmask) == vmask               V: pr pi       */
-    G_MATP_R = 26,   /* pack-bit target, real (f32 only)               V: A B         */
-    G_MATP_G = 27,   /* pack-bit target, complex (f32 only)            V: Ar Ai Br Bi */
-    G_DIAGA = 28,    /* +vb: MERGED controlled phases on one vector bit (QFT ladders, round 2): e^{2 pi i A} on the vectors
+    G_DIAG_V = 24,   /* +vb: phase where vector bit vb is set          V: pr pi       */
+    G_DIAGA = 32,    /* +vb: MERGED controlled phases on one vector bit (QFT ladders, round 2): e^{2 pi i A} on the vectors
                         whose bit vb is set, A = the sum of the fixed-point angles of the entries this thread satisfies.
                         One sincospi + one packed complex multiply of half the vectors for the whole run, instead of a
                         multiply (+ dispatch) per gate.  Payload: 16 bytes {n_entries, -, -, -}, then n_entries GTAngle
                         entries (thread mask, outer mask, angle; 16 bytes f32 / 32 bytes f64).  No predicate of its own. */
-    G_NCODES = 32
+    G_DIAG_ALL = 40, /* phase on every vector (lane dependent)         V: pr pi       */
+    G_DIAG_GEN = 41, /* phase where (v & vmask) == vmask               V: pr pi       */
+    G_MATP_R = 42,   /* pack-bit target, real (f32 only)               V: A B         */
+    G_MATP_G = 43,   /* pack-bit target, complex (f32 only)            V: Ar Ai Br Bi */
+    G_NCODES = 44
 };
 /* Special op header (16 bytes):
- *   x = code | two << 8 | skip << 9 | vmask << 12 | size16 << 16
+ *   x = code | two << 8 | skip << 9 | vmask << 10 | size16 << 16
  *       two : a multiplexer -- two coefficient sets follow; threads whose predicate fails use set 0
  *             (the control-off matrix), the others set 1.  Otherwise one set: threads whose predicate
  *             fails skip the op (a controlled gate)
@@ -204,7 +211,8 @@ enum {              /* special op codes (generic interpreter); V = 8 bytes (f32:
  *   y = 8-bit mask over threadIdx.x          z, w = 64-bit mask over the outer (per-CTA) index bits
  * predicate = (tid & y) == y && (outer & zw) == zw.  Coefficient sets are padded to 16 bytes. */
 #define GOPK(code, two, skip, vmask, size16) \
-    ((uint32_t)(code) | ((uint32_t)(two) << 8) | ((uint32_t)(skip) << 9) | ((uint32_t)(vmask) << 12) | ((uint32_t)(size16) << 16))
+    ((uint32_t)(code) | ((uint32_t)(two) << 8) | ((uint32_t)(skip) << 9) | ((uint32_t)(vmask) << 10) | ((uint32_t)(size16) << 16))
+#define GOP_VMASK(x) (((x) >> 10) & 0x3fu)
 
 struct GTPhase {               /* thread-level phase, applied through the pending scalar (32 bytes) */
     uint32_t tmask, pad;

@@ -229,11 +229,17 @@ template <> struct IO<double> {
 };
 
 /* ------------------------------------------------------------------ the kernel */
+#if QSB_NVB == 5
+#define CASE_VB4(base, ...) case (base) + 4: { enum { VB = 4 }; __VA_ARGS__ } break;
+#else
+#define CASE_VB4(base, ...)
+#endif
 #define CASE4(base, ...)                              \
     case (base) + 0: { enum { VB = 0 }; __VA_ARGS__ } break; \
     case (base) + 1: { enum { VB = 1 }; __VA_ARGS__ } break; \
     case (base) + 2: { enum { VB = 2 }; __VA_ARGS__ } break; \
-    case (base) + 3: { enum { VB = 3 }; __VA_ARGS__ } break;
+    case (base) + 3: { enum { VB = 3 }; __VA_ARGS__ } break; \
+    CASE_VB4(base, __VA_ARGS__)
 
 /* One slot of a group = the op on vector bit VB: a one-hot form byte, a predicate mask and two
  * 4-scalar coefficient sets.  Slots are software-pipelined: the coefficient loads of the next
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(QSB_THREADS, QSB_CTAS_PER_SM)
 k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *dst, const __grid_constant__ PeerTab peers, uint32_t tile_base)
 {
     typedef VT<R> T; typedef typename T::V V; typedef typename T::S S;
-    static_assert(QSB_NVB == 4, "the interpreter is written for 4 vector bits");
+    static_assert(QSB_NVB == 4 || QSB_NVB == 5, "the interpreter is written for 4 or 5 vector bits");
     extern __shared__ __align__(16) uint8_t smem[];
     const uint4 *B = blob.q;
     const GPass &P = *reinterpret_cast<const GPass *>(B);
@@ -391,14 +397,10 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                     break;
                 }
                 case G_DIAG_GEN: {
-                    const uint32_t vmask = (h.x >> 12) & 0xfu;
+                    const uint32_t vmask = GOP_VMASK(h.x);   /* uniform: one predicated sweep over the vectors, one copy of the code */
                     V pr, pi; load_phase<R>(c, two, s1, pr, pi);
-                    switch (vmask) {   /* uniform: one static variant per mask, only the matching vectors are touched */
-#define DGEN(MASK) case MASK: diag_mask<R, MASK>(re, im, pr, pi); break;
-                    DGEN(3) DGEN(5) DGEN(6) DGEN(7) DGEN(9) DGEN(10) DGEN(11) DGEN(12) DGEN(13) DGEN(14) DGEN(15)
-#undef DGEN
-                    default: break;
-                    }
+#pragma unroll
+                    for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) cmul_inplace<R>(re[v], im[v], pr, pi);
                     break;
                 }
                 case G_MATP_R: {
@@ -425,6 +427,9 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                     const uint4 gh = nh, gm = nm;
                     nh = gp[G16]; nm = gp[G16 + 1];            /* next group's header (or slack) */
                     const uint32_t f0 = gh.x & 0xffu, f1 = (gh.x >> 8) & 0xffu, f2 = (gh.x >> 16) & 0xffu, f3 = gh.x >> 24;
+#if QSB_NVB == 5
+                    const uint32_t f4 = gh.y & 0xffu;      /* slot 4: form byte 4, predicate mask in word 2 of the header unit */
+#endif
                     const uint4 *cp = gp + 2;
                     SlotC<R> sa, sc;
                     if (f0) slot_fetch<R>(cp, sa);
@@ -434,7 +439,13 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                     if (f1) slot_exec<R, 1>(f1, gm.y, sc, re, im, tw, psr, psi, xm);
                     if (f3) slot_fetch<R>(cp + 3 * S16, sc);
                     if (f2) slot_exec<R, 2>(f2, gm.z, sa, re, im, tw, psr, psi, xm);
+#if QSB_NVB == 5
+                    if (f4) slot_fetch<R>(cp + 4 * S16, sa);
+#endif
                     if (f3) slot_exec<R, 3>(f3, gm.w, sc, re, im, tw, psr, psi, xm);
+#if QSB_NVB == 5
+                    if (f4) slot_exec<R, 4>(f4, gh.z, sa, re, im, tw, psr, psi, xm);
+#endif
                 }
             }
         }

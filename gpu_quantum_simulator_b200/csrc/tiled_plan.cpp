@@ -1096,7 +1096,7 @@ struct PassBuilder {
                     const double pr = h.c[0][0][1], pi = h.c[0][1][1];
                     return fabs(pr * pr + pi * pi - 1.0) <= 1e-15;
                 };
-                int open_run[QSB_NVB] = {-1, -1, -1, -1};
+                int open_run[QSB_NVB]; for (int b = 0; b < QSB_NVB; b++) open_run[b] = -1;
                 for (uint32_t k = 0; k < rn; k++) {
                     const HostOp &h = hp.ops[rb + k];
                     const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf;
@@ -1114,7 +1114,7 @@ struct PassBuilder {
             std::vector<uint8_t> specials; uint32_t n_special = 0;
             std::vector<std::vector<uint8_t>> groups;       /* each QSB_GROUP16 * 16 bytes */
             std::vector<std::array<bool, QSB_NVB>> slot_single;   /* slot holds an unconditional single-set gate */
-            int next_group[QSB_NVB] = {0, 0, 0, 0};
+            int next_group[QSB_NVB]; for (int b = 0; b < QSB_NVB; b++) next_group[b] = 0;
             auto close_segment = [&]() {
                 if (!n_special && groups.empty()) return;
                 SegRec sr; sr.n_special = n_special; sr.special_rel = (uint32_t)bodystream[r].size();
@@ -1128,7 +1128,7 @@ struct PassBuilder {
 
             for (uint32_t k = hp.round_op_begin[r]; k < hp.round_op_begin[r] + hp.round_op_count[r]; k++) {
                 const HostOp &h = hp.ops[k];
-                const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf, vmask = (h.kind >> 20) & 0xf;
+                const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf, vmask = OPK_VMASK(h.kind);
                 const bool mux = (h.kind >> 16) & 1;
                 uint32_t tm8; uint64_t om;
                 split_mask(h.tmask, tm8, om);
@@ -1233,21 +1233,21 @@ struct PassBuilder {
                          * An unconditional single-set gate takes the X's predicate (both coefficient sets identical). */
                         uint8_t *Gp = groups[next_group[vb] - 1].data();
                         const uint8_t pf = Gp[vb];
-                        uint32_t ppm; memcpy(&ppm, Gp + 16 + 4 * vb, 4);
+                        uint32_t ppm; memcpy(&ppm, Gp + QSB_GROUP_MASK_OFF(vb), 4);
                         uint8_t *sets = Gp + 32 + (size_t)vb * 2 * SET16 * 16;
                         const bool prev_uncond = ppm == 0 && slot_single[next_group[vb] - 1][vb];
                         if ((pf & (S_UNIT_R | S_UNIT_I | S_UNIT_H | S_DIAG)) && !(pf & S_XDEF) && (ppm == pm_new || prev_uncond)) {
-                            if (ppm != pm_new) { memcpy(sets, sets + (size_t)SET16 * 16, (size_t)SET16 * 16); memcpy(Gp + 16 + 4 * vb, &pm_new, 4); }
+                            if (ppm != pm_new) { memcpy(sets, sets + (size_t)SET16 * 16, (size_t)SET16 * 16); memcpy(Gp + QSB_GROUP_MASK_OFF(vb), &pm_new, 4); }
                             Gp[vb] = (uint8_t)(pf | S_XDEF);
                             continue;
                         }
                     }
                     const int g = next_group[vb]++;
-                    if (g == (int)groups.size()) { groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0)); slot_single.push_back({{false, false, false, false}}); }
+                    if (g == (int)groups.size()) { groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0)); slot_single.push_back(std::array<bool, QSB_NVB>{}); }
                     slot_single[g][vb] = !mux && !cond;
                     uint8_t *G0 = groups[g].data();
                     G0[vb] = (uint8_t)sform;                                   /* form byte of slot vb */
-                    memcpy(G0 + 16 + 4 * vb, &pm_new, 4);                      /* predicate mask */
+                    memcpy(G0 + QSB_GROUP_MASK_OFF(vb), &pm_new, 4);           /* predicate mask */
                     memcpy(G0 + 32 + (size_t)vb * 2 * SET16 * 16, slot.data(), slot.size());
                     continue;
                 }

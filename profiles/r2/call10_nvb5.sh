@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round 2, GPU call 10: 32 vectors per thread (-DQSB_NVB=5 -DQSB_TB=6, 64-thread CTAs x 4 per SM, 254 registers) against the
+# default geometry (16 vectors, 128-thread CTAs x 4 per SM), same box back to back.
+cd "$(dirname "$0")/../.."
+O=gpurun_out/r2c10; mkdir -p $O
+QSB_LIB_SUFFIX=_nvb5 python -m pytest tests/test_gpu_parity.py -m "gpu and not slow" -x -q > $O/pytest_nvb5.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_nvb5.log
+B="python bench.py --qubits 30 --steps 4 --warmup 3 --no-e2e --no-cpu"
+run() { echo "cfg=$1"; shift; "$@" 2>&1 | tail -1; }
+{
+run "default f32" $B
+run "nvb5 f32" env QSB_LIB_SUFFIX=_nvb5 $B
+run "default f64" $B --precision 64
+run "nvb5 f64" env QSB_LIB_SUFFIX=_nvb5 $B --precision 64
+run "default qft f32" $B --workload qft
+run "nvb5 qft f32" env QSB_LIB_SUFFIX=_nvb5 $B --workload qft
+run "nvb5 f32 cap12" env QSB_LIB_SUFFIX=_nvb5 $B --cost-cap 12
+} > $O/bench.log 2>&1
+tail -3 $O/pytest_nvb5.log

@@ -88,9 +88,9 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                     uint32_t h[4]; memcpy(h, op, 16);
                     const uint8_t *c = op + 16;
                     op += (size_t)(h[0] >> 16) * 16;
-                    const uint32_t code = h[0] & 0xff, vmask = (h[0] >> 12) & 0xf; const bool two = (h[0] >> 8) & 1;
+                    const uint32_t code = h[0] & 0xff, vmask = GOP_VMASK(h[0]); const bool two = (h[0] >> 8) & 1;
                     const uint64_t om = ((uint64_t)h[3] << 32) | h[2];
-                    if (code >= G_DIAGA && code < G_DIAGA + 4) {   /* merged controlled phases: per-thread fixed-point angle sum, one phase */
+                    if (code >= G_DIAGA && code < G_DIAGA + QSB_NVB) {   /* merged controlled phases: per-thread fixed-point angle sum, one phase */
                         const int vb = code - G_DIAGA;
                         uint32_t n_e; memcpy(&n_e, c, 4);
                         const size_t stride = f32 ? 16 : 32;
@@ -116,7 +116,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                         if (!two && !pred) continue;
                         const bool s1 = two && pred;
                         cd *R = &regs[(size_t)tid * QSB_NV * L];
-                        if (code >= G_FULL_G && code < G_FULL_G + 4) {
+                        if (code >= G_FULL_G && code < G_FULL_G + QSB_NVB) {
                             const int vb = code - G_FULL_G; const uint8_t *cs = c + (s1 ? 64 : 0);
                             double m[8][2]; for (int k = 0; k < 8; k++) rd.V(cs, k, m[k]);
                             for (int v = 0; v < QSB_NV; v++) if (!((v >> vb) & 1)) for (int l = 0; l < L; l++) {
@@ -125,7 +125,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                                 cd x0 = R[v * L + l], x1 = R[(v | (1 << vb)) * L + l];
                                 R[v * L + l] = m00 * x0 + m01 * x1; R[(v | (1 << vb)) * L + l] = m10 * x0 + m11 * x1;
                             }
-                        } else if ((code >= G_DIAG_V && code < G_DIAG_V + 4) || code == G_DIAG_ALL || code == G_DIAG_GEN) {
+                        } else if ((code >= G_DIAG_V && code < G_DIAG_V + QSB_NVB) || code == G_DIAG_ALL || code == G_DIAG_GEN) {
                             double pr[2], pi[2]; const uint8_t *cs = c + (s1 ? 16 : 0);
                             rd.V(cs, 0, pr); rd.V(cs, 1, pi);
                             for (int v = 0; v < QSB_NV; v++) {
@@ -148,7 +148,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                 }
                 const uint8_t *gp = B + (size_t)SG.group_off16 * 16;
                 for (uint32_t g = 0; g < SG.n_groups; g++, gp += (size_t)G16 * 16) {
-                    uint32_t pm[4]; memcpy(pm, gp + 16, 16);
+                    uint32_t pm[QSB_NVB]; for (int j = 0; j < QSB_NVB; j++) memcpy(&pm[j], gp + QSB_GROUP_MASK_OFF(j), 4);
                     for (int vb = 0; vb < QSB_NVB; vb++) {
                         const uint32_t form = gp[vb];
                         if (!form) continue;

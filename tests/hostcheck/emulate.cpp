@@ -100,7 +100,7 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                 cd pend(1.0, 0.0);
                 for (uint32_t i = 0; i < hp.round_op_count[rd]; i++) {
                     const HostOp &op = hp.ops[hp.round_op_begin[rd] + i];
-                    const uint32_t code = op.kind & 0xff, vb = (op.kind >> 8) & 0xf, vmask = (op.kind >> 20) & 0xf;
+                    const uint32_t code = op.kind & 0xff, vb = (op.kind >> 8) & 0xf, vmask = OPK_VMASK(op.kind);
                     const bool mux = (op.kind >> 16) & 1;
                     const bool pred = (gthr[tid] & op.tmask) == op.tmask;
                     if (!pred && !mux) continue;
