@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, GPU call 10: 32 vectors per thread (-DQSB_NVB=5 -DQSB_TB=6, 64-thread CTAs x 4 per SM, 254 registers) against the
-# default geometry (16 vectors, 128-thread CTAs x 4 per SM), same box back to back.
+# default geometry (16 vectors, 128-thread CTAs x 4 per SM), same box back to back; _nvb5t7 = 32 vectors x 128 threads x 2 CTAs/SM (2^13 tiles).
 cd "$(dirname "$0")/../.."
 O=gpurun_out/r2c10; mkdir -p $O
 QSB_LIB_SUFFIX=_nvb5 python -m pytest tests/test_gpu_parity.py -m "gpu and not slow" -x -q > $O/pytest_nvb5.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_nvb5.log
@@ -14,5 +14,8 @@ run "nvb5 f64" env QSB_LIB_SUFFIX=_nvb5 $B --precision 64
 run "default qft f32" $B --workload qft
 run "nvb5 qft f32" env QSB_LIB_SUFFIX=_nvb5 $B --workload qft
 run "nvb5 f32 cap12" env QSB_LIB_SUFFIX=_nvb5 $B --cost-cap 12
+run "nvb5t7 f32" env QSB_LIB_SUFFIX=_nvb5t7 $B
+run "nvb5t7 f64" env QSB_LIB_SUFFIX=_nvb5t7 $B --precision 64
+run "nvb5t7 qft f32" env QSB_LIB_SUFFIX=_nvb5t7 $B --workload qft
 } > $O/bench.log 2>&1
 tail -3 $O/pytest_nvb5.log
