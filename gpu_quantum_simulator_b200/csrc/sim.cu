@@ -288,6 +288,7 @@ extern "C" void qsb_destroy(qsb_t *s)
     if (s->state2) cudaFree(s->state2);
     if (s->staging) cudaFree(s->staging);
     if (s->d_scratch) cudaFree(s->d_scratch);
+    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->evx0) cudaEventDestroy(s->evx0);

@@ -1,5 +1,6 @@
 /* sim.h -- host-side objects behind the opaque handles of qsim_b200.h. */
 #pragma once
+#include <vector>
 #include "common.cuh"
 #include "dense.h"
 
@@ -20,6 +21,9 @@ struct qsb_sim {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};   /* pipelined exchange: peer copies on the copy engines */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
+    /* events of the exchanges of one qsb_execute: created on first use, reused by every later execution (no
+     * cudaEventCreate / Destroy inside the timed loop), destroyed with the handle */
+    std::vector<cudaEvent_t> ev_pool; size_t ev_next = 0;
     void *staging = nullptr; /* device staging for readout (two halves, double-buffered by the downloads) */
     cudaStream_t dl_stream = nullptr;                        /* device -> host copies of the readout pipeline */
     cudaEvent_t dl_filled[2] = {nullptr, nullptr}, dl_copied[2] = {nullptr, nullptr};

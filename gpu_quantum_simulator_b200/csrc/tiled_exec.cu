@@ -30,6 +30,28 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
     TiledPlan *p = new TiledPlan();
     int rc = tiled_schedule(n, prec, g, nloc, rank, opt, start, cops, gphase, p);
     if (rc) { delete p; return rc; }
+    if (g > 0 && opt && opt->reserved[0] == 0) {
+        /* Sharded run, exchange threshold not pinned by the caller: the threshold (how few runnable gates make the
+         * scheduler exchange qubits) trades passes against exchanges, and the best value depends on the circuit.
+         * Plan with a few thresholds and keep the cheapest schedule -- cost in pass units: an exchange pass is NVLink
+         * bound and takes (1 - 2^-g) * local bytes / ~700 GB/s against 2 * local bytes / ~3 TB/s for an ordinary pass
+         * (measured), plus the barrier.  Every rank plans the same circuit and picks the same
+         * schedule (the rank only enters the descriptors, not the structure).  ~10 ms of host time per candidate. */
+        const double xcost = std::max(0.0, (1.0 - 1.0 / (double)(1 << g)) * 2.14 - 1.0) + 0.15;
+        auto cost_of = [&](const TiledPlan *q) {
+            double c = 0;
+            for (auto &hp : q->passes) { if (hp.is_swap) c += 1.0 + xcost; else c += hp.fused_swap ? 1.0 + xcost : 1.0; }
+            return c;
+        };
+        double best = cost_of(p);
+        static const int cand[] = {8, 6, 14};
+        for (int smo : cand) {
+            qsb_options_t o2 = *opt; o2.reserved[0] = smo;
+            TiledPlan *q = new TiledPlan();
+            if (tiled_schedule(n, prec, g, nloc, rank, &o2, start, cops, gphase, q) == QSB_OK && cost_of(q) < best - 1e-9) { best = cost_of(q); delete p; p = q; }
+            else delete q;
+        }
+    }
     uint64_t n_ops = 0, n_rounds = 0, sweeps = 0, swaps = 0;
     for (auto &hp : p->passes) {
         if (hp.is_swap) { swaps++; continue; }
@@ -193,6 +215,14 @@ void tiled_comm_destroy(qsb_sim *s)
     if (s->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy((qsb_nccl_comm_t)s->comm); s->comm = nullptr; }
 }
 
+/* next event of the handle's pool (timing enabled: some bracket the exchange for exchange_ms) */
+static int pool_event(qsb_sim *s, cudaEvent_t *out)
+{
+    if (s->ev_next == s->ev_pool.size()) { cudaEvent_t e; QSB_CUDA(cudaEventCreate(&e)); s->ev_pool.push_back(e); }
+    *out = s->ev_pool[s->ev_next++];
+    return QSB_OK;
+}
+
 static int exchange(qsb_sim *s)
 {
     if (!s->comm) { qsb_set_error("plan needs a qubit exchange but qsb_comm_init was not called"); return QSB_ERR_COMM; }
@@ -248,16 +278,15 @@ static int pipelined_exchange(qsb_sim *s, TiledPlan *p, size_t k_pass, bool have
     for (int q = lo + 1; q < nloc - g; q++) if (std::find(slice_pos.begin(), slice_pos.end(), q) == slice_pos.end()) mid.push_back(q);
     const size_t piece = ((size_t)1 << lo) * AMP;
     cudaEvent_t x0, x1;
-    QSB_CUDA(cudaEventCreate(&x0)); QSB_CUDA(cudaEventCreate(&x1));
+    { int rc = pool_event(s, &x0); if (rc) return rc; rc = pool_event(s, &x1); if (rc) return rc; }
     for (int sl = 0; sl < K; sl++) {
         if (have_pass) {
             int rc = tiled_launch_pass(s, p, k_pass, s->state, s->state, nullptr, (uint64_t)sl * (n_tiles / K), n_tiles / K);
             if (rc) return rc;
         }
-        cudaEvent_t e; QSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        cudaEvent_t e; { int rc = pool_event(s, &e); if (rc) return rc; }
         QSB_CUDA(cudaEventRecord(e, s->stream));
         for (int i = 0; i < NCS; i++) QSB_CUDA(cudaStreamWaitEvent(s->copy_stream[i], e, 0));
-        QSB_CUDA(cudaEventDestroy(e));
         if (sl == K - 1) QSB_CUDA(cudaEventRecord(x0, s->stream));   /* what follows is exposed transfer time */
         /* slice sl = the slicing bits take the value sl (highest slicing bit = highest bit of sl) */
         uint64_t base = 0;
@@ -275,10 +304,9 @@ static int pipelined_exchange(qsb_sim *s, TiledPlan *p, size_t k_pass, bool have
         }
     }
     for (int i = 0; i < NCS; i++) {
-        cudaEvent_t done; QSB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        cudaEvent_t done; { int rc = pool_event(s, &done); if (rc) return rc; }
         QSB_CUDA(cudaEventRecord(done, s->copy_stream[i]));
         QSB_CUDA(cudaStreamWaitEvent(s->stream, done, 0));
-        QSB_CUDA(cudaEventDestroy(done));
     }
     int *flag = (int *)((char *)s->d_scratch + 65536);
     QSB_NCCL(g_nccl.AllReduce(flag, flag + 1, 1, 2 /* ncclInt32 */, 3 /* ncclMin */, (qsb_nccl_comm_t)s->comm, s->stream));
@@ -291,7 +319,8 @@ static int pipelined_exchange(qsb_sim *s, TiledPlan *p, size_t k_pass, bool have
 
 int tiled_execute(qsb_sim *s, TiledPlan *p)
 {
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev;      /* (start, end) pairs that bracket the exchanges; all from the handle's pool */
+    s->ev_next = 0;
     const bool pipelined = s->peers_ok && s->opt.reserved[5] == 3;
     for (size_t k = 0; k < p->passes.size(); k++) {
         if (pipelined && !p->passes[k].is_swap && k + 1 < p->passes.size() && p->passes[k + 1].is_swap) {
@@ -307,7 +336,7 @@ int tiled_execute(qsb_sim *s, TiledPlan *p)
         }
         if (p->passes[k].is_swap) {
             cudaEvent_t a, b;
-            QSB_CUDA(cudaEventCreate(&a)); QSB_CUDA(cudaEventCreate(&b));
+            { int rc = pool_event(s, &a); if (rc) return rc; rc = pool_event(s, &b); if (rc) return rc; }
             QSB_CUDA(cudaEventRecord(a, s->stream));
             int rc = exchange(s);
             if (rc) return rc;
@@ -320,7 +349,7 @@ int tiled_execute(qsb_sim *s, TiledPlan *p)
              * stream is the barrier) the buffers trade places everywhere */
             if (!s->peers_ok) { qsb_set_error("plan has fused exchanges but the peer shards are not mapped"); return QSB_ERR_COMM; }
             cudaEvent_t a, b;
-            QSB_CUDA(cudaEventCreate(&a)); QSB_CUDA(cudaEventCreate(&b));
+            { int rc = pool_event(s, &a); if (rc) return rc; rc = pool_event(s, &b); if (rc) return rc; }
             PeerTab pt; memset(&pt, 0, sizeof pt);
             for (int r = 0; r < s->world; r++) pt.p[r] = (char *)s->peer_state2[r];
             pt.shard_bytes = s->state_bytes; pt.world = (uint32_t)s->world;
@@ -345,7 +374,6 @@ int tiled_execute(qsb_sim *s, TiledPlan *p)
         for (size_t i = 0; i < ev.size(); i += 2) {
             float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
             p->last_exchange_ms += ms;
-            cudaEventDestroy(ev[i]); cudaEventDestroy(ev[i + 1]);
         }
     }
     return QSB_OK;

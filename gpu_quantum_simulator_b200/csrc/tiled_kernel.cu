@@ -24,6 +24,7 @@
  * Reference kernels replaced: kernel_gate / kernel_gate_2 (naive.cu:72-95),
  * kernel_cnot (naive.cu:97-122), kernel_gate_4 (4x4.cu:109-146).
  */
+#include <mutex>
 #include "sim.h"
 #include "tiled.h"
 
@@ -365,19 +366,9 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 const bool pred = ((src_outer & om) == om) && ((tid & h.y) == h.y);
                 if (!two && !pred) continue;   /* controlled gate: the other threads sit this op out */
                 const bool s1 = two && pred;   /* multiplexer: threads that pass use coefficient set 1 */
-                switch (code) {
-                CASE4(G_FULL_G, {
-                    const uint4 *cs = c + (s1 ? 4 : 0);     /* rare form: per-thread constant loads are fine */
-                    V m[8];
-                    T::vec2(cs, 0, m[0], m[1]); T::vec2(cs, 1, m[2], m[3]); T::vec2(cs, 2, m[4], m[5]); T::vec2(cs, 3, m[6], m[7]);
-                    gen_v<R, VB>(re, im, m);
-                })
-                CASE4(G_DIAG_V, {
-                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
-                    diag_v<R, VB>(re, im, pr, pi);
-                })
-                CASE4(G_DIAGA, {
-                    /* merged controlled phases: integer angle sum over the entries this thread satisfies, one sincospi, one multiply */
+                if (code >= G_DIAGA && code < G_DIAGA + QSB_NVB) {
+                    /* merged controlled phases (G_DIAGA): integer angle sum over the entries this thread satisfies, ONE
+                     * sincospi (one copy of its code for all vector bits), then the phase on the vectors whose bit is set */
                     const uint32_t n_e = c[0].x;
                     const uint4 *e = c + 1;
                     typename T::A acc = 0;
@@ -388,7 +379,23 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                         acc += ((tid & eh.x) == eh.x) ? T::ang(eh, e) : (typename T::A)0;
                     }
                     S apr, api; T::turn(acc, apr, api);
-                    diag_v<R, VB>(re, im, T::bc(apr), T::bc(api));
+                    const V vpr = T::bc(apr), vpi = T::bc(api);
+                    switch (code - G_DIAGA) {
+                    CASE4(0, { diag_v<R, VB>(re, im, vpr, vpi); })
+                    default: break;
+                    }
+                    continue;
+                }
+                switch (code) {
+                CASE4(G_FULL_G, {
+                    const uint4 *cs = c + (s1 ? 4 : 0);     /* rare form: per-thread constant loads are fine */
+                    V m[8];
+                    T::vec2(cs, 0, m[0], m[1]); T::vec2(cs, 1, m[2], m[3]); T::vec2(cs, 2, m[4], m[5]); T::vec2(cs, 3, m[6], m[7]);
+                    gen_v<R, VB>(re, im, m);
+                })
+                CASE4(G_DIAG_V, {
+                    V pr, pi; load_phase<R>(c, two, s1, pr, pi);
+                    diag_v<R, VB>(re, im, pr, pi);
                 })
                 case G_DIAG_ALL: {
                     V pr, pi; load_phase<R>(c, two, s1, pr, pi);
@@ -546,8 +553,10 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 template <typename R, int BLOB, bool PEER>
 static int ensure_smem_optin(int device)
 {
+    static std::mutex mu;                 /* handles on different host threads may launch their first pass at the same time */
     static bool attr_set[64] = {false};
     const int dev = device & 63;
+    std::lock_guard<std::mutex> lock(mu);
     if (!attr_set[dev]) {
         QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSB_SMEM_BYTES));
         attr_set[dev] = true;
