@@ -169,7 +169,8 @@ enum {              /* slot forms (one-hot bytes, so the kernel dispatches with 
     S_SKIP = 0,
     S_UNIT_R = 1,   /* real unit form  a[[1,p],[q,r]]: x0 += p x1; x1 = k x1 + q x0     S: p q k a */
     S_UNIT_I = 2,   /* rx unit form    a[[1,ip],[iq,r]]                                 S: p q k a */
-    S_UNIT_H = 4,   /* real unit form with q == 1 (Hadamard-like), unconditional, a == 1:
+    S_UNIT_H = 4,   /* (only with -DQSB_UNIT_H; measured neutral on B200 and left out of the default build to keep the
+                       interpreter's code small, profiles/r2/README.md) real unit form with q == 1 (Hadamard-like), unconditional, a == 1:
                        x0 += p x1; x1 = k x1 + x0 -- 4 instead of 6 packed operations per vector pair   S: p 1 k 1 */
     S_DIAG = 8,     /* phase on the vectors whose bit is set                           S: pr pi   */
     S_XDEF = 16,    /* X (swap of the two halves) under the predicate, DEFERRED: the thread only

@@ -264,7 +264,9 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
     const S c0 = pred ? s.d[0] : s.c[0], c1 = pred ? s.d[1] : s.c[1], c2 = pred ? s.d[2] : s.c[2], c3 = pred ? s.d[3] : s.c[3];
     if (form & S_UNIT_R) { unit_v<R, VB, false>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
     else if (form & S_UNIT_I) { unit_v<R, VB, true>(re, im, c0, c1, c2); psr *= c3; psi *= c3; }
+#ifdef QSB_UNIT_H
     else if (form & S_UNIT_H) unit_h<R, VB>(re, im, c0, c2);
+#endif
     else if (form & S_DIAG) diag_v<R, VB>(re, im, T::bc(c0), T::bc(c1));
     /* S_XDEF alone, or merged into the gate it follows (the planner then gives both the same predicate) */
     if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;

@@ -1371,7 +1371,11 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                                                         same speed on random circuits, 2.4x more rounds on QFT) */
     M.trim_thin = (opt && opt->reserved[2] > 0) ? opt->reserved[2] - 1 : 2;   /* reserved[2] = k+1: trim tail rounds with < k gates (1 = off) */
     M.diaga = !(opt && opt->reserved[4] == 4);       /* reserved[4] = 4: no merged controlled phases G_DIAGA (A/B runs) */
-    M.hform = !(opt && opt->reserved[4] == 3);       /* reserved[4] = 3: no Hadamard-like slot form S_UNIT_H (A/B runs) */
+#ifdef QSB_UNIT_H
+    M.hform = !(opt && opt->reserved[4] == 3);
+#else
+    M.hform = false;                                 /* S_UNIT_H is not compiled into the default kernel */
+#endif       /* reserved[4] = 3: no Hadamard-like slot form S_UNIT_H (A/B runs) */
     M.defer_diag = !(opt && opt->reserved[4] == 1);  /* reserved[4] = 1: do not defer vector-bit phase gates (A/B runs) */
     M.force_top = g > 0 && opt && opt->reserved[5] == 3;        /* reserved[5] = 3: NCCL-style plan executed as a pipelined exchange */
     M.fused_exchange = g > 0 && opt && (opt->reserved[5] == 1 || opt->reserved[5] == 4);   /* reserved[5] = 1 / 4: exchanges fused into a pass (peer stores) */
