@@ -256,3 +256,50 @@ def test_cx_chains_on_one_target_share_a_round():
     assert st["source_gates"] == 2445 and st["rounds"] < 450 and st["passes"] < 60        # was 1011 rounds in 140 passes
     got, rep = helpers.hostcheck_run(q.gates_from_circuit(circ), n, 64)
     assert rep["bad_slots"] == 0 and np.max(np.abs(got - amps)) < 1e-12
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_controlled_phase_ladders_are_merged(precision):
+    """Round 2 (G_DIAGA): a run of controlled phases on one vector bit (a QFT ladder) is lowered to ONE op -- per-thread
+    fixed-point angle sum, one sincospi, one multiply -- instead of one multiply per gate.  The device encoding, read
+    byte for byte by the blob double, must still reproduce the oracle, with and without the merge, and the merge must
+    remove device ops' worth of specials (fewer bytes of pass descriptor is the visible trace on the host)."""
+    n = 18
+    circ = circuits.qft(n)
+    gates = q.gates_from_circuit(circ)
+    want = helpers.oracle_run_circuit(circ, n)
+    helpers.hostcheck_use_blob(True)
+    try:
+        got, rep = helpers.hostcheck_run(gates, n, precision)
+        assert rep["bad_slots"] == 0
+        assert np.max(np.abs(got - want)) < (3e-6 if precision == 32 else 1e-12)
+    finally:
+        helpers.hostcheck_use_blob(False)
+    # a ladder of cp gates onto one target, controls everywhere: exactly the pattern the merge is for
+    ladder = [("h", (0,), ())] + [("cp", (c, 0), (0.37 * c,)) for c in range(1, n)] + [("h", (0,), ())]
+    want = helpers.oracle_run_circuit(ladder, n)
+    for blob in (False, True):
+        helpers.hostcheck_use_blob(blob)
+        got, rep = helpers.hostcheck_run(q.gates_from_circuit(ladder), n, precision)
+        helpers.hostcheck_use_blob(False)
+        assert rep["bad_slots"] == 0
+        assert np.max(np.abs(got - want)) < (3e-6 if blob and precision == 32 else 1e-12)
+
+
+def test_dense_fusion_plans_fewer_sweeps_with_wider_blocks():
+    """QSB_MODE_DENSE (the k = 2..5 experiment of BASELINE.json configuration 4): the host fusion needs no GPU.  Wider
+    blocks -> fewer sweeps; every sweep is one read + one write of the state; a gate wider than k is refused."""
+    circ = circuits.random_layered(24, 20, 12345)
+    gates = q.gates_from_circuit(circ)
+    sweeps = []
+    for k in (1, 2, 3, 4, 5):
+        if k == 1:
+            with pytest.raises(q.QsbError):
+                q.plan_dry_run(24, gates, mode=q.MODE_DENSE, dense_k=1)     # a CX does not fit one qubit
+            continue
+        st = q.plan_dry_run(24, gates, mode=q.MODE_DENSE, dense_k=k)
+        assert st["bytes_moved"] == st["passes"] * 2 * (1 << 24) * 8
+        sweeps.append(st["passes"])
+    assert sweeps == sorted(sweeps, reverse=True) and sweeps[-1] < 0.5 * sweeps[0]
+    tiled = q.plan_dry_run(24, gates)
+    assert tiled["passes"] * 4 < sweeps[-1]                                  # the sparse register-tile schedule: far fewer sweeps
