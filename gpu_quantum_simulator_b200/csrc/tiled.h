@@ -57,6 +57,12 @@
 #define QSB_T_F32 (QSB_T_F64 + 1)      /* tile bits f32: pack + NVB + TB (12)        */
 #define QSB_SLOTS (1 << QSB_T_F64)     /* 16-byte shared-memory slots of a tile       */
 #define QSB_SMEM_BYTES (QSB_SLOTS * 16)
+/* behind the exchange buffer: the per-thread exchange base offsets of the first QSB_SBT_ROUNDS rounds of the pass, computed
+ * once per CTA while its gather loads are in flight (round 2) */
+#ifndef QSB_SBT_ROUNDS
+#define QSB_SBT_ROUNDS 16
+#endif
+#define QSB_SMEM_TOTAL (QSB_SMEM_BYTES + QSB_SBT_ROUNDS * QSB_THREADS * 4)
 #ifndef QSB_CTAS_PER_SM
 #define QSB_CTAS_PER_SM (512 / QSB_THREADS)
 #endif

@@ -337,16 +337,55 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 
     uint32_t xm = 0;   /* deferred X: this thread's register v holds logical vector v ^ xm */
     const uint4 *rp = B + P.rounds_off16;
+#if QSB_SBT_ROUNDS > 0
+    /* While the 16 gather loads are in flight: this thread's exchange base offsets of every round (they depend on the
+     * thread and the round, not on the tile: ~25 instructions and a chain of constant loads per round that would
+     * otherwise sit at the top of each round, between a barrier and the shared-memory loads).  Private slots: each
+     * thread reads back only what it wrote, no synchronisation. */
+    uint32_t *sbt = reinterpret_cast<uint32_t *>(smem + QSB_SMEM_BYTES) + tid;
+    {
+        const int nt = n_rounds < QSB_SBT_ROUNDS ? n_rounds : QSB_SBT_ROUNDS;
+        const uint4 *rq = rp;
+        for (int r = 0; r < nt; r++, rq += sizeof(GRound) / 16) {
+            const GRound &RQ = *reinterpret_cast<const GRound *>(rq);
+            uint32_t b = 0;
+#pragma unroll
+            for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) b ^= RQ.thr_x[j];
+            sbt[r * QSB_THREADS] = b;
+        }
+    }
+#endif
     for (int rd = 0; rd < n_rounds; rd++, rp += sizeof(GRound) / 16) {
         const GRound &RD = *reinterpret_cast<const GRound *>(rp);
         uint32_t sb = 0; /* this thread's smem byte offset: load side in the low half, store side in the high half */
+#if QSB_SBT_ROUNDS > 0
+        if (rd < QSB_SBT_ROUNDS) sb = sbt[rd * QSB_THREADS];
+        else
+#endif
+        {
 #pragma unroll
-        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr_x[j];
+            for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr_x[j];
+        }
 
         if (rd > 0) {
             const uint32_t sl = sb & 0xffffu;
+#ifdef QSB_XOR_BASIS
+            /* the slot map is GF(2)-linear: the 2^NVB vector offsets are the XOR combinations of NVB basis words (one
+             * uniform load + uniform XORs instead of 2^NVB table loads) */
+            uint32_t bl[QSB_NVB];
+#pragma unroll
+            for (int b = 0; b < QSB_NVB; b++) bl[b] = RD.vld_x[1 << b];
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) x ^= bl[b];
+                IO<R>::sload(smem, sl ^ x, re[v], im[v]);
+            }
+#else
 #pragma unroll
             for (int v = 0; v < NV; v++) IO<R>::sload(smem, sl ^ RD.vld_x[v], re[v], im[v]);
+#endif
             __syncthreads(); /* every thread has its registers before anyone overwrites the tile */
         }
 
@@ -508,8 +547,21 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 #pragma unroll
             for (int b = 0; b < QSB_NVB; b++) if ((xm >> b) & 1) ss ^= RD.vst_x[1 << b];
             xm = 0;
+#ifdef QSB_XOR_BASIS
+            uint32_t bs[QSB_NVB];
+#pragma unroll
+            for (int b = 0; b < QSB_NVB; b++) bs[b] = RD.vst_x[1 << b];
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) x ^= bs[b];
+                IO<R>::sstore(smem, ss ^ x, re[v], im[v]);
+            }
+#else
 #pragma unroll
             for (int v = 0; v < NV; v++) IO<R>::sstore(smem, ss ^ RD.vst_x[v], re[v], im[v]);
+#endif
             __syncthreads();
         }
     }
@@ -560,7 +612,7 @@ static int ensure_smem_optin(int device)
     const int dev = device & 63;
     std::lock_guard<std::mutex> lock(mu);
     if (!attr_set[dev]) {
-        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSB_SMEM_BYTES));
+        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSB_SMEM_TOTAL));
         attr_set[dev] = true;
     }
     return QSB_OK;
@@ -574,7 +626,7 @@ static int launch_one(qsb_sim *s, const HostPass &hp, const void *src, void *dst
     if (hp.hdr.n_tiles > 0x7fffffffULL) { qsb_set_error("too many tiles"); return QSB_ERR_ARG; }
     if (ntile == 0) { tile0 = 0; ntile = hp.hdr.n_tiles; }
     const PassBlob<BLOB> *blob = reinterpret_cast<const PassBlob<BLOB> *>(hp.blob.data());
-    k_tile_pass<R, BLOB, PEER><<<(unsigned)ntile, QSB_THREADS, QSB_SMEM_BYTES, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, (uint32_t)tile0);
+    k_tile_pass<R, BLOB, PEER><<<(unsigned)ntile, QSB_THREADS, QSB_SMEM_TOTAL, s->stream>>>(*blob, (const char *)src, (char *)dst, peers, (uint32_t)tile0);
     QSB_CUDA(cudaGetLastError());
     return QSB_OK;
 }
