@@ -369,7 +369,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 
         if (rd > 0) {
             const uint32_t sl = sb & 0xffffu;
-#ifdef QSB_XOR_BASIS
+#ifndef QSB_NO_XOR_BASIS
             /* the slot map is GF(2)-linear: the 2^NVB vector offsets are the XOR combinations of NVB basis words (one
              * uniform load + uniform XORs instead of 2^NVB table loads) */
             uint32_t bl[QSB_NVB];
@@ -547,7 +547,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 #pragma unroll
             for (int b = 0; b < QSB_NVB; b++) if ((xm >> b) & 1) ss ^= RD.vst_x[1 << b];
             xm = 0;
-#ifdef QSB_XOR_BASIS
+#ifndef QSB_NO_XOR_BASIS
             uint32_t bs[QSB_NVB];
 #pragma unroll
             for (int b = 0; b < QSB_NVB; b++) bs[b] = RD.vst_x[1 << b];
