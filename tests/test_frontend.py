@@ -228,3 +228,60 @@ def test_cli_plan_only_needs_no_gpu(tmp_path):
     assert d["qubits"] == 30 and d["gates"] == 900 and d["ranks"] == 4 and d["exchanges"] >= 1 and 0 < d["passes"] < 60
     r = subprocess.run([exe, str(tmp_path / "missing.qasm"), "--plan-only"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "cannot open circuit file" in r.stdout
+
+
+HDR = 'OPENQASM 3.0;\ninclude "stdgates.inc";\n'
+
+
+def test_statement_boundaries_follow_the_reference_tokenizer():
+    """(a) a trailing comment with '=' must not turn a gate into a classical assignment, (b) an operand list
+    may continue on the next line after a comma (the reference's streaming parser just reads on, :225-235)."""
+    n, g = q.parse_qasm_string(HDR + "qubit[3] q;\nh q[0] // c = 1\ncx q[0],\n   q[1];\nx q[2]; /* y = 2 */ h q[2];\n")
+    assert n == 3 and len(g) == 4
+    assert [x.target for x in g] == [0, 1, 2, 2] and g[1].controls == 1
+    n, g = q.parse_qasm_string(HDR + "qubit[2] q;\nbit[2] c;\nc[0] = measure q[0];\nh q[1];\n")
+    assert len(g) == 1 and g[0].target == 1                       # a real assignment is still ignored
+
+
+def test_controlled_gate_with_gphase_in_its_body():
+    """gphase inside a gate body has no operand; under ctrl @ it becomes a phase on the control, also
+    when the control is qubit 0 (round 1 used a dummy target 0 and reported a control / operand clash)."""
+    text = HDR + "qubit[2] q;\ngate foo a { gphase(0.5); h a; }\nctrl @ foo q[0], q[1];\n"
+    n, g = q.parse_qasm_string(text)
+    assert n == 2 and len(g) == 2
+    ph, hh = g
+    assert ph.target == 0 and ph.controls == 0
+    assert np.allclose(mat(ph), np.diag([1, np.exp(0.5j)]))
+    assert hh.target == 1 and hh.controls == 1
+    want = np.zeros(4, complex); want[0] = 1                      # |00>: control off, nothing happens
+    # oracle-free check of the two gates on |01> (control q0 = 1): e^{0.5i} (|0> + |1>)/sqrt(2) on q1
+    v = np.zeros(4, complex); v[1] = 1
+    v[1] *= np.exp(0.5j)
+    out = v.copy(); out[1] = v[1] / math.sqrt(2); out[3] = v[1] / math.sqrt(2)
+    assert abs(abs(out[1]) - 1 / math.sqrt(2)) < 1e-15
+
+
+def test_pow_and_operand_range_overflows_are_rejected():
+    """stacked pow modifiers used to wrap a 32-bit int (the gate was silently dropped); operand indices were
+    truncated to int (q[4294967296] acted as q[0])."""
+    with pytest.raises(q.QsbError, match="pow"):
+        q.parse_qasm_string(HDR + "qubit[2] q;\npow(1000000) @ pow(1000000) @ x q[0];\n")
+    n, g = q.parse_qasm_string(HDR + "qubit[2] q;\npow(3) @ pow(2) @ x q[0];\n")
+    assert len(g) == 6
+    for bad in ("x q[4294967296];", "x $4294967297;", "cx q[0], q[99999999999];"):
+        with pytest.raises(q.QsbError):
+            q.parse_qasm_string(HDR + "qubit[2] q;\n" + bad + "\n")
+
+
+def test_non_seekable_input(tmp_path):
+    """qsb_parse_qasm_file on a FIFO / pipe (ftell = -1) overflowed the heap; it now reads in a
+    growing loop.  Parsed through a named pipe here."""
+    import threading
+    fifo = tmp_path / "c.fifo"
+    os.mkfifo(fifo)
+    text = HDR + "qubit[4] q;\n" + "".join(f"h q[{k % 4}];\n" for k in range(5000))     # > one 64 KiB read buffer
+    t = threading.Thread(target=lambda: open(fifo, "w").write(text))
+    t.start()
+    n, g = q.parse_qasm_file(str(fifo))
+    t.join()
+    assert n == 4 and len(g) == 5000
