@@ -85,9 +85,12 @@ typedef struct qsb_options {
      *   [1] 2 = keep the qubits of phase gates thread-level at any price ("lazy diagonals")
      *   [2] k+1 = trim tail rounds of SM-bound passes that hold fewer than k gates (default k = 2; 1 = off)
      *   [3] fusion-depth cap: stop adding rounds to a pass at this estimated SM cost (unit-form gate units)
-     *   [4] 1 = do not defer phase gates that touch a vector bit; 2 = no 2x2 products of consecutive one-qubit gates
-     *   [5] exchange flavour: 1 fused peer scatter, 2 NCCL all-to-all, 3 pipelined copy-engine exchange
-     *       (0: chosen by qsb_comm_init -- pipelined at 2 ranks, fused beyond, NCCL if peers cannot be mapped)
+     *   [4] 1 = do not defer phase gates that touch a vector bit; 2 = no 2x2 products of consecutive one-qubit gates;
+     *       4 = no merged controlled-phase runs (G_DIAGA)
+     *   [5] exchange flavour: 1 direct fused peer scatter (victims trade places with the rank bits wherever they are),
+     *       2 NCCL all-to-all, 3 pipelined copy-engine exchange, 4 round-1 fused scatter (victims moved to the top local
+     *       positions first)   (0: chosen by qsb_comm_init -- 1, or 2 if the peer shards cannot be mapped)
+     *       With [0] = 0 a sharded plan is built for a few exchange thresholds and the cheapest schedule kept.
      *   [6] 1 = do not sink thread-level phases to later rounds; 2 = first-come tile choice (no hill climbing) */
     int32_t reserved[7];
 } qsb_options_t;
