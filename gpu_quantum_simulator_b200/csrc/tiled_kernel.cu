@@ -272,6 +272,33 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
     if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;
 }
 
+/* The same slot in two steps (-DQSB_SLOT_PIPE): slot_select does everything that depends only on the thread (predicate,
+ * coefficient select, deferred-X toggle, pending scale) and can run BEFORE the packed arithmetic of the previous slot,
+ * so that its dependent chain (LOP3 -> ISETP -> FSEL) hides behind ~100 cycles of FFMA2; slot_math is the arithmetic. */
+template <typename R> struct SlotS { typename VT<R>::S c0, c1, c2; };
+template <typename R, int VB>
+__device__ __forceinline__ void slot_select(uint32_t form, uint32_t pmask, const SlotC<R> &s, uint32_t tw, SlotS<R> &o,
+                                            typename VT<R>::S &psr, typename VT<R>::S &psi, uint32_t &xm)
+{
+    typedef typename VT<R>::S S;
+    const bool pred = (tw & pmask) == pmask;
+    o.c0 = pred ? s.d[0] : s.c[0]; o.c1 = pred ? s.d[1] : s.c[1]; o.c2 = pred ? s.d[2] : s.c[2];
+    const S c3 = pred ? s.d[3] : s.c[3];
+    if (form & (S_UNIT_R | S_UNIT_I)) { psr *= c3; psi *= c3; }
+    if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;
+}
+template <typename R, int VB>
+__device__ __forceinline__ void slot_math(uint32_t form, const SlotS<R> &o, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV])
+{
+    typedef VT<R> T;
+    if (form & S_UNIT_R) unit_v<R, VB, false>(re, im, o.c0, o.c1, o.c2);
+    else if (form & S_UNIT_I) unit_v<R, VB, true>(re, im, o.c0, o.c1, o.c2);
+#ifdef QSB_UNIT_H
+    else if (form & S_UNIT_H) unit_h<R, VB>(re, im, o.c0, o.c2);
+#endif
+    else if (form & S_DIAG) diag_v<R, VB>(re, im, T::bc(o.c0), T::bc(o.c1));
+}
+
 /* PEER: the scatter of a fused-exchange pass -- every amplitude goes straight into the shard of the rank
  * named by its victim bits (peer memory over NVLink), so the qubit exchange costs no extra sweep. */
 template <typename R, int BLOB, bool PEER>
@@ -480,6 +507,21 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 #endif
                     const uint4 *cp = gp + 2;
                     SlotC<R> sa, sc;
+#if defined(QSB_SLOT_PIPE) && QSB_NVB == 4
+                    SlotS<R> ea, eb;
+                    if (f0) slot_fetch<R>(cp, sa);
+                    if (f1) slot_fetch<R>(cp + S16, sc);
+                    if (f0) slot_select<R, 0>(f0, gm.x, sa, tw, ea, psr, psi, xm);
+                    if (f2) slot_fetch<R>(cp + 2 * S16, sa);
+                    if (f1) slot_select<R, 1>(f1, gm.y, sc, tw, eb, psr, psi, xm);
+                    if (f0) slot_math<R, 0>(f0, ea, re, im);
+                    if (f3) slot_fetch<R>(cp + 3 * S16, sc);
+                    if (f2) slot_select<R, 2>(f2, gm.z, sa, tw, ea, psr, psi, xm);
+                    if (f1) slot_math<R, 1>(f1, eb, re, im);
+                    if (f3) slot_select<R, 3>(f3, gm.w, sc, tw, eb, psr, psi, xm);
+                    if (f2) slot_math<R, 2>(f2, ea, re, im);
+                    if (f3) slot_math<R, 3>(f3, eb, re, im);
+#else
                     if (f0) slot_fetch<R>(cp, sa);
                     if (f1) slot_fetch<R>(cp + S16, sc);
                     if (f0) slot_exec<R, 0>(f0, gm.x, sa, re, im, tw, psr, psi, xm);
@@ -493,6 +535,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                     if (f3) slot_exec<R, 3>(f3, gm.w, sc, re, im, tw, psr, psi, xm);
 #if QSB_NVB == 5
                     if (f4) slot_exec<R, 4>(f4, gh.z, sa, re, im, tw, psr, psi, xm);
+#endif
 #endif
                 }
             }
