@@ -25,6 +25,8 @@
  * kernel_cnot (naive.cu:97-122), kernel_gate_4 (4x4.cu:109-146).
  */
 #include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
 #include "sim.h"
 #include "tiled.h"
 
@@ -656,6 +658,14 @@ static int ensure_smem_optin(int device)
     std::lock_guard<std::mutex> lock(mu);
     if (!attr_set[dev]) {
         QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, QSB_SMEM_TOTAL));
+        /* QSB_CTAS_PER_SM resident CTAs need QSB_CTAS_PER_SM x (tile + 1 KiB) of shared memory: ask for the largest carve-out,
+         * or the driver may pick one that fits fewer CTAs than the registers allow (round 2: the 5-CTA build ran 4) */
+        QSB_CUDA(cudaFuncSetAttribute(k_tile_pass<R, BLOB, PEER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (getenv("QSB_VERBOSE_OCC")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tile_pass<R, BLOB, PEER>, QSB_THREADS, QSB_SMEM_TOTAL);
+            fprintf(stderr, "qsim_b200: k_tile_pass<%s, %d, %d>: %d resident CTAs per SM (built for %d)\n", sizeof(R) == 4 ? "float" : "double", BLOB, (int)PEER, nb, QSB_CTAS_PER_SM);
+        }
         attr_set[dev] = true;
     }
     return QSB_OK;
