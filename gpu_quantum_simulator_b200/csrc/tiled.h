@@ -260,14 +260,20 @@ struct GSegment {              /* 16 bytes */
 
 #define QSB_MAX_COND 24        /* distinct outer conditions a pass can name through W */
 
-struct alignas(16) GRound {    /* the kernel steps through the round array in 16-byte units */
-    uint32_t n_seg, seg_off16; /* GSegment array, 16-byte units from the blob start                  */
+/* Blob layout (round 2): everything a round reads lies in one contiguous run -- [GRound][its GSegment table][specials and
+ * groups][thread-phase and angle lists] -- followed by the next round's run, so that a round touches few, adjacent
+ * constant-cache lines and its segment table sits at a fixed distance from its header (no dependent load for its address). */
+struct alignas(16) GRound {
+    uint32_t n_seg, seg_off16; /* GSegment array, 16-byte units from the blob start (== this header + sizeof(GRound)) */
     uint32_t n_tph, tph_off16; /* GTPhase array                                                      */
-    uint32_t flags, n_ang, pad[2]; /* flags bit0: apply the pending scalar at the end of the round; n_ang: GTAngle
+    uint32_t flags, n_ang, next16, pad; /* next16: the next round's GRound, 16-byte units from the blob start; flags bit0: apply the pending scalar at the end of the round; n_ang: GTAngle
                                   entries, stored right after the n_tph GTPhase entries                */
     uint32_t thr_x[QSB_TB];    /* smem byte XOR per thread bit: load side | store side << 16         */
-    uint32_t vld_x[QSB_NV];    /* smem byte XOR per vector, load side                                */
-    uint32_t vst_x[QSB_NV];    /*                            store side                              */
+    /* smem byte XOR per VECTOR BIT, load side / store side: the slot map is GF(2)-linear, so the offset of vector v is
+     * the XOR of the words of the bits set in v.  (Round 1 stored all 2^NVB combinations: 128 bytes more per round of
+     * constant-cache traffic at a kernel whose uniform constant loads miss the SM-level cache 14.5 % of the time.) */
+    uint32_t vld_b[QSB_NVB];
+    uint32_t vst_b[QSB_NVB];
 };
 
 struct GPass {

@@ -375,8 +375,9 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
     {
         const int nt = n_rounds < QSB_SBT_ROUNDS ? n_rounds : QSB_SBT_ROUNDS;
         const uint4 *rq = rp;
-        for (int r = 0; r < nt; r++, rq += sizeof(GRound) / 16) {
+        for (int r = 0; r < nt; r++) {
             const GRound &RQ = *reinterpret_cast<const GRound *>(rq);
+            rq = B + RQ.next16;
             uint32_t b = 0;
 #pragma unroll
             for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) b ^= RQ.thr_x[j];
@@ -384,7 +385,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
         }
     }
 #endif
-    for (int rd = 0; rd < n_rounds; rd++, rp += sizeof(GRound) / 16) {
+    for (int rd = 0; rd < n_rounds; rd++, rp = B + reinterpret_cast<const GRound *>(rp)->next16) {   /* every round's tables are one contiguous run (tiled.h) */
         const GRound &RD = *reinterpret_cast<const GRound *>(rp);
         uint32_t sb = 0; /* this thread's smem byte offset: load side in the low half, store side in the high half */
 #if QSB_SBT_ROUNDS > 0
@@ -398,12 +399,11 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 
         if (rd > 0) {
             const uint32_t sl = sb & 0xffffu;
-#ifndef QSB_NO_XOR_BASIS
             /* the slot map is GF(2)-linear: the 2^NVB vector offsets are the XOR combinations of NVB basis words (one
              * uniform load + uniform XORs instead of 2^NVB table loads) */
             uint32_t bl[QSB_NVB];
 #pragma unroll
-            for (int b = 0; b < QSB_NVB; b++) bl[b] = RD.vld_x[1 << b];
+            for (int b = 0; b < QSB_NVB; b++) bl[b] = RD.vld_b[b];
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 uint32_t x = 0;
@@ -411,17 +411,13 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) x ^= bl[b];
                 IO<R>::sload(smem, sl ^ x, re[v], im[v]);
             }
-#else
-#pragma unroll
-            for (int v = 0; v < NV; v++) IO<R>::sload(smem, sl ^ RD.vld_x[v], re[v], im[v]);
-#endif
             __syncthreads(); /* every thread has its registers before anyone overwrites the tile */
         }
 
         /* ---- the fused gates of this round ---- */
         S psr = S(1), psi = S(0); /* per-thread pending scalar: unit-form scales and thread-level phases */
         const uint32_t n_seg = RD.n_seg;
-        const GSegment *seg = reinterpret_cast<const GSegment *>(B + RD.seg_off16);
+        const GSegment *seg = reinterpret_cast<const GSegment *>(rp + sizeof(GRound) / 16);   /* right behind the header */
         for (uint32_t sg = 0; sg < n_seg; sg++) {
             /* -- specials: generic interpreter -- */
             const uint32_t n_ops = seg[sg].n_special;
@@ -590,12 +586,11 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
             uint32_t ss = sb >> 16;
             /* deferred X: register v holds logical vector v ^ xm; the slot map is GF(2)-linear */
 #pragma unroll
-            for (int b = 0; b < QSB_NVB; b++) if ((xm >> b) & 1) ss ^= RD.vst_x[1 << b];
+            for (int b = 0; b < QSB_NVB; b++) if ((xm >> b) & 1) ss ^= RD.vst_b[b];
             xm = 0;
-#ifndef QSB_NO_XOR_BASIS
             uint32_t bs[QSB_NVB];
 #pragma unroll
-            for (int b = 0; b < QSB_NVB; b++) bs[b] = RD.vst_x[1 << b];
+            for (int b = 0; b < QSB_NVB; b++) bs[b] = RD.vst_b[b];
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 uint32_t x = 0;
@@ -603,10 +598,6 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) x ^= bs[b];
                 IO<R>::sstore(smem, ss ^ x, re[v], im[v]);
             }
-#else
-#pragma unroll
-            for (int v = 0; v < NV; v++) IO<R>::sstore(smem, ss ^ RD.vst_x[v], re[v], im[v]);
-#endif
             __syncthreads();
         }
     }

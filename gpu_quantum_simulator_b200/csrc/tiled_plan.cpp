@@ -1050,11 +1050,7 @@ struct PassBuilder {
             GRound &G = gr[r]; memset(&G, 0, sizeof G);
             G.flags = D.flags;
             for (int j = 0; j < QSB_TB; j++) G.thr_x[j] = ((uint32_t)D.thr[j].ld * 16u) | (((uint32_t)D.thr[j].st * 16u) << 16);
-            for (int v = 0; v < QSB_NV; v++) {
-                uint32_t l = 0, t = 0;
-                for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) { l ^= D.vec[b].ld; t ^= D.vec[b].st; }
-                G.vld_x[v] = l * 16u; G.vst_x[v] = t * 16u;
-            }
+            for (int b = 0; b < QSB_NVB; b++) { G.vld_b[b] = (uint32_t)D.vec[b].ld * 16u; G.vst_b[b] = (uint32_t)D.vec[b].st * 16u; }
             /* predicate masks: source index bit -> thread bit of this round, or outer */
             auto split_mask = [&](uint64_t tmask, uint32_t &tm8, uint64_t &om) {
                 tm8 = 0; om = 0;
@@ -1328,8 +1324,10 @@ struct PassBuilder {
         gp.n_cond = n_cond;
         size_t off = al16(sizeof(GPass));
         gp.rounds_off16 = (uint32_t)(off / 16);
-        off += al16(sizeof(GRound) * nrounds);
+        std::vector<size_t> round_at(nrounds);
         for (int r = 0; r < nrounds; r++) {
+            round_at[r] = off;
+            off += al16(sizeof(GRound));
             gr[r].seg_off16 = (uint32_t)(off / 16);
             const size_t body0 = off + segrec[r].size() * sizeof(GSegment);
             for (const SegRec &sr : segrec[r]) {
@@ -1339,6 +1337,7 @@ struct PassBuilder {
             }
             off = body0 + bodystream[r].size();
             gr[r].tph_off16 = (uint32_t)(off / 16); off += tphstream[r].size() + angstream[r].size();
+            gr[r].next16 = (uint32_t)(off / 16);
         }
         const size_t total = off + 64;   /* slack: the group loop prefetches one group header past the last group */
         if (total > QSB_BLOB_LARGE) { qsb_set_error("internal: pass descriptor of %zu bytes exceeds the limit", total); return QSB_PLAN_OVERFLOW; }
@@ -1346,8 +1345,8 @@ struct PassBuilder {
         std::vector<uint8_t> &b = hp.blob;
         b.assign(total <= QSB_BLOB_SMALL ? QSB_BLOB_SMALL : total <= QSB_BLOB_MEDIUM ? QSB_BLOB_MEDIUM : QSB_BLOB_LARGE, 0);
         memcpy(&b[0], &gp, sizeof gp);
-        memcpy(&b[(size_t)gp.rounds_off16 * 16], gr.data(), sizeof(GRound) * nrounds);
         for (int r = 0; r < nrounds; r++) {
+            memcpy(&b[round_at[r]], &gr[r], sizeof(GRound));
             size_t at = (size_t)gr[r].seg_off16 * 16;
             if (!segstream[r].empty()) memcpy(&b[at], segstream[r].data(), segstream[r].size());
             at += segstream[r].size();

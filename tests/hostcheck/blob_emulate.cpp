@@ -62,12 +62,15 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
             xm[tid] = 0;
         }
         const uint8_t *rp = B + (size_t)P.rounds_off16 * 16;
-        for (uint32_t r = 0; r < P.n_rounds; r++, rp += sizeof(GRound)) {
+        for (uint32_t r = 0; r < P.n_rounds; r++) {
             GRound RD; memcpy(&RD, rp, sizeof RD);
+            if ((size_t)RD.seg_off16 * 16 != (size_t)(rp - B) + sizeof(GRound)) bad++;   /* the kernel finds the segment table right behind the header */
+            rp = B + (size_t)RD.next16 * 16;
             std::vector<uint32_t> sb(QSB_THREADS, 0);
             for (int tid = 0; tid < QSB_THREADS; tid++) for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb[tid] ^= RD.thr_x[j];
             if (r > 0) for (int tid = 0; tid < QSB_THREADS; tid++) for (int v = 0; v < QSB_NV; v++) {
-                const uint32_t a = (sb[tid] & 0xffffu) ^ RD.vld_x[v];
+                uint32_t vx = 0; for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) vx ^= RD.vld_b[b];
+                const uint32_t a = (sb[tid] & 0xffffu) ^ vx;
                 if (a % 16 || a / 16 >= QSB_SLOTS) { bad++; continue; }
                 for (int l = 0; l < L; l++) regs[((size_t)tid * QSB_NV + v) * L + l] = smem[(size_t)(a / 16) * L + l];
             }
@@ -200,10 +203,11 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                 std::vector<int> written(QSB_SLOTS, 0);
                 for (int tid = 0; tid < QSB_THREADS; tid++) {
                     uint32_t ss = sb[tid] >> 16;
-                    for (int b = 0; b < QSB_NVB; b++) if ((xm[tid] >> b) & 1) ss ^= RD.vst_x[1 << b];
+                    for (int b = 0; b < QSB_NVB; b++) if ((xm[tid] >> b) & 1) ss ^= RD.vst_b[b];
                     xm[tid] = 0;
                     for (int v = 0; v < QSB_NV; v++) {
-                        const uint32_t a = ss ^ RD.vst_x[v];
+                        uint32_t vx = 0; for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) vx ^= RD.vst_b[b];
+                        const uint32_t a = ss ^ vx;
                         if (a % 16 || a / 16 >= QSB_SLOTS) { bad++; continue; }
                         written[a / 16]++;
                         for (int l = 0; l < L; l++) smem[(size_t)(a / 16) * L + l] = regs[((size_t)tid * QSB_NV + v) * L + l];
