@@ -203,7 +203,9 @@ enum {              /* special op codes (generic interpreter); V = 8 bytes (f32:
                         whose bit vb is set, A = the sum of the fixed-point angles of the entries this thread satisfies.
                         One sincospi + one packed complex multiply of half the vectors for the whole run, instead of a
                         multiply (+ dispatch) per gate.  Payload: 16 bytes {n_entries, -, -, -}, then n_entries GTAngle
-                        entries (thread mask, outer mask, angle; 16 bytes f32 / 32 bytes f64).  No predicate of its own. */
+                        entries (thread mask, outer mask, angle; 16 bytes f32 / 32 bytes f64).  No predicate of its own.
+                        +QSB_NVB (f32 only): the same for phases on the PACK qubit -- the merged phase multiplies the high
+                        lane of every vector (a run of G_DIAG_ALL ops). */
     G_DIAG_ALL = 40, /* phase on every vector (lane dependent)         V: pr pi       */
     G_DIAG_GEN = 41, /* phase where (v & vmask) == vmask               V: pr pi       */
     G_MATP_R = 42,   /* pack-bit target, real (f32 only)               V: A B         */
@@ -252,6 +254,7 @@ struct GTAngle {
  * instructions) + ~5 per entry) */
 #define QSB_DIAGA_MIN_F32 3
 #define QSB_DIAGA_MIN_F64 6
+#define QSB_DIAGA_MIN_PACK 2   /* pack-qubit runs: a G_DIAG_ALL op multiplies all 2^QSB_NVB vectors (64 packed operations) */
 
 struct GSegment {              /* 16 bytes */
     uint32_t n_special, special_off16;

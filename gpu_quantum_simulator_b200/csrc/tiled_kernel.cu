@@ -52,6 +52,7 @@ template <> struct VT<float> {
     static __device__ __forceinline__ V nmul(V a, V b) { V d; asm("{ .reg .b64 t; .reg .f32 lo, hi; mov.b64 {lo, hi}, %1; neg.f32 lo, lo; neg.f32 hi, hi; mov.b64 t, {lo, hi}; mul.rn.f32x2 %0, t, %2; }" : "=l"(d) : "l"(a), "l"(b)); return d; }
     static __device__ __forceinline__ void nacc(V &acc_, V a, V b) { asm("{ .reg .b64 t; .reg .f32 lo, hi; mov.b64 {lo, hi}, %1; neg.f32 lo, lo; neg.f32 hi, hi; mov.b64 t, {lo, hi}; fma.rn.f32x2 %0, t, %2, %0; }" : "+l"(acc_) : "l"(a), "l"(b)); }
     static __device__ __forceinline__ V bc(float s) { unsigned u = __float_as_uint(s); return ((V)u << 32) | u; }
+    static __device__ __forceinline__ V lanes(float lo, float hi) { return ((V)__float_as_uint(hi) << 32) | __float_as_uint(lo); }
     static __device__ __forceinline__ V swp(V a) { return (a >> 32) | (a << 32); }
     static __device__ __forceinline__ V as_v(uint2 u) { return ((V)u.y << 32) | u.x; }
     /* scalar k of a coefficient set (16-byte units starting at c) */
@@ -80,6 +81,7 @@ template <> struct VT<double> {
     static __device__ __forceinline__ V nmul(V a, V b) { V d; asm("{ .reg .f64 t; neg.f64 t, %1; mul.rn.f64 %0, t, %2; }" : "=d"(d) : "d"(a), "d"(b)); return d; }
     static __device__ __forceinline__ void nacc(V &acc_, V a, V b) { asm("{ .reg .f64 t; neg.f64 t, %1; fma.rn.f64 %0, t, %2, %0; }" : "+d"(acc_) : "d"(a), "d"(b)); }
     static __device__ __forceinline__ V bc(double s) { return s; }
+    static __device__ __forceinline__ V lanes(double, double hi) { return hi; }   /* no pack qubit in f64 tiles: never emitted */
     static __device__ __forceinline__ V swp(V a) { return a; }
     static __device__ __forceinline__ double lohi(unsigned lo, unsigned hi) { return __hiloint2double((int)hi, (int)lo); }
     static __device__ __forceinline__ void scalars4(const uint4 *c, S &a, S &b, S &cc, S &d)
@@ -432,7 +434,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 const bool pred = ((src_outer & om) == om) && ((tid & h.y) == h.y);
                 if (!two && !pred) continue;   /* controlled gate: the other threads sit this op out */
                 const bool s1 = two && pred;   /* multiplexer: threads that pass use coefficient set 1 */
-                if (code >= G_DIAGA && code < G_DIAGA + QSB_NVB) {
+                if (code >= G_DIAGA && code <= G_DIAGA + QSB_NVB) {
                     /* merged controlled phases (G_DIAGA): integer angle sum over the entries this thread satisfies, ONE
                      * sincospi (one copy of its code for all vector bits), then the phase on the vectors whose bit is set */
                     const uint32_t n_e = c[0].x;
@@ -445,6 +447,12 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                         acc += ((tid & eh.x) == eh.x) ? T::ang(eh, e) : (typename T::A)0;
                     }
                     S apr, api; T::turn(acc, apr, api);
+                    if (code == G_DIAGA + QSB_NVB) {                    /* run on the pack qubit: high lane of every vector */
+                        const V lpr = T::lanes(S(1), apr), lpi = T::lanes(S(0), api);
+#pragma unroll
+                        for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], lpr, lpi);
+                        continue;
+                    }
                     const V vpr = T::bc(apr), vpi = T::bc(api);
                     switch (code - G_DIAGA) {
                     CASE4(0, { diag_v<R, VB>(re, im, vpr, vpi); })

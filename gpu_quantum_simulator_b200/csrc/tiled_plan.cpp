@@ -1092,18 +1092,38 @@ struct PassBuilder {
                     const double pr = h.c[0][0][1], pi = h.c[0][1][1];
                     return fabs(pr * pr + pi * pi - 1.0) <= 1e-15;
                 };
-                int open_run[QSB_NVB]; for (int b = 0; b < QSB_NVB; b++) open_run[b] = -1;
+                /* run QSB_NVB: phases whose target is the PACK qubit (OP_DIAG_ALL: low lane 1, high lane the phase) under
+                 * thread-level controls.  Only a matrix on the pack qubit ends it: everything else either is diagonal or
+                 * uses the pack qubit as a control. */
+                auto mergeable_pack = [&](const HostOp &h) {
+                    if ((h.kind & 0xff) != OP_DIAG_ALL || ((h.kind >> 16) & 1)) return false;
+                    if (h.c[0][0][0] != 1.0 || h.c[0][1][0] != 0.0) return false;
+                    const double pr = h.c[0][0][1], pi = h.c[0][1][1];
+                    return fabs(pr * pr + pi * pi - 1.0) <= 1e-15;
+                };
+                int open_run[QSB_NVB + 1]; for (int b = 0; b <= QSB_NVB; b++) open_run[b] = -1;
+                std::vector<char> pack_run;                         /* run id -> it is a pack-qubit run */
                 for (uint32_t k = 0; k < rn; k++) {
                     const HostOp &h = hp.ops[rb + k];
                     const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf;
-                    if (code == OP_TPHASE || code == OP_DIAG_ALL || code == OP_DIAG_GEN || code == OP_MATP_R || code == OP_MATP_G) continue;
+                    if (code == OP_MATP_R || code == OP_MATP_G) { open_run[QSB_NVB] = -1; continue; }
+                    if (code == OP_DIAG_ALL) {
+                        if (mergeable_pack(h)) {
+                            if (open_run[QSB_NVB] < 0) { open_run[QSB_NVB] = (int)runs.size(); runs.emplace_back(); pack_run.push_back(1); }
+                            runs[open_run[QSB_NVB]].push_back(k); run_of[k] = open_run[QSB_NVB];
+                        }
+                        continue;
+                    }
+                    if (code == OP_TPHASE || code == OP_DIAG_GEN) continue;
                     if (mergeable(h)) {
-                        if (open_run[vb] < 0) { open_run[vb] = (int)runs.size(); runs.emplace_back(); }
+                        if (open_run[vb] < 0) { open_run[vb] = (int)runs.size(); runs.emplace_back(); pack_run.push_back(0); }
                         runs[open_run[vb]].push_back(k); run_of[k] = open_run[vb];
                     } else open_run[vb] = -1;
                 }
                 const size_t dga_min = M.diaga ? (f32 ? QSB_DIAGA_MIN_F32 : QSB_DIAGA_MIN_F64) : ((size_t)1 << 30);
-                for (auto &rr : runs) if (rr.size() < dga_min) { for (uint32_t k : rr) run_of[k] = -1; rr.clear(); }
+                const size_t dga_min_pack = M.diaga ? QSB_DIAGA_MIN_PACK : ((size_t)1 << 30);
+                for (size_t i = 0; i < runs.size(); i++)
+                    if (runs[i].size() < (pack_run[i] ? dga_min_pack : dga_min)) { for (uint32_t k : runs[i]) run_of[k] = -1; runs[i].clear(); }
             }
             std::vector<char> run_done(runs.size(), 0);
             /* segment under construction */
@@ -1182,7 +1202,7 @@ struct PassBuilder {
                     }
                     const size_t bytes = 16 + body.size();
                     if (bytes / 16 > 0xffff) { qsb_set_error("internal: merged phase run too long"); return QSB_ERR_ARG; }
-                    uint32_t hdr[4] = {GOPK(G_DIAGA + vb, 0, 0, 0, bytes / 16), 0, 0, 0};
+                    uint32_t hdr[4] = {GOPK(G_DIAGA + (code == OP_DIAG_ALL ? QSB_NVB : vb), 0, 0, 0, bytes / 16), 0, 0, 0};
                     const uint8_t *q = (const uint8_t *)hdr; specials.insert(specials.end(), q, q + 16);
                     specials.insert(specials.end(), body.begin(), body.end());
                     n_special++;

@@ -93,8 +93,9 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                     op += (size_t)(h[0] >> 16) * 16;
                     const uint32_t code = h[0] & 0xff, vmask = GOP_VMASK(h[0]); const bool two = (h[0] >> 8) & 1;
                     const uint64_t om = ((uint64_t)h[3] << 32) | h[2];
-                    if (code >= G_DIAGA && code < G_DIAGA + QSB_NVB) {   /* merged controlled phases: per-thread fixed-point angle sum, one phase */
-                        const int vb = code - G_DIAGA;
+                    if (code >= G_DIAGA && code <= G_DIAGA + QSB_NVB) {   /* merged controlled phases: per-thread fixed-point angle sum, one phase */
+                        const int vb = code - G_DIAGA;                     /* == QSB_NVB: run on the pack qubit (high lane of every vector) */
+                        if (vb == QSB_NVB && !f32) bad++;
                         uint32_t n_e; memcpy(&n_e, c, 4);
                         const size_t stride = f32 ? 16 : 32;
                         if (two || h[1] || om || (size_t)(h[0] >> 16) != 2 + (size_t)n_e * (stride / 16)) bad++;
@@ -110,7 +111,8 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                             const double PI_ = 3.14159265358979323846;
                             const cd ph(cos(PI_ * half_turns), sin(PI_ * half_turns));
                             cd *R = &regs[(size_t)tid * QSB_NV * L];
-                            for (int v = 0; v < QSB_NV; v++) if ((v >> vb) & 1) for (int l = 0; l < L; l++) R[v * L + l] *= ph;
+                            if (vb == QSB_NVB) { for (int v = 0; v < QSB_NV; v++) R[v * L + (L - 1)] *= ph; }
+                            else for (int v = 0; v < QSB_NV; v++) if ((v >> vb) & 1) for (int l = 0; l < L; l++) R[v * L + l] *= ph;
                         }
                         continue;
                     }
