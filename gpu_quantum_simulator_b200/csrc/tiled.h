@@ -254,7 +254,9 @@ struct GTAngle {
  * instructions) + ~5 per entry) */
 #define QSB_DIAGA_MIN_F32 3
 #define QSB_DIAGA_MIN_F64 6
+#ifndef QSB_DIAGA_MIN_PACK     /* A/B builds pass a huge value: no pack-qubit runs */
 #define QSB_DIAGA_MIN_PACK 2   /* pack-qubit runs: a G_DIAG_ALL op multiplies all 2^QSB_NVB vectors (64 packed operations) */
+#endif
 
 struct GSegment {              /* 16 bytes */
     uint32_t n_special, special_off16;

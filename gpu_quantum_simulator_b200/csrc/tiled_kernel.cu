@@ -447,7 +447,7 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                         acc += ((tid & eh.x) == eh.x) ? T::ang(eh, e) : (typename T::A)0;
                     }
                     S apr, api; T::turn(acc, apr, api);
-                    if (code == G_DIAGA + QSB_NVB) {                    /* run on the pack qubit: high lane of every vector */
+                    if (sizeof(R) == 4 && code == G_DIAGA + QSB_NVB) {  /* run on the pack qubit: high lane of every vector */
                         const V lpr = T::lanes(S(1), apr), lpi = T::lanes(S(0), api);
 #pragma unroll
                         for (int v = 0; v < NV; v++) cmul_inplace<R>(re[v], im[v], lpr, lpi);

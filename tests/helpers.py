@@ -19,9 +19,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 REFERENCE_DIR = "/root/reference"
 
 
-def _build(path, directory):
-    if not os.path.exists(path):
+_made = set()
+
+
+def _build(path, directory, always=False):
+    """always: let make decide (once per process) -- the host test double links the product planner, so a stale build
+    would silently test yesterday's planner."""
+    if not os.path.exists(path) or (always and directory not in _made):
         subprocess.run(["make", "-C", directory], check=True, capture_output=True)
+    _made.add(directory)
     return path
 
 
@@ -120,15 +126,22 @@ def ref_run_circuit(circ, n):
 def hostcheck_use_blob(on):
     """Switch the host test double between the planner's logical tables (False) and the DEVICE ENCODING, i.e. the
     kernel-parameter blob exactly as k_tile_pass reads it (True)."""
-    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck")))
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
     L.qsb_hostcheck_use_blob(1 if on else 0)
+
+
+def hostcheck_blob_code_count(code, reset=False):
+    """How many special ops with this code (tiled.h G_*) the blob double has interpreted since the last reset."""
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
+    L.qsb_hostcheck_blob_code_count.restype = C.c_ulong
+    return int(L.qsb_hostcheck_blob_code_count(int(code), 1 if reset else 0))
 
 
 def hostcheck_run(circ_gates, n, precision=32, low_bits=0, state=None):
     """Schedule with the product planner, interpret the tables on the host (tests/hostcheck).
     -> (complex128 state in LOGICAL order, report dict)"""
     from gpu_quantum_simulator_b200 import Gate
-    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck")))
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
     L.qsb_hostcheck_run.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(Gate), C.c_size_t, C.c_void_p,
                                     C.POINTER(C.c_int), C.c_void_p]
     L.qsb_hostcheck_run.restype = C.c_int
@@ -201,7 +214,7 @@ def parse_reference_style_file(path):
 # ---- sharded schedules on the host -------------------------------------------------------------
 def _hc():
     from gpu_quantum_simulator_b200 import Gate
-    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck")))
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
     L.qsb_hostcheck_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Gate), C.c_size_t]
     L.qsb_hostcheck_plan.restype = C.c_void_p
     L.qsb_hostcheck_plan_fused.argtypes = L.qsb_hostcheck_plan.argtypes

@@ -30,6 +30,15 @@ struct Rd {
 }
 
 /* returns the number of inconsistencies found (bad slot, out-of-range address, unknown code) */
+/* how many special ops of each code the blob double has interpreted (tests ask whether a lowering was actually used) */
+static unsigned long g_code_count[256];
+extern "C" unsigned long qsb_hostcheck_blob_code_count(int code, int reset)
+{
+    const unsigned long v = g_code_count[code & 0xff];
+    if (reset) for (auto &c : g_code_count) c = 0;
+    return v;
+}
+
 int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, cd *const *outs)
 {
     int bad = 0;
@@ -93,6 +102,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                     op += (size_t)(h[0] >> 16) * 16;
                     const uint32_t code = h[0] & 0xff, vmask = GOP_VMASK(h[0]); const bool two = (h[0] >> 8) & 1;
                     const uint64_t om = ((uint64_t)h[3] << 32) | h[2];
+                    g_code_count[code]++;
                     if (code >= G_DIAGA && code <= G_DIAGA + QSB_NVB) {   /* merged controlled phases: per-thread fixed-point angle sum, one phase */
                         const int vb = code - G_DIAGA;                     /* == QSB_NVB: run on the pack qubit (high lane of every vector) */
                         if (vb == QSB_NVB && !f32) bad++;

@@ -258,6 +258,31 @@ def test_cx_chains_on_one_target_share_a_round():
     assert rep["bad_slots"] == 0 and np.max(np.abs(got - amps)) < 1e-12
 
 
+def test_phase_ladders_onto_the_pack_qubit_are_merged():
+    """G_DIAGA + QSB_NVB (f32): controlled phases whose target sits on the PACK qubit (the two lanes of a packed
+    register) and whose controls are thread / CTA bits used to cost one multiply of all 16 vectors each (G_DIAG_ALL);
+    a run of them is one angle sum + one multiply.  The byte-exact double must see the merged code and still
+    reproduce the oracle; f64 tiles have no pack qubit and must never carry it."""
+    G_DIAGA, G_DIAG_ALL, NVB = 32, 40, 4
+    n = 18
+    for circ in (circuits.qft(n),
+                 [("h", (q0,), ()) for q0 in range(n)] + [("cp", (c, 0), (0.21 * c + 0.1,)) for c in range(1, n)] + [("h", (0,), ())]):
+        want = helpers.oracle_run_circuit(circ, n)
+        seen = {}
+        for precision in (32, 64):
+            helpers.hostcheck_use_blob(True)
+            helpers.hostcheck_blob_code_count(0, reset=True)
+            try:
+                got, rep = helpers.hostcheck_run(q.gates_from_circuit(circ), n, precision)
+                seen[precision] = (helpers.hostcheck_blob_code_count(G_DIAGA + NVB), helpers.hostcheck_blob_code_count(G_DIAG_ALL))
+            finally:
+                helpers.hostcheck_use_blob(False)
+            assert rep["bad_slots"] == 0
+            assert np.max(np.abs(got - want)) < (3e-6 if precision == 32 else 1e-12)
+        assert seen[64] == (0, 0), seen
+        assert seen[32][0] > 0, seen          # the ladder onto qubit 0 (the pack qubit of the first pass) is merged
+
+
 @pytest.mark.parametrize("precision", [32, 64])
 def test_controlled_phase_ladders_are_merged(precision):
     """Round 2 (G_DIAGA): a run of controlled phases on one vector bit (a QFT ladder) is lowered to ONE op -- per-thread
