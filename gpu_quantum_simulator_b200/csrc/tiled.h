@@ -234,11 +234,11 @@ struct GTPhase {               /* thread-level phase, applied through the pendin
  * fixed-point fraction of a turn.  The kernel adds the angles of the entries a thread satisfies with integer
  * adds (exact, wraps modulo one turn) and pays ONE sincospi per round instead of a complex multiply per entry.
  * f32 passes store 16-byte entries (ang32 = the top 32 bits), f64 passes the full 32 bytes. */
-struct GTAngle {
-    uint32_t tmask, ang32;
-    uint64_t omask;
-    uint64_t ang64, pad;
-};
+struct GTAngle32 { uint32_t mask, ang32; };                /* f32 passes: two per 16-byte unit (lists are padded with a zero entry) */
+struct GTAngle64 { uint32_t mask, pad; uint64_t ang64; };  /* f64 passes */
+/* mask is over the per-thread PREDICATE WORD (the one slot predicates test): bits 0..QSB_TB-1 = threadIdx.x, bit
+ * QSB_TB + i = outer condition GPass::cond[i]; every outer control of an angle entry takes a single-bit condition (shared
+ * with the slots that test the same bit).  An entry that finds the table full stays a plain phase op. */
 /* Fewer qualifying phases in a round: they stay GTPhase entries.  Break-even measured on B200 (profiles/
  * r1h_angle_ab.txt): an entry costs ~12 instructions as a complex multiply and ~5 as an angle, the sincospi
  * ~40 (f32) / ~150 (f64); with a threshold of 4 the 30 q layered circuit lost 1.8 % (f32) and 4.8 % (f64). */

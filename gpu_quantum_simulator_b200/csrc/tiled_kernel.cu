@@ -64,10 +64,13 @@ template <> struct VT<float> {
     static __device__ __forceinline__ void vec2(const uint4 *c, int k, V &x, V &y) { const uint4 u = c[k]; x = ((V)u.y << 32) | u.x; y = ((V)u.w << 32) | u.z; }
     static __device__ __forceinline__ void tph(const uint4 u, S &pr, S &pi) { pr = __uint_as_float(u.x); pi = __uint_as_float(u.y); }
     enum { SET4 = 1 };   /* 16-byte units per 4-scalar coefficient set */
-    /* GTAngle entries: 16 bytes, the angle is the top 32 bits of the turn fraction */
+    /* angle entries (GTAngle32): 8 bytes {mask over the predicate word tw, top 32 bits of the turn fraction}, TWO per 16-byte unit */
     typedef uint32_t A;
-    enum { ANG16 = 1 };
-    static __device__ __forceinline__ A ang(const uint4 h, const uint4 *) { return h.y; }
+    static __device__ __forceinline__ void ang_acc(const uint4 u, uint32_t aw, A &acc)
+    {
+        acc += ((aw & u.x) == u.x) ? u.y : 0u;
+        acc += ((aw & u.z) == u.z) ? u.w : 0u;
+    }
     static __device__ __forceinline__ void turn(A acc, S &c, S &s) { sincospif((float)(int)acc * 4.656612873077393e-10f, &s, &c); }   /* acc / 2^31 half-turns */
 };
 template <> struct VT<double> {
@@ -92,9 +95,12 @@ template <> struct VT<double> {
     static __device__ __forceinline__ void vec2(const uint4 *c, int k, V &x, V &y) { const uint4 u = c[k]; x = lohi(u.x, u.y); y = lohi(u.z, u.w); }
     static __device__ __forceinline__ void tph(const uint4 u, S &pr, S &pi) { pr = lohi(u.x, u.y); pi = lohi(u.z, u.w); }
     enum { SET4 = 2 };
+    /* angle entries (GTAngle64): 16 bytes {mask, -, 64-bit turn fraction}, one per unit */
     typedef uint64_t A;
-    enum { ANG16 = 2 };
-    static __device__ __forceinline__ A ang(const uint4, const uint4 *e) { const uint4 w = e[1]; return ((uint64_t)w.y << 32) | w.x; }
+    static __device__ __forceinline__ void ang_acc(const uint4 u, uint32_t aw, A &acc)
+    {
+        acc += ((aw & u.x) == u.x) ? (((uint64_t)u.w << 32) | u.z) : 0ull;
+    }
     static __device__ __forceinline__ void turn(A acc, S &c, S &s) { sincospi((double)(long long)acc * 1.0842021724855044e-19, &s, &c); }   /* acc / 2^63 half-turns */
 };
 
@@ -188,6 +194,14 @@ __device__ __forceinline__ void load_phase(const uint4 *c, bool two, bool s1, ty
     typedef VT<R> T;
     T::vec2(c, 0, pr, pi);
     if (two) { typename T::V pr1, pi1; T::vec2(c, 1, pr1, pi1); if (s1) { pr = pr1; pi = pi1; } }
+}
+
+/* phase on the vectors v with (v & VM) == VM (a controlled phase between vector-bit qubits) */
+template <typename R, int VM>
+__device__ __forceinline__ void diag_gen(typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV], typename VT<R>::V pr, typename VT<R>::V pi)
+{
+#pragma unroll
+    for (int v = 0; v < NV; v++) if ((v & VM) == VM) cmul_inplace<R>(re[v], im[v], pr, pi);
 }
 
 /* 2x2 on the pack bit (f32 only): out = A * x + B * swap(x), A = (m00, m11), B = (m01, m10) */
@@ -423,11 +437,12 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
         for (uint32_t sg = 0; sg < n_seg; sg++) {
             /* -- specials: generic interpreter -- */
             const uint32_t n_ops = seg[sg].n_special;
-            const uint4 *op = B + seg[sg].special_off16;
+            uint32_t opi = seg[sg].special_off16;      /* an INDEX into the descriptor, not a pointer: keeps every load a constant-bank load */
             for (uint32_t i = 0; i < n_ops; i++) {
-                const uint4 h = *op;
-                const uint4 *c = op + 1;
-                op += h.x >> 16;
+                const uint4 h = B[opi];
+                const uint32_t ci = opi + 1;
+                const uint4 *c = B + ci;
+                opi += h.x >> 16;
                 const uint32_t code = h.x & 0xffu;
                 const uint64_t om = ((uint64_t)h.w << 32) | h.z;
                 const bool two = (h.x >> 8) & 1u;
@@ -437,15 +452,9 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                 if (code >= G_DIAGA && code <= G_DIAGA + QSB_NVB) {
                     /* merged controlled phases (G_DIAGA): integer angle sum over the entries this thread satisfies, ONE
                      * sincospi (one copy of its code for all vector bits), then the phase on the vectors whose bit is set */
-                    const uint32_t n_e = c[0].x;
-                    const uint4 *e = c + 1;
+                    const uint32_t n_u = B[ci].x;                       /* 16-byte units of angle entries */
                     typename T::A acc = 0;
-                    for (uint32_t k = 0; k < n_e; k++, e += T::ANG16) {
-                        const uint4 eh = e[0];
-                        const uint64_t eom = ((uint64_t)eh.w << 32) | eh.z;
-                        if ((src_outer & eom) != eom) continue;          /* uniform */
-                        acc += ((tid & eh.x) == eh.x) ? T::ang(eh, e) : (typename T::A)0;
-                    }
+                    for (uint32_t k = 0; k < n_u; k++) T::ang_acc(B[ci + 1 + k], tw, acc);
                     S apr, api; T::turn(acc, apr, api);
                     if (sizeof(R) == 4 && code == G_DIAGA + QSB_NVB) {  /* run on the pack qubit: high lane of every vector */
                         const V lpr = T::lanes(S(1), apr), lpi = T::lanes(S(0), api);
@@ -478,10 +487,18 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                     break;
                 }
                 case G_DIAG_GEN: {
-                    const uint32_t vmask = GOP_VMASK(h.x);   /* uniform: one predicated sweep over the vectors, one copy of the code */
+                    const uint32_t vmask = GOP_VMASK(h.x);   /* uniform */
                     V pr, pi; load_phase<R>(c, two, s1, pr, pi);
+#if QSB_NVB == 4
+                    /* one copy per mask: only the 4 / 2 / 1 vectors the mask selects are touched (a predicated sweep over
+                     * all 16 costs 150 instructions per op -- 21 % of a QFT pass, profiles/r2/qft_pass_ncu_summary.txt) */
+#define QSB_DG(m) case m: diag_gen<R, m>(re, im, pr, pi); break;
+                    switch (vmask) { QSB_DG(3) QSB_DG(5) QSB_DG(6) QSB_DG(9) QSB_DG(10) QSB_DG(12) QSB_DG(7) QSB_DG(11) QSB_DG(13) QSB_DG(14) QSB_DG(15) default: break; }
+#undef QSB_DG
+#else
 #pragma unroll
                     for (int v = 0; v < NV; v++) if ((v & vmask) == vmask) cmul_inplace<R>(re[v], im[v], pr, pi);
+#endif
                     break;
                 }
                 case G_MATP_R: {
@@ -549,12 +566,12 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
         /* ---- thread-level phases of this round ---- */
         {
             const uint32_t n_tph = RD.n_tph;
-            const uint4 *e = B + RD.tph_off16;
-            for (uint32_t i = 0; i < n_tph; i++, e += 2) {
-                const uint4 h = e[0];
+            const uint32_t ti = RD.tph_off16;
+            for (uint32_t i = 0; i < n_tph; i++) {
+                const uint4 h = B[ti + 2 * i];
                 const uint64_t om = ((uint64_t)h.w << 32) | h.z;
                 if ((src_outer & om) != om) continue;          /* uniform */
-                S pr, pi; T::tph(e[1], pr, pi);
+                S pr, pi; T::tph(B[ti + 2 * i + 1], pr, pi);
                 if ((tid & h.x) != h.x) { pr = S(1); pi = S(0); }
                 const S nr = psr * pr - psi * pi;
                 psi = psr * pi + psi * pr; psr = nr;
@@ -565,14 +582,10 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 #else
             const uint32_t n_ang = RD.n_ang;
 #endif
-            if (n_ang) {
+            if (n_ang) {                                               /* n_ang: 16-byte units */
                 typename T::A acc = 0;
-                for (uint32_t i = 0; i < n_ang; i++, e += T::ANG16) {
-                    const uint4 h = e[0];
-                    const uint64_t om = ((uint64_t)h.w << 32) | h.z;
-                    if ((src_outer & om) != om) continue;          /* uniform */
-                    acc += ((tid & h.x) == h.x) ? T::ang(h, e) : (typename T::A)0;
-                }
+                const uint32_t ai = ti + 2 * n_tph;
+                for (uint32_t i = 0; i < n_ang; i++) T::ang_acc(B[ai + i], tw, acc);
                 S pr, pi; T::turn(acc, pr, pi);
                 const S nr = psr * pr - psi * pi;
                 psi = psr * pi + psi * pr; psr = nr;

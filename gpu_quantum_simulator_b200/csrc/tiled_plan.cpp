@@ -1045,6 +1045,23 @@ struct PassBuilder {
         std::vector<std::vector<SegRec>> segrec(nrounds);
         const int SET16 = QSB_SET16(f32), GROUP16 = QSB_GROUP16(f32);
         uint32_t n_cond = 0;
+        /* angle entries (round-level thread phases and merged phase runs): fixed-point turn fraction + ONE 32-bit mask over
+         * the per-thread predicate word (thread bits, then the pass's outer-condition bits: angle_mask below) */
+        auto turn_fraction = [](double pr, double pi) {   /* e^{2 pi i f}, f as a 64-bit fixed-point fraction of a turn */
+            long double turns = (long double)atan2(pi, pr) / (2.0L * 3.14159265358979323846264338327950288L);
+            /* exact fractions for the phases circuits are made of (-1, +-i, e^{i pi/4}, pi/2^k ladders) */
+            if (pi == 0.0) turns = pr > 0 ? 0.0L : 0.5L;
+            else if (pr == 0.0) turns = pi > 0 ? 0.25L : 0.75L;
+            turns -= floorl(turns);
+            long double scaled = roundl(ldexpl(turns, 64));
+            if (scaled >= ldexpl(1.0L, 64)) scaled = 0.0L;
+            return (uint64_t)scaled;
+        };
+        auto put_angle = [&](std::vector<uint8_t> &o, uint32_t m32, uint64_t ang64) {
+            if (f32) { GTAngle32 e; e.mask = m32; e.ang32 = (uint32_t)((ang64 + 0x80000000ULL) >> 32);   /* top 32 bits, rounded; wraps to 0 at one turn */
+                       const uint8_t *q = (const uint8_t *)&e; o.insert(o.end(), q, q + sizeof e); }
+            else { GTAngle64 e; e.mask = m32; e.pad = 0; e.ang64 = ang64; const uint8_t *q = (const uint8_t *)&e; o.insert(o.end(), q, q + sizeof e); }
+        };
         for (int r = 0; r < nrounds; r++) {
             const DevRound &D = hp.rounds[r];
             GRound &G = gr[r]; memset(&G, 0, sizeof G);
@@ -1068,6 +1085,17 @@ struct PassBuilder {
                 for (uint32_t i = 0; i < n_cond; i++) if (gp.cond[i] == om) { wbits = 1u << i; return true; }
                 if (n_cond >= QSB_MAX_COND) return false;
                 gp.cond[n_cond] = om; wbits = 1u << n_cond; n_cond++;
+                return true;
+            };
+            /* mask of an angle entry over the predicate word: thread bits + one single-bit outer condition per outer control.
+             * false if the outer-condition table is full (the caller keeps the gate in its plain form) */
+            auto angle_mask = [&](uint32_t tm8, uint64_t om, uint32_t &m32) {
+                m32 = tm8;
+                for (uint64_t m = om; m; m &= m - 1) {
+                    uint32_t wb;
+                    if (!cond_bit(m & (~m + 1), wb)) return false;
+                    m32 |= wb << QSB_TB;
+                }
                 return true;
             };
             std::vector<uint8_t> &ts = tphstream[r];
@@ -1107,15 +1135,17 @@ struct PassBuilder {
                     const HostOp &h = hp.ops[rb + k];
                     const int code = h.kind & 0xff, vb = (h.kind >> 8) & 0xf;
                     if (code == OP_MATP_R || code == OP_MATP_G) { open_run[QSB_NVB] = -1; continue; }
+                    uint32_t tmm, amm; uint64_t omm;
+                    split_mask(h.tmask, tmm, omm);
                     if (code == OP_DIAG_ALL) {
-                        if (mergeable_pack(h)) {
+                        if (mergeable_pack(h) && angle_mask(tmm, omm, amm)) {
                             if (open_run[QSB_NVB] < 0) { open_run[QSB_NVB] = (int)runs.size(); runs.emplace_back(); pack_run.push_back(1); }
                             runs[open_run[QSB_NVB]].push_back(k); run_of[k] = open_run[QSB_NVB];
                         }
                         continue;
                     }
                     if (code == OP_TPHASE || code == OP_DIAG_GEN) continue;
-                    if (mergeable(h)) {
+                    if (mergeable(h) && angle_mask(tmm, omm, amm)) {
                         if (open_run[vb] < 0) { open_run[vb] = (int)runs.size(); runs.emplace_back(); pack_run.push_back(0); }
                         runs[open_run[vb]].push_back(k); run_of[k] = open_run[vb];
                     } else open_run[vb] = -1;
@@ -1126,6 +1156,7 @@ struct PassBuilder {
                     if (runs[i].size() < (pack_run[i] ? dga_min_pack : dga_min)) { for (uint32_t k : runs[i]) run_of[k] = -1; runs[i].clear(); }
             }
             std::vector<char> run_done(runs.size(), 0);
+            unsigned tr_slot = 0, tr_xmerge = 0, tr_run = 0, tr_run_members = 0, tr_code[G_NCODES] = {0};   /* QSB_PLAN_TRACE */
             /* segment under construction */
             std::vector<uint8_t> specials; uint32_t n_special = 0;
             std::vector<std::vector<uint8_t>> groups;       /* each QSB_GROUP16 * 16 bytes */
@@ -1148,21 +1179,9 @@ struct PassBuilder {
                 const bool mux = (h.kind >> 16) & 1;
                 uint32_t tm8; uint64_t om;
                 split_mask(h.tmask, tm8, om);
-                if (code == OP_TPHASE && use_angles && is_unit_phase(h)) {
-                    GTAngle e; memset(&e, 0, sizeof e);
-                    e.tmask = tm8; e.omask = om;
-                    long double turns = (long double)atan2(h.tph[1], h.tph[0]) / (2.0L * 3.14159265358979323846264338327950288L);
-                    /* exact fractions for the phases circuits are made of (-1, +-i, e^{i pi/4}, pi/2^k ladders) */
-                    if (h.tph[1] == 0.0) turns = h.tph[0] > 0 ? 0.0L : 0.5L;
-                    else if (h.tph[0] == 0.0) turns = h.tph[1] > 0 ? 0.25L : 0.75L;
-                    turns -= floorl(turns);
-                    long double scaled = roundl(ldexpl(turns, 64));
-                    if (scaled >= ldexpl(1.0L, 64)) scaled = 0.0L;
-                    e.ang64 = (uint64_t)scaled;
-                    /* f32 passes read the top 32 bits, rounded to nearest */
-                    const uint64_t r32 = (e.ang64 + 0x80000000ULL) >> 32;
-                    e.ang32 = (uint32_t)r32;     /* wraps to 0 at one full turn */
-                    const uint8_t *q = (const uint8_t *)&e; angstream[r].insert(angstream[r].end(), q, q + (f32 ? 16 : 32));
+                uint32_t am32 = 0;
+                if (code == OP_TPHASE && use_angles && is_unit_phase(h) && angle_mask(tm8, om, am32)) {
+                    put_angle(angstream[r], am32, turn_fraction(h.tph[0], h.tph[1]));
                     n_ang++;
                     continue;
                 }
@@ -1180,26 +1199,20 @@ struct PassBuilder {
                     const int run = run_of[k - rb];
                     if (run_done[run]) continue;
                     run_done[run] = 1;
+                    tr_run++; tr_run_members += (unsigned)runs[run].size();
                     if (!groups.empty()) close_segment();
-                    std::vector<uint8_t> body(16, 0);
-                    const uint32_t n_e = (uint32_t)runs[run].size();
-                    memcpy(body.data(), &n_e, 4);
+                    std::vector<uint8_t> ents;
                     for (uint32_t km : runs[run]) {
                         const HostOp &hm = hp.ops[rb + km];
-                        uint32_t tmm; uint64_t omm; split_mask(hm.tmask, tmm, omm);
-                        GTAngle e; memset(&e, 0, sizeof e);
-                        e.tmask = tmm; e.omask = omm;
-                        const double pr = hm.c[0][0][1], pi = hm.c[0][1][1];
-                        long double turns = (long double)atan2(pi, pr) / (2.0L * 3.14159265358979323846264338327950288L);
-                        if (pi == 0.0) turns = pr > 0 ? 0.0L : 0.5L;
-                        else if (pr == 0.0) turns = pi > 0 ? 0.25L : 0.75L;
-                        turns -= floorl(turns);
-                        long double scaled = roundl(ldexpl(turns, 64));
-                        if (scaled >= ldexpl(1.0L, 64)) scaled = 0.0L;
-                        e.ang64 = (uint64_t)scaled;
-                        e.ang32 = (uint32_t)((e.ang64 + 0x80000000ULL) >> 32);
-                        const uint8_t *q = (const uint8_t *)&e; body.insert(body.end(), q, q + (f32 ? 16 : 32));
+                        uint32_t tmm, amm; uint64_t omm; split_mask(hm.tmask, tmm, omm);
+                        if (!angle_mask(tmm, omm, amm)) { qsb_set_error("internal: angle word overflow in a merged run"); return QSB_ERR_ARG; }   /* the pre-scan reserved the bits */
+                        put_angle(ents, amm, turn_fraction(hm.c[0][0][1], hm.c[0][1][1]));
                     }
+                    pad16(ents);                                  /* f32: an odd count ends with a zero entry (adds nothing) */
+                    std::vector<uint8_t> body(16, 0);
+                    const uint32_t n_u = (uint32_t)(ents.size() / 16);
+                    memcpy(body.data(), &n_u, 4);
+                    body.insert(body.end(), ents.begin(), ents.end());
                     const size_t bytes = 16 + body.size();
                     if (bytes / 16 > 0xffff) { qsb_set_error("internal: merged phase run too long"); return QSB_ERR_ARG; }
                     uint32_t hdr[4] = {GOPK(G_DIAGA + (code == OP_DIAG_ALL ? QSB_NVB : vb), 0, 0, 0, bytes / 16), 0, 0, 0};
@@ -1255,9 +1268,11 @@ struct PassBuilder {
                         if ((pf & (S_UNIT_R | S_UNIT_I | S_UNIT_H | S_DIAG)) && !(pf & S_XDEF) && (ppm == pm_new || prev_uncond)) {
                             if (ppm != pm_new) { memcpy(sets, sets + (size_t)SET16 * 16, (size_t)SET16 * 16); memcpy(Gp + QSB_GROUP_MASK_OFF(vb), &pm_new, 4); }
                             Gp[vb] = (uint8_t)(pf | S_XDEF);
+                            tr_xmerge++;
                             continue;
                         }
                     }
+                    tr_slot++;
                     const int g = next_group[vb]++;
                     if (g == (int)groups.size()) { groups.push_back(std::vector<uint8_t>((size_t)GROUP16 * 16, 0)); slot_single.push_back(std::array<bool, QSB_NVB>{}); }
                     slot_single[g][vb] = !mux && !cond;
@@ -1337,9 +1352,18 @@ struct PassBuilder {
                 specials.insert(specials.end(), sets[0].begin(), sets[0].end());
                 specials.insert(specials.end(), sets[1].begin(), sets[1].end());
                 n_special++;
+                if (gcode < G_NCODES) tr_code[gcode]++;
             }
             close_segment();
-            G.n_tph = n_tph; G.n_ang = n_ang; G.n_seg = (uint32_t)segrec[r].size();
+            pad16(angstream[r]);
+            G.n_tph = n_tph; G.n_ang = (uint32_t)(angstream[r].size() / 16); G.n_seg = (uint32_t)segrec[r].size();   /* n_ang: 16-byte units */
+            if (getenv("QSB_PLAN_TRACE")) {   /* host-side op mix of the lowered round (stderr); tools and DESIGN.md quote it */
+                unsigned full = 0, dv = 0;
+                for (int b = 0; b < QSB_NVB; b++) { full += tr_code[G_FULL_G + b]; dv += tr_code[G_DIAG_V + b]; }
+                fprintf(stderr, "qsb-plan: round %d: segments %u, slots %u (+%u merged X), phase runs %u (%u gates), FULL_G %u, DIAG_V %u, "
+                                "DIAG_ALL %u, DIAG_GEN %u, MATP %u, thread phases %u, angle phases %u\n", r, G.n_seg, tr_slot, tr_xmerge,
+                        tr_run, tr_run_members, full, dv, tr_code[G_DIAG_ALL], tr_code[G_DIAG_GEN], tr_code[G_MATP_R] + tr_code[G_MATP_G], n_tph, n_ang);
+            }
         }
         gp.n_cond = n_cond;
         size_t off = al16(sizeof(GPass));

@@ -35,6 +35,6 @@ for o, n in byop.most_common(14): print(f"  {o:10s} {n:12d} {100 * n / tot:5.1f}
 ts = sum(stalls.values())
 print("stalls:", ", ".join(f"{s[6:]} {100 * n / ts:.1f}%" for s, n in stalls.most_common(8)))
 blocks.sort(key=lambda b: -b['n'] * sum(b['ops'].values()))
-for b in blocks[:12]:
+for b in blocks[:int(sys.argv[4]) if len(sys.argv) > 4 else 12]:
     w = b['n'] * sum(b['ops'].values())
     print(f"  {100 * w / tot:5.1f}%  exec={b['n']:9d} len={sum(b['ops'].values()):4d} idx={b['first']:5d} {dict(b['ops'].most_common(5))}")

@@ -59,6 +59,17 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
         const uint64_t src_outer = outer | P.src_fixed;
         uint32_t W = 0;
         for (uint32_t i = 0; i < P.n_cond; i++) if ((src_outer & P.cond[i]) == P.cond[i]) W |= 1u << i;
+        /* angle entries test ONE 32-bit mask against the predicate word (tid, then the outer-condition bits W) */
+        auto angle_word = [&](int tid) { return (uint32_t)tid | (W << QSB_TB); };
+        /* sum of the entries of n_u 16-byte units that the word satisfies: f32 two {mask, ang32} per unit, f64 one {mask, -, ang64} */
+        auto angle_sum = [&](const uint8_t *p, uint32_t n_u, uint32_t aw) {
+            uint64_t acc = 0;
+            for (uint32_t u = 0; u < n_u; u++, p += 16) {
+                if (f32) { GTAngle32 e[2]; memcpy(e, p, 16); for (int k = 0; k < 2; k++) { if ((uint64_t)e[k].mask >> (QSB_TB + P.n_cond)) bad++; if ((aw & e[k].mask) == e[k].mask) acc += e[k].ang32; } }
+                else { GTAngle64 e; memcpy(&e, p, 16); if ((uint64_t)e.mask >> (QSB_TB + P.n_cond)) bad++; if ((aw & e.mask) == e.mask) acc += e.ang64; }
+            }
+            return acc;
+        };
         /* gather */
         for (int tid = 0; tid < QSB_THREADS; tid++) {
             uint64_t off = outer * AMP;
@@ -106,17 +117,10 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                     if (code >= G_DIAGA && code <= G_DIAGA + QSB_NVB) {   /* merged controlled phases: per-thread fixed-point angle sum, one phase */
                         const int vb = code - G_DIAGA;                     /* == QSB_NVB: run on the pack qubit (high lane of every vector) */
                         if (vb == QSB_NVB && !f32) bad++;
-                        uint32_t n_e; memcpy(&n_e, c, 4);
-                        const size_t stride = f32 ? 16 : 32;
-                        if (two || h[1] || om || (size_t)(h[0] >> 16) != 2 + (size_t)n_e * (stride / 16)) bad++;
+                        uint32_t n_u; memcpy(&n_u, c, 4);                 /* 16-byte units of angle entries */
+                        if (two || h[1] || om || (size_t)(h[0] >> 16) != 2 + (size_t)n_u) bad++;
                         for (int tid = 0; tid < QSB_THREADS; tid++) {
-                            uint64_t acc = 0;
-                            for (uint32_t i = 0; i < n_e; i++) {
-                                GTAngle T; memset(&T, 0, sizeof T); memcpy(&T, c + 16 + i * stride, stride);
-                                if ((src_outer & T.omask) != T.omask) continue;
-                                if (T.tmask >> QSB_TB) bad++;
-                                if (((uint32_t)tid & T.tmask) == T.tmask) acc += f32 ? (uint64_t)T.ang32 : T.ang64;
-                            }
+                            const uint64_t acc = angle_sum(c + 16, n_u, angle_word(tid));
                             const double half_turns = f32 ? (double)(int32_t)(uint32_t)acc / 2147483648.0 : (double)(int64_t)acc / 9223372036854775808.0;
                             const double PI_ = 3.14159265358979323846;
                             const cd ph(cos(PI_ * half_turns), sin(PI_ * half_turns));
@@ -192,15 +196,10 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
                 const cd ph(rd.S(T.val, 0), rd.S(T.val, 1));
                 for (int tid = 0; tid < QSB_THREADS; tid++) if (((uint32_t)tid & T.tmask) == T.tmask) pend[tid] *= ph;
             }
-            /* GTAngle entries follow the GTPhase entries: fixed-point turn fractions, summed per thread (wrapping) */
-            if (RD.n_ang) {
-                const size_t stride = f32 ? 16 : 32;
+            /* angle entries follow the GTPhase entries: fixed-point turn fractions, summed per thread (wrapping) */
+            if (RD.n_ang) {                                           /* n_ang: 16-byte units */
                 std::vector<uint64_t> acc(QSB_THREADS, 0);
-                for (uint32_t i = 0; i < RD.n_ang; i++, e += stride) {
-                    GTAngle T; memset(&T, 0, sizeof T); memcpy(&T, e, stride);
-                    if ((src_outer & T.omask) != T.omask) continue;
-                    for (int tid = 0; tid < QSB_THREADS; tid++) if (((uint32_t)tid & T.tmask) == T.tmask) acc[tid] += f32 ? (uint64_t)T.ang32 : T.ang64;
-                }
+                for (int tid = 0; tid < QSB_THREADS; tid++) acc[tid] = angle_sum(e, RD.n_ang, angle_word(tid));
                 for (int tid = 0; tid < QSB_THREADS; tid++) {
                     const double half_turns = f32 ? (double)(int32_t)(uint32_t)acc[tid] / 2147483648.0 : (double)(int64_t)acc[tid] / 9223372036854775808.0;
                     const double PI_ = 3.14159265358979323846;
