@@ -567,23 +567,25 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
         {
             const uint32_t n_tph = RD.n_tph;
             const uint32_t ti = RD.tph_off16;
-            auto tph_entry = [&](uint32_t i) {
-                const uint4 h = B[ti + 2 * i];
-                const uint64_t om = ((uint64_t)h.w << 32) | h.z;
-                if ((src_outer & om) != om) return;            /* uniform */
-                S pr, pi; T::tph(B[ti + 2 * i + 1], pr, pi);
-                if ((tid & h.x) != h.x) { pr = S(1); pi = S(0); }
-                const S nr = psr * pr - psi * pi;
-                psi = psr * pi + psi * pr; psr = nr;
-            };
             /* One or two entries per round on the circuits measured.  nvcc unrolls the loop 4x with the masks prefetched;
-             * same-box A/B (calls 24, 25): the f32 kernel is 0.9 % faster with that, the f64 kernel 1.4 % slower (code size). */
+             * same-box A/B (calls 24-26): the f32 kernel is 0.9 % faster with that, the f64 kernel 1.4 % slower (code size).
+             * The body is spelled twice on purpose: behind a lambda the f32 kernel allocates registers differently and
+             * QFT loses 1.8 %. */
+#define QSB_TPH_ENTRY                                                                  \
+                const uint4 h = B[ti + 2 * i];                                         \
+                const uint64_t om = ((uint64_t)h.w << 32) | h.z;                       \
+                if ((src_outer & om) != om) continue;          /* uniform */          \
+                S pr, pi; T::tph(B[ti + 2 * i + 1], pr, pi);                           \
+                if ((tid & h.x) != h.x) { pr = S(1); pi = S(0); }                      \
+                const S nr = psr * pr - psi * pi;                                      \
+                psi = psr * pi + psi * pr; psr = nr;
             if (sizeof(R) == 8) {
 #pragma unroll 1
-                for (uint32_t i = 0; i < n_tph; i++) tph_entry(i);
+                for (uint32_t i = 0; i < n_tph; i++) { QSB_TPH_ENTRY }
             } else {
-                for (uint32_t i = 0; i < n_tph; i++) tph_entry(i);
+                for (uint32_t i = 0; i < n_tph; i++) { QSB_TPH_ENTRY }
             }
+#undef QSB_TPH_ENTRY
             /* unit-modulus phases as fixed-point angles (GTAngle): integer adds per entry, one sincospi per round */
 #ifdef QSB_NO_TANGLE   /* A/B builds only: the planner must then be told not to emit GTAngle entries */
             const uint32_t n_ang = 0;
