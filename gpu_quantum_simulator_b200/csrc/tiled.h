@@ -263,7 +263,9 @@ struct GSegment {              /* 16 bytes */
     uint32_t n_groups, group_off16;
 };
 
+#ifndef QSB_MAX_COND           /* tests build the host doubles with a tiny table to exercise every full-table fallback */
 #define QSB_MAX_COND 24        /* distinct outer conditions a pass can name through W */
+#endif
 
 /* Blob layout (round 2): everything a round reads lies in one contiguous run -- [GRound][its GSegment table][specials and
  * groups][thread-phase and angle lists] -- followed by the next round's run, so that a round touches few, adjacent

@@ -14,7 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libqsim_ref.so")
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "ref_cexe")
-HOSTCHECK_SO = os.path.join(ROOT, "tests", "hostcheck", "libqsb_hostcheck%s.so" % os.environ.get("QSB_LIB_SUFFIX", ""))
+# QSB_HOSTCHECK_SUFFIX: a variant of the host doubles built by the caller (make -C tests/hostcheck SUFFIX=... EXTRA=...)
+_HC_SUFFIX = os.environ.get("QSB_HOSTCHECK_SUFFIX", os.environ.get("QSB_LIB_SUFFIX", ""))
+HOSTCHECK_SO = os.path.join(ROOT, "tests", "hostcheck", "libqsb_hostcheck%s.so" % _HC_SUFFIX)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 REFERENCE_DIR = "/root/reference"
 
@@ -25,7 +27,7 @@ _made = set()
 def _build(path, directory, always=False):
     """always: let make decide (once per process) -- the host test double links the product planner, so a stale build
     would silently test yesterday's planner."""
-    if not os.path.exists(path) or (always and directory not in _made):
+    if not os.path.exists(path) or (always and directory not in _made and not (_HC_SUFFIX and path == HOSTCHECK_SO)):
         subprocess.run(["make", "-C", directory], check=True, capture_output=True)
     _made.add(directory)
     return path
@@ -135,6 +137,13 @@ def hostcheck_blob_code_count(code, reset=False):
     L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
     L.qsb_hostcheck_blob_code_count.restype = C.c_ulong
     return int(L.qsb_hostcheck_blob_code_count(int(code), 1 if reset else 0))
+
+
+def hostcheck_blob_max_cond(reset=False):
+    """Largest outer-condition table among the passes the blob double has interpreted since the last reset."""
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
+    L.qsb_hostcheck_blob_max_cond.restype = C.c_uint
+    return int(L.qsb_hostcheck_blob_max_cond(1 if reset else 0))
 
 
 def hostcheck_run(circ_gates, n, precision=32, low_bits=0, state=None):

@@ -39,6 +39,10 @@ extern "C" unsigned long qsb_hostcheck_blob_code_count(int code, int reset)
     return v;
 }
 
+/* the largest outer-condition table of the passes interpreted so far (QSB_MAX_COND = full: later gates fell back) */
+static unsigned g_max_cond;
+extern "C" unsigned qsb_hostcheck_blob_max_cond(int reset) { const unsigned v = g_max_cond; if (reset) g_max_cond = 0; return v; }
+
 int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, cd *const *outs)
 {
     int bad = 0;
@@ -47,6 +51,7 @@ int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, c
     const uint8_t *B = hp.blob.data();
     Rd rd{B, f32};
     GPass P; memcpy(&P, B, sizeof P);
+    if (P.n_cond > g_max_cond) g_max_cond = P.n_cond;
     const int SET16 = QSB_SET16(f32), G16 = QSB_GROUP16(f32);
     const uint64_t loc_bytes = ((uint64_t)1 << nloc) * AMP;
     std::vector<cd> regs((size_t)QSB_THREADS * QSB_NV * L), smem((size_t)QSB_SLOTS * L);

@@ -283,6 +283,26 @@ def test_phase_ladders_onto_the_pack_qubit_are_merged():
         assert seen[32][0] > 0, seen          # the ladder onto qubit 0 (the pack qubit of the first pass) is merged
 
 
+def test_full_outer_condition_table_falls_back():
+    """Slots, merged phase runs and angle entries all name outer controls through the pass's 24-entry outer-condition
+    table; a gate that finds it full must take its fallback (generic special, plain phase op, thread phase with its
+    own 64-bit mask).  Real circuits rarely fill 24 entries, so the host doubles are rebuilt with a 3-entry table and
+    run in a child process: QFT, a layered circuit and a ccx / cp mix must still reproduce the oracle byte-exactly
+    interpreted, and the table must actually have been full."""
+    import subprocess, sys, os
+    hc = os.path.join(helpers.ROOT, "tests", "hostcheck")
+    subprocess.run(["make", "-C", hc, "SUFFIX=_smallcond", "EXTRA=-DQSB_MAX_COND=3"], check=True, capture_output=True)
+    env = dict(os.environ, QSB_HOSTCHECK_SUFFIX="_smallcond")
+    r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "hostcheck_small_table_worker.py")],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("case=")]
+    assert len(lines) == 6 and all(l.endswith(" ok") for l in lines), r.stdout
+    assert all("max_cond=3 " in l for l in lines), r.stdout                   # the table was full in every case
+    qft32 = [l for l in lines if l.startswith("case=qft prec=32")][0]
+    assert "merged_runs=0 " not in qft32 and "plain_phase_ops=0 " not in qft32, qft32     # both the merged form and its fallback ran
+
+
 @pytest.mark.parametrize("precision", [32, 64])
 def test_controlled_phase_ladders_are_merged(precision):
     """Round 2 (G_DIAGA): a run of controlled phases on one vector bit (a QFT ladder) is lowered to ONE op -- per-thread
