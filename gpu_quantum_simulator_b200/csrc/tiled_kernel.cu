@@ -66,10 +66,20 @@ template <> struct VT<float> {
     enum { SET4 = 1 };   /* 16-byte units per 4-scalar coefficient set */
     /* angle entries (GTAngle32): 8 bytes {mask over the predicate word tw, top 32 bits of the turn fraction}, TWO per 16-byte unit */
     typedef uint32_t A;
+    /* acc += ang where the word satisfies the mask, as ONE logic op writing a predicate (mask & ~word == 0) + ONE predicated
+     * add; from C++ nvcc makes LOP3 + ISETP + SEL + IADD3 of it (ncu, call 29: angle entries were 20 % of a QFT pass) */
+    static __device__ __forceinline__ void ang_add(uint32_t mask, uint32_t ang, uint32_t aw, A &acc)
+    {
+        asm("{ .reg .pred p; .reg .b32 t;\n\t"
+            "lop3.b32 t, %1, %2, 0, 0x30;\n\t"          /* mask & ~word */
+            "setp.eq.u32 p, t, 0;\n\t"
+            "@p add.u32 %0, %0, %3;\n\t"
+            "}" : "+r"(acc) : "r"(mask), "r"(aw), "r"(ang));
+    }
     static __device__ __forceinline__ void ang_acc(const uint4 u, uint32_t aw, A &acc)
     {
-        acc += ((aw & u.x) == u.x) ? u.y : 0u;
-        acc += ((aw & u.z) == u.z) ? u.w : 0u;
+        ang_add(u.x, u.y, aw, acc);
+        ang_add(u.z, u.w, aw, acc);
     }
     static __device__ __forceinline__ void turn(A acc, S &c, S &s) { sincospif((float)(int)acc * 4.656612873077393e-10f, &s, &c); }   /* acc / 2^31 half-turns */
 };
@@ -99,7 +109,12 @@ template <> struct VT<double> {
     typedef uint64_t A;
     static __device__ __forceinline__ void ang_acc(const uint4 u, uint32_t aw, A &acc)
     {
-        acc += ((aw & u.x) == u.x) ? (((uint64_t)u.w << 32) | u.z) : 0ull;
+        asm("{ .reg .pred p; .reg .b32 t; .reg .b64 a;\n\t"
+            "lop3.b32 t, %1, %2, 0, 0x30;\n\t"          /* mask & ~word */
+            "setp.eq.u32 p, t, 0;\n\t"
+            "mov.b64 a, {%3, %4};\n\t"
+            "@p add.u64 %0, %0, a;\n\t"
+            "}" : "+l"(acc) : "r"(u.x), "r"(aw), "r"(u.z), "r"(u.w));
     }
     static __device__ __forceinline__ void turn(A acc, S &c, S &s) { sincospi((double)(long long)acc * 1.0842021724855044e-19, &s, &c); }   /* acc / 2^63 half-turns */
 };
