@@ -57,13 +57,7 @@
 #define QSB_T_F32 (QSB_T_F64 + 1)      /* tile bits f32: pack + NVB + TB (12)        */
 #define QSB_SLOTS (1 << QSB_T_F64)     /* 16-byte shared-memory slots of a tile       */
 #define QSB_SMEM_BYTES (QSB_SLOTS * 16)
-/* Optional (-DQSB_SBT_ROUNDS=16): behind the exchange buffer, the per-thread exchange base offsets of the first rounds of the
- * pass, computed once per CTA while its gather loads are in flight instead of at the top of every round.  Measured
- * SLOWER on B200 (135.3-135.6 vs 132.9 ms at 30 q, call 11 of round 2), so it is off by default. */
-#ifndef QSB_SBT_ROUNDS
-#define QSB_SBT_ROUNDS 0
-#endif
-#define QSB_SMEM_TOTAL (QSB_SMEM_BYTES + QSB_SBT_ROUNDS * QSB_THREADS * 4)
+#define QSB_SMEM_TOTAL QSB_SMEM_BYTES   /* dynamic shared memory of a CTA: the exchange buffer, nothing else */
 #ifndef QSB_CTAS_PER_SM
 #define QSB_CTAS_PER_SM (512 / QSB_THREADS)
 #endif

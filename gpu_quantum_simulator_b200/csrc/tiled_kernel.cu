@@ -305,33 +305,6 @@ __device__ __forceinline__ void slot_exec(uint32_t form, uint32_t pmask, const S
     if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;
 }
 
-/* The same slot in two steps (-DQSB_SLOT_PIPE): slot_select does everything that depends only on the thread (predicate,
- * coefficient select, deferred-X toggle, pending scale) and can run BEFORE the packed arithmetic of the previous slot,
- * so that its dependent chain (LOP3 -> ISETP -> FSEL) hides behind ~100 cycles of FFMA2; slot_math is the arithmetic. */
-template <typename R> struct SlotS { typename VT<R>::S c0, c1, c2; };
-template <typename R, int VB>
-__device__ __forceinline__ void slot_select(uint32_t form, uint32_t pmask, const SlotC<R> &s, uint32_t tw, SlotS<R> &o,
-                                            typename VT<R>::S &psr, typename VT<R>::S &psi, uint32_t &xm)
-{
-    typedef typename VT<R>::S S;
-    const bool pred = (tw & pmask) == pmask;
-    o.c0 = pred ? s.d[0] : s.c[0]; o.c1 = pred ? s.d[1] : s.c[1]; o.c2 = pred ? s.d[2] : s.c[2];
-    const S c3 = pred ? s.d[3] : s.c[3];
-    if (form & (S_UNIT_R | S_UNIT_I)) { psr *= c3; psi *= c3; }
-    if (form & S_XDEF) xm ^= pred ? (1u << VB) : 0u;
-}
-template <typename R, int VB>
-__device__ __forceinline__ void slot_math(uint32_t form, const SlotS<R> &o, typename VT<R>::V (&re)[NV], typename VT<R>::V (&im)[NV])
-{
-    typedef VT<R> T;
-    if (form & S_UNIT_R) unit_v<R, VB, false>(re, im, o.c0, o.c1, o.c2);
-    else if (form & S_UNIT_I) unit_v<R, VB, true>(re, im, o.c0, o.c1, o.c2);
-#ifdef QSB_UNIT_H
-    else if (form & S_UNIT_H) unit_h<R, VB>(re, im, o.c0, o.c2);
-#endif
-    else if (form & S_DIAG) diag_v<R, VB>(re, im, T::bc(o.c0), T::bc(o.c1));
-}
-
 /* PEER: the scatter of a fused-exchange pass -- every amplitude goes straight into the shard of the rank
  * named by its victim bits (peer memory over NVLink), so the qubit exchange costs no extra sweep. */
 template <typename R, int BLOB, bool PEER>
@@ -375,58 +348,15 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
         const char *p = src + off;
 #pragma unroll
         for (int v = 0; v < NV; v++) IO<R>::gload(p + P.ld_vec[v], re[v], im[v]);
-#ifdef QSB_L2_PREFETCH
-        /* Pull the tile of the CTA that will take this one's place (QSB_L2_PREFETCH CTAs further on: the number
-         * resident on the chip) from HBM into L2 now: its gather then costs an L2 hit instead of a DRAM round trip.
-         * Threads 8k .. 8k+7 share 128-byte lines on the edge rounds (thread bits 0-2 are the physical bits next
-         * to the pack bit), so each of them asks for two of the 16 vectors.  A hint only: redundancy is harmless. */
-        {
-            uint64_t t2 = (uint64_t)blockIdx.x + tile_base + (uint64_t)QSB_L2_PREFETCH;
-            if (t2 < P.n_tiles) {
-                uint64_t o2 = 0;
-                const int nr = (int)P.n_runs;
-                for (int r = 0; r < nr; r++) { const int len = P.run_len[r]; o2 |= (t2 & ((1ULL << len) - 1)) << P.run_start[r]; t2 >>= len; }
-                const char *p2 = p + (o2 - outer) * AMP;
-                const int v0 = (tid & 7) * 2;
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + P.ld_vec[v0]));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(p2 + P.ld_vec[v0 + 1]));
-            }
-        }
-#endif
     }
 
     uint32_t xm = 0;   /* deferred X: this thread's register v holds logical vector v ^ xm */
     const uint4 *rp = B + P.rounds_off16;
-#if QSB_SBT_ROUNDS > 0
-    /* While the 16 gather loads are in flight: this thread's exchange base offsets of every round (they depend on the
-     * thread and the round, not on the tile: ~25 instructions and a chain of constant loads per round that would
-     * otherwise sit at the top of each round, between a barrier and the shared-memory loads).  Private slots: each
-     * thread reads back only what it wrote, no synchronisation. */
-    uint32_t *sbt = reinterpret_cast<uint32_t *>(smem + QSB_SMEM_BYTES) + tid;
-    {
-        const int nt = n_rounds < QSB_SBT_ROUNDS ? n_rounds : QSB_SBT_ROUNDS;
-        const uint4 *rq = rp;
-        for (int r = 0; r < nt; r++) {
-            const GRound &RQ = *reinterpret_cast<const GRound *>(rq);
-            rq = B + RQ.next16;
-            uint32_t b = 0;
-#pragma unroll
-            for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) b ^= RQ.thr_x[j];
-            sbt[r * QSB_THREADS] = b;
-        }
-    }
-#endif
     for (int rd = 0; rd < n_rounds; rd++, rp = B + reinterpret_cast<const GRound *>(rp)->next16) {   /* every round's tables are one contiguous run (tiled.h) */
         const GRound &RD = *reinterpret_cast<const GRound *>(rp);
         uint32_t sb = 0; /* this thread's smem byte offset: load side in the low half, store side in the high half */
-#if QSB_SBT_ROUNDS > 0
-        if (rd < QSB_SBT_ROUNDS) sb = sbt[rd * QSB_THREADS];
-        else
-#endif
-        {
 #pragma unroll
-            for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr_x[j];
-        }
+        for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) sb ^= RD.thr_x[j];
 
         if (rd > 0) {
             const uint32_t sl = sb & 0xffffu;
@@ -545,21 +475,6 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
 #endif
                     const uint4 *cp = gp + 2;
                     SlotC<R> sa, sc;
-#if defined(QSB_SLOT_PIPE) && QSB_NVB == 4
-                    SlotS<R> ea, eb;
-                    if (f0) slot_fetch<R>(cp, sa);
-                    if (f1) slot_fetch<R>(cp + S16, sc);
-                    if (f0) slot_select<R, 0>(f0, gm.x, sa, tw, ea, psr, psi, xm);
-                    if (f2) slot_fetch<R>(cp + 2 * S16, sa);
-                    if (f1) slot_select<R, 1>(f1, gm.y, sc, tw, eb, psr, psi, xm);
-                    if (f0) slot_math<R, 0>(f0, ea, re, im);
-                    if (f3) slot_fetch<R>(cp + 3 * S16, sc);
-                    if (f2) slot_select<R, 2>(f2, gm.z, sa, tw, ea, psr, psi, xm);
-                    if (f1) slot_math<R, 1>(f1, eb, re, im);
-                    if (f3) slot_select<R, 3>(f3, gm.w, sc, tw, eb, psr, psi, xm);
-                    if (f2) slot_math<R, 2>(f2, ea, re, im);
-                    if (f3) slot_math<R, 3>(f3, eb, re, im);
-#else
                     if (f0) slot_fetch<R>(cp, sa);
                     if (f1) slot_fetch<R>(cp + S16, sc);
                     if (f0) slot_exec<R, 0>(f0, gm.x, sa, re, im, tw, psr, psi, xm);
@@ -573,7 +488,6 @@ k_tile_pass(const __grid_constant__ PassBlob<BLOB> blob, const char *src, char *
                     if (f3) slot_exec<R, 3>(f3, gm.w, sc, re, im, tw, psr, psi, xm);
 #if QSB_NVB == 5
                     if (f4) slot_exec<R, 4>(f4, gh.z, sa, re, im, tw, psr, psi, xm);
-#endif
 #endif
                 }
             }
