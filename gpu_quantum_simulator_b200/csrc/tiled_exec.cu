@@ -15,6 +15,8 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <algorithm>
+#include <functional>
+#include <thread>
 #include <utility>
 #include <string.h>
 
@@ -27,30 +29,64 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
                      const std::vector<COp> &cops, const double gphase[2], bool /*with_device*/,
                      TiledPlan **out, qsb_run_stats_t *stats)
 {
-    TiledPlan *p = new TiledPlan();
-    int rc = tiled_schedule(n, prec, g, nloc, rank, opt, start, cops, gphase, p);
-    if (rc) { delete p; return rc; }
-    if (g > 0 && opt && opt->reserved[0] == 0) {
-        /* Sharded run, exchange threshold not pinned by the caller: the threshold (how few runnable gates make the
-         * scheduler exchange qubits) trades passes against exchanges, and the best value depends on the circuit.
-         * Plan with a few thresholds and keep the cheapest schedule -- cost in pass units: an exchange pass is NVLink
-         * bound and takes (1 - 2^-g) * local bytes / ~700 GB/s against 2 * local bytes / ~3 TB/s for an ordinary pass
-         * (measured), plus the barrier.  Every rank plans the same circuit and picks the same
-         * schedule (the rank only enters the descriptors, not the structure).  ~10 ms of host time per candidate. */
-        const double xcost = std::max(0.0, (1.0 - 1.0 / (double)(1 << g)) * 2.14 - 1.0) + 0.15;
+    TiledPlan *p = nullptr;
+    const bool search_threshold = g > 0 && opt && opt->reserved[0] == 0;
+    const bool search_lanes = g > 0 && opt && opt->reserved[6] == 0;
+    if (!search_threshold && !search_lanes) {
+        p = new TiledPlan();
+        int rc = tiled_schedule(n, prec, g, nloc, rank, opt, start, cops, gphase, p);
+        if (rc) { delete p; return rc; }
+    } else {
+        /* Sharded run with planner knobs the caller did not pin.  Two of them trade passes and rounds against qubit
+         * exchanges, and the best setting depends on the circuit and on the number of ranks:
+         *   - the exchange threshold (how few runnable gates make the scheduler exchange qubits), reserved[0];
+         *   - the lane relocation policy (every pass re-picks the qubits on the lane positions: fewer passes, but the
+         *     schedule runs dry behind a global qubit sooner; or only on conflict), reserved[6].
+         * Plan every combination -- each on its own host thread, ~10 ms -- and keep the cheapest schedule.  The cost model
+         * is the fit of DESIGN.md section 9, in ms at 2^30 local amplitudes: 1.5 per pass + 0.72 per round + the extra time
+         * of an exchange pass (NVLink-bound scatter of (1 - 2^-g) of the shard at ~700 GB/s, then the barrier): 1.25 with
+         * one peer, 2.5 with three, 8 with seven.  Every rank plans the same circuit and picks the same schedule (the rank
+         * only enters the descriptors, not the structure); ties go to the earlier candidate. */
+        static const int thresholds[] = {10, 8, 6, 14, 12, 7};
+        static const int lane_policies[] = {0, 4};
+        struct Cand { qsb_options_t o; TiledPlan *plan; int rc; char err[512]; };
+        std::vector<Cand> cand;
+        for (int lp : lane_policies) {
+            if (!search_lanes && lp != lane_policies[0]) continue;
+            for (int th : thresholds) {
+                if (!search_threshold && th != thresholds[0]) continue;
+                Cand c; c.o = *opt; c.plan = nullptr; c.rc = QSB_OK; c.err[0] = 0;
+                if (search_threshold) c.o.reserved[0] = th;
+                if (search_lanes) c.o.reserved[6] = lp;
+                cand.push_back(c);
+            }
+        }
+        auto run = [&](Cand &c) {
+            c.plan = new TiledPlan();
+            c.rc = tiled_schedule(n, prec, g, nloc, rank, &c.o, start, cops, gphase, c.plan);
+            if (c.rc) { snprintf(c.err, sizeof c.err, "%s", qsb_last_error()); delete c.plan; c.plan = nullptr; }   /* the message is thread-local */
+        };
+        std::vector<std::thread> workers;
+        for (size_t i = 1; i < cand.size(); i++) workers.emplace_back(run, std::ref(cand[i]));
+        run(cand[0]);
+        for (std::thread &w : workers) w.join();
+        const double xcost = g == 1 ? 1.25 : g == 2 ? 2.5 : 8.0;
         auto cost_of = [&](const TiledPlan *q) {
             double c = 0;
-            for (auto &hp : q->passes) { if (hp.is_swap) c += 1.0 + xcost; else c += hp.fused_swap ? 1.0 + xcost : 1.0; }
+            for (auto &hp : q->passes) {
+                if (hp.is_swap) { c += 1.5 + xcost; continue; }     /* the all-to-all costs about a pass on top */
+                c += 1.5 + 0.72 * (double)hp.rounds.size() + (hp.fused_swap ? xcost : 0.0);
+            }
             return c;
         };
-        double best = cost_of(p);
-        static const int cand[] = {8, 6, 14};
-        for (int smo : cand) {
-            qsb_options_t o2 = *opt; o2.reserved[0] = smo;
-            TiledPlan *q = new TiledPlan();
-            if (tiled_schedule(n, prec, g, nloc, rank, &o2, start, cops, gphase, q) == QSB_OK && cost_of(q) < best - 1e-9) { best = cost_of(q); delete p; p = q; }
-            else delete q;
+        double best = 0;
+        for (Cand &c : cand) {
+            if (!c.plan) continue;
+            const double cc = cost_of(c.plan);
+            if (!p || cc < best - 1e-9) { delete p; p = c.plan; best = cc; } else delete c.plan;
+            c.plan = nullptr;
         }
+        if (!p) { qsb_set_error("%s", cand[0].err); return cand[0].rc ? cand[0].rc : QSB_ERR_ARG; }
     }
     uint64_t n_ops = 0, n_rounds = 0, sweeps = 0, swaps = 0;
     for (auto &hp : p->passes) {

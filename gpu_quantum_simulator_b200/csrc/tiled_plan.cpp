@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <array>
+#include <functional>
 
 #include "sim.h"
 #include "tiled.h"
@@ -141,6 +142,7 @@ struct Machine {
     bool f32, lazy_diag, defer_diag, sink_phases, tile_search, hform, diaga;
     int trim_thin, cost_cap;
     bool fused_exchange, force_top, fused_direct;
+    int lane_reloc;   /* 0 off; 1..: policy of the end-of-pass lane relocation (build_rounds) */
 };
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
@@ -390,6 +392,12 @@ struct PassBuilder {
     HostPass hp;
     int tile_of_qubit[64];      /* logical qubit -> tile bit or -1              */
     std::vector<int> tile_qubit; /* tile bit -> logical qubit or -1 (padding)   */
+    /* lane relocation (build_rounds): the caller allows it and tells, for the ops this pass consumed, at which op
+     * each logical qubit is next used as a target; reloc_map (position -> position) is what the pass then did */
+    bool may_relocate = false;
+    std::function<void(const std::vector<char> &, size_t *)> next_use_cb;
+    bool relocated = false;
+    int8_t reloc_map[64];
 
     PassBuilder(const Machine &m, const BitPerm &p) : M(m), perm(p) {}
 
@@ -593,8 +601,69 @@ struct PassBuilder {
             roundR.push_back(R); round_ops.push_back(mine);
             if (!left) break;
         }
-        /* last round must keep the low destination bits on lanes */
-        if (roundR.back() & F) { roundR.push_back(0); round_ops.push_back({}); }
+        /* The last round must keep the low DESTINATION bits on lanes (coalesced 128-byte stores).  If it uses a
+         * qubit of the low segment as a vector bit, that qubit trades places -- inside the tile, which the pass
+         * gathers and scatters anyway -- with a qubit that is a thread bit in the last round: the pass leaves the
+         * qubits permuted (the caller folds reloc_map into the layout) instead of paying an empty round, i.e. one
+         * more trip of the tile through shared memory, just to turn the registers.  Flast: tile bits whose
+         * destination is a lane position. */
+        uint32_t Flast = F;
+        relocated = false;
+        if (may_relocate && M.lane_reloc && roundR.size() >= 2) {
+            const uint32_t Rl = roundR.back();
+            uint32_t nonpack = 0, ctrl_last = 0;
+            for (int tb = 0; tb < M.T; tb++) if (tb != P) nonpack |= 1u << tb;
+            for (int i : round_ops.back()) if (ops[i].kind != C_PHASE)
+                for (uint64_t m = ops[i].ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) ctrl_last |= 1u << tb; }
+            size_t next_use[64];
+            for (int q = 0; q < 64; q++) next_use[q] = ~(size_t)0;
+            if (next_use_cb) next_use_cb(done, next_use);
+            auto key = [&](int tb) { return tile_qubit[tb] >= 0 ? next_use[tile_qubit[tb]] : ~(size_t)0; };
+            /* always: every lane position is re-assigned; otherwise only the qubits in conflict move out */
+            auto try_relocate = [&](bool always) {
+                std::vector<int> cands;       /* thread bits of the last round that may live on the lanes afterwards */
+                for (int tb = 0; tb < M.T; tb++) if (((nonpack & ~Rl & (always ? ~0u : ~F)) >> tb) & 1) cands.push_back(tb);
+                /* Who lives on the lanes from now on: the qubits whose next use as a target is NEAREST.  The low positions
+                 * are part of every tile, so their qubits are resident in every pass without taking one of the freely
+                 * chosen tile slots (30 q layered: 22 -> 18 passes); the price -- they cannot be vector bits of a first
+                 * round -- is one round of delay for their first gate.  (On the planner's counts, parking the qubits
+                 * with the FURTHEST next use there costs passes instead: 22 passes / 134 rounds.) */
+                std::stable_sort(cands.begin(), cands.end(), [&](int x, int y) {
+                    if (key(x) != key(y)) return key(x) < key(y);
+                    const int fx = (F >> x) & 1, fy = (F >> y) & 1;     /* ties: whoever is there already stays */
+                    if (fx != fy) return fx > fy;
+                    return x > y;
+                });
+                const int need = always ? popc(F) : popc(Rl & F);
+                if ((int)cands.size() < need) return false;
+                uint32_t chosen = 0;
+                for (int k = 0; k < need; k++) chosen |= 1u << cands[k];
+                const uint32_t incoming = chosen & ~F, outgoing = always ? (F & ~chosen) : (Rl & F);
+                if (!incoming || popc(incoming) != popc(outgoing)) return false;
+                const uint32_t Fl = (F & ~outgoing) | incoming;
+                /* the last round must still find its padding vector bits outside the new lane set */
+                if (popc(nonpack & ~Fl & ~(ctrl_last | Rl)) + popc(Rl) < QSB_NVB) return false;
+                for (int q = 0; q < 64; q++) reloc_map[q] = (int8_t)q;
+                for (uint32_t in = incoming, out = outgoing; in; in &= in - 1, out &= out - 1) {
+                    const int tj = __builtin_ctz(out), tc = __builtin_ctz(in);
+                    const int8_t pj = hp.tile_src[tj], pc = hp.tile_src[tc];
+                    hp.tile_dst[tj] = pc; hp.tile_dst[tc] = pj;
+                    reloc_map[pj] = pc; reloc_map[pc] = pj;
+                }
+                Flast = Fl;
+                return true;
+            };
+            if (M.lane_reloc >= 4) relocated = try_relocate(true);
+            if (!relocated && (Rl & F)) relocated = try_relocate(false);
+        }
+        if (roundR.back() & Flast) { roundR.push_back(0); round_ops.push_back({}); Flast = F; }
+        if (getenv("QSB_PLAN_TRACE")) {
+            for (size_t r = 0; r < roundR.size(); r++) {
+                int useful = 0, ph = 0; for (int i : round_ops[r]) (ops[i].kind != C_PHASE ? useful : ph)++;
+                fprintf(stderr, "qsb-plan: selected round %zu: vector bits %03x, gates %d, phases %d\n", r, roundR[r], useful, ph);
+            }
+            fprintf(stderr, "qsb-plan: pass of %zu rounds, %zu of %zu ops left to the next pass, lane relocation %d\n", roundR.size(), left, n, (int)relocated);
+        }
 
         const int nrounds = (int)roundR.size();
         /* Sink thread-level phase gates to the latest round that can take them: a phase whose qubits are
@@ -607,7 +676,7 @@ struct PassBuilder {
             for (int tb = 0; tb < M.T; tb++) if (tb != P) nonpack |= 1u << tb;
             for (int i : round_ops[r + 1])
                 for (uint64_t m = ops[i].ctrl; m; m &= m - 1) { int tb = tile_of_qubit[__builtin_ctzll(m)]; if (tb >= 0 && tb != P) busy |= 1u << tb; }
-            const uint32_t edgeF = (r + 1 == nrounds - 1) ? F : 0u;
+            const uint32_t edgeF = (r + 1 == nrounds - 1) ? Flast : 0u;
             for (int i : round_ops[r]) {
                 const COp &o = ops[i];
                 bool move = false;
@@ -640,19 +709,20 @@ struct PassBuilder {
                 }
         for (int r = 0; r < nrounds; r++) {
             uint32_t R = roundR[r];
-            const bool edge = (r == 0 || r == nrounds - 1);
+            /* lane bits of the edge rounds: the low source positions in the first round, the low destinations in the last */
+            const uint32_t edgeF = (r == 0 ? F : 0u) | (r == nrounds - 1 ? Flast : 0u);
             /* pad R with the highest free tile bits: never a control of this round; the qubits of its phase
              * gates only if nothing else is left (they then cost vector arithmetic instead of a thread phase) */
             for (int tb = M.T - 1; tb >= 0 && popc(R) < QSB_NVB; tb--) {
                 if (tb == P || ((R >> tb) & 1) || (((ctrl_of_round[r] | phase_of_round[r]) >> tb) & 1)) continue;
-                if (edge && ((F >> tb) & 1)) continue;
+                if ((edgeF >> tb) & 1) continue;
                 R |= 1u << tb;
             }
             while (popc(R) < QSB_NVB) {   /* second choice: the phase-gate qubit with the fewest phase gates on it */
                 int best = -1, best_cnt = 1 << 30;
                 for (int tb = M.T - 1; tb >= 0; tb--) {
                     if (tb == P || ((R >> tb) & 1) || ((ctrl_of_round[r] >> tb) & 1)) continue;
-                    if (edge && ((F >> tb) & 1)) continue;
+                    if ((edgeF >> tb) & 1) continue;
                     int cnt = 0;
                     for (int i : round_ops[r]) if (ops[i].kind == C_PHASE && tile_qubit[tb] >= 0 && ((ops[i].ctrl >> tile_qubit[tb]) & 1)) cnt++;
                     if (cnt < best_cnt) { best_cnt = cnt; best = tb; }
@@ -665,6 +735,9 @@ struct PassBuilder {
             for (int tb = 0; tb < M.T; tb++) if ((R >> tb) & 1) vec.push_back((int8_t)tb);
             /* thread bits: ascending; on edge rounds this puts the low physical bits on the lanes */
             for (int tb = 0; tb < M.T; tb++) if (tb != P && !((R >> tb) & 1)) thr.push_back((int8_t)tb);
+            /* after a lane relocation the last round orders them by destination */
+            if (relocated && r == nrounds - 1)
+                std::stable_sort(thr.begin(), thr.end(), [&](int8_t x, int8_t y) { return hp.tile_dst[x] < hp.tile_dst[y]; });
             hp.round_vec[r] = vec; hp.round_thr[r] = thr;
             DevRound &D = hp.rounds[r];
             memset(&D, 0, sizeof D);
@@ -1426,6 +1499,9 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                                                                    flavour, victims moved to the top local positions first (A/B) */
     M.tile_search = !(opt && opt->reserved[6] == 2);   /* reserved[6] = 2: first-come tile choice (A/B runs) */
     M.sink_phases = !(opt && opt->reserved[6] == 1);   /* reserved[6] = 1: keep thread-level phases in the round that accepted them (A/B) */
+    /* reserved[6] = 3: no lane relocation at the end of a pass (an empty round turns the registers instead; round 1 / A-B);
+     * 4: relocate only the qubits in conflict; default: every pass re-picks the qubits that live on the lanes */
+    M.lane_reloc = (opt && opt->reserved[6] == 3) ? 0 : (opt && opt->reserved[6] == 4) ? 2 : 4;
     M.cost_cap = opt ? opt->reserved[3] : 0;   /* reserved[3] = k: stop adding rounds to a pass once its estimated SM cost reaches k gate units */
     M.nb = 3;   /* 16-byte shared-memory slots in both precisions: 8 lanes per 128-bit access phase */
     M.a = opt && opt->low_bits > 0 ? opt->low_bits : (M.f32 ? 4 : 3);   /* measured optimum on B200: DESIGN.md §5 */
@@ -1482,16 +1558,31 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         S_out = S;
     };
     /* ops a pass would run if exactly the qubits of S were resident (no growth): the score of a tile choice */
+    /* (the hill climbing calls this some 500 times per pass: it runs on a compact copy of the op list -- 16 bytes per
+     * op instead of the 160-byte COp -- with the blocker's two levels as bit masks) */
+    struct LiteOp { uint64_t ctrl; int8_t target; uint8_t phase; };
+    std::vector<LiteOp> lite(N);
+    for (size_t i = 0; i < N; i++) { lite[i].ctrl = cops[i].ctrl; lite[i].target = (int8_t)cops[i].target; lite[i].phase = cops[i].kind == C_PHASE; }
     auto count_fixed = [&](uint64_t S) -> int {
-        Blocker B; B.clear();
-        int score = 0, budget = 4 * max_pass_ops(M.f32);
+        uint64_t any = 0, hard = 0;     /* qubits blocked at level >= 1 / at level 2 (Blocker) */
+        uint64_t local = 0;
+        for (int q = 0; q < n; q++) if (perm.pos[q] < nloc) local |= 1ULL << q;
+        const uint64_t resident = S & local;
+        int score = 0, budget = 4 * max_pass_ops(M.f32), full = 0;
+        const LiteOp *L = lite.data();
+        const char *dn = done.data();
         for (size_t i = first_open; i < N && budget > 0; i++) {
-            if (done[i]) continue;
-            const COp &o = cops[i];
-            bool can = B.ok(o);
-            if (can && o.target >= 0 && (perm.pos[o.target] >= nloc || !((S >> o.target) & 1))) can = false;
-            if (can) { score += o.target >= 0 ? 8 : 1; budget -= o.kind == C_PHASE ? 1 : 4; }
-            else { B.block(o); if (B.full >= n) break; }
+            if (dn[i]) continue;
+            const LiteOp &o = L[i];
+            const uint64_t tbit = o.target >= 0 ? 1ULL << o.target : 0;
+            bool can = !(tbit & any) && !(o.ctrl & hard);
+            if (can && tbit && !(tbit & resident)) can = false;
+            if (can) { score += tbit ? 8 : 1; budget -= o.phase ? 1 : 4; }
+            else {
+                if (tbit && !(hard & tbit)) { hard |= tbit; full++; }
+                any |= tbit | o.ctrl;
+                if (full >= n) break;
+            }
         }
         return score;
     };
@@ -1517,6 +1608,18 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                          const std::vector<size_t> &mine_idx, bool allow_empty, bool fuse_exchange = false, const int *victim_pos = nullptr) -> int {
         PassBuilder pb(M, perm);
         pb.set_tile(S, forced_pos, pos_map, fuse_exchange, victim_pos);
+        /* plain passes may end with a lane relocation (build_rounds); it wants to know when each qubit is next a target */
+        pb.may_relocate = !pos_map && !fuse_exchange && !forced_pos;
+        pb.next_use_cb = [&](const std::vector<char> &used_now, size_t *next_use) {
+            std::vector<char> mine_used(N, 0);
+            for (size_t k = 0; k < mine_idx.size() && k < used_now.size(); k++) if (used_now[k]) mine_used[mine_idx[k]] = 1;
+            int found = 0;
+            for (size_t i = first_open; i < N && found < n; i++) {
+                if (done[i] || mine_used[i] || cops[i].target < 0) continue;
+                const int qq = cops[i].target;
+                if (next_use[qq] == ~(size_t)0) { next_use[qq] = i; found++; }
+            }
+        };
         std::vector<char> used;
         int rc = pb.build_rounds(mine, used, !allow_empty && mine_idx.size() < left);
         if (rc) return rc;
@@ -1527,6 +1630,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         if (!consumed && !allow_empty) { qsb_set_error("scheduler made no progress inside a pass"); return QSB_ERR_ARG; }
         while (first_open < N && done[first_open]) first_open++;
         if (pos_map) for (int q = 0; q < n; q++) if (perm.pos[q] < nloc) perm.pos[q] = pos_map[perm.pos[q]];
+        if (pb.relocated) for (int q = 0; q < n; q++) if (perm.pos[q] < nloc) perm.pos[q] = pb.reloc_map[perm.pos[q]];
         plan->passes.push_back(std::move(pb.hp));
         return QSB_OK;
     };

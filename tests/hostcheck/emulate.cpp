@@ -9,6 +9,7 @@
  *   - first-round loads / last-round stores of a warp are contiguous.
  * It is linked only into tests/hostcheck/libqsb_hostcheck.so.
  */
+#include <algorithm>
 #include <complex>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,24 @@ struct Report { int max_conflict; int bad_slots; int noncontig; int passes; int 
  * (outs[rank] = that rank's NEW shard); null for ordinary in-place passes */
 int blob_run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, cd *const *outs);   /* blob_emulate.cpp */
 static int g_use_blob = 0;   /* 1: interpret the device encoding (the kernel-parameter blob) instead of the logical tables */
+static int g_low_a = 0;      /* contiguous low index bits of the plan being run (0: precision default), for the coalescing check */
+
+/* Coalescing of the global accesses of an edge round: for a fixed vector, each group of 2^k consecutive lanes
+ * (k = lane bits inside the low segment, at most 3) must touch 2^k consecutive 16-byte units of ONE aligned run.
+ * idx[tid]: amplitude index that thread tid accesses for that vector (pack bit clear).  Returns the violations. */
+static int lanes_not_contiguous(const std::vector<uint64_t> &idx, bool f32, int a)
+{
+    const int unit_shift = f32 ? 1 : 0;                    /* amplitudes per 16-byte unit: 2 (f32) or 1 (f64) */
+    const int k = std::min(3, a - unit_shift);             /* lane bits inside the contiguous low segment */
+    if (k <= 0) return 0;
+    int bad = 0;
+    for (size_t t0 = 0; t0 < idx.size(); t0 += (size_t)1 << k) {
+        const uint64_t base = idx[t0] >> unit_shift;
+        if (base & ((1ULL << k) - 1)) { bad++; continue; }
+        for (int ln = 0; ln < (1 << k); ln++) if ((idx[t0 + ln] >> unit_shift) != base + (uint64_t)ln) { bad++; break; }
+    }
+    return bad;
+}
 extern "C" void qsb_hostcheck_use_blob(int on) { g_use_blob = on; }
 
 static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, Report &rep, cd *const *outs = nullptr)
@@ -70,14 +89,11 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                     }
                 }
             }
-            /* contiguity of the first load: a warp's 32 lanes, fixed v, must cover one aligned run */
+            /* contiguity of the first load (the vector bits only add high index bits, so vector 0 stands for all) */
             if (rd == 0) {
-                for (int w = 0; w < QSB_THREADS / 32; w++) {
-                    uint64_t lo = ~0ULL, hi = 0;
-                    for (int ln = 0; ln < 32; ln++) { uint64_t g = gthr[w * 32 + ln]; lo = std::min(lo, g); hi = std::max(hi, g); }
-                    /* with a >= 6 (f32) / 5 (f64) the span equals 32 units; smaller a: 2 or more runs */
-                    (void)lo; (void)hi;
-                }
+                std::vector<uint64_t> idx(QSB_THREADS);
+                for (int tid = 0; tid < QSB_THREADS; tid++) idx[tid] = gthr[tid] & loc_mask;
+                rep.noncontig += lanes_not_contiguous(idx, f32, g_low_a > 0 ? g_low_a : (f32 ? 4 : 3));
             }
             /* bank check, load side */
             if (rd > 0) {
@@ -156,6 +172,7 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
             }
             /* ---- store ---- */
             if (rd == nr - 1) {
+                std::vector<uint64_t> didx(QSB_THREADS);
                 for (int tid = 0; tid < QSB_THREADS; tid++) {
                     uint64_t d = outer | hp.hdr.dst_fixed;
                     for (uint32_t k = 0; k < hp.hdr.n_xo; k++) {   /* victims outside the tile: the outer bit names a bit of the destination rank */
@@ -164,6 +181,7 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                         d |= bit << (nloc + hp.hdr.xo_rank[k]);
                     }
                     for (int j = 0; j < QSB_TB; j++) if ((tid >> j) & 1) d |= hp.hdr.dst_thr[j];
+                    didx[tid] = d & loc_mask;
                     for (int v = 0; v < QSB_NV; v++) {
                         uint64_t gi = d;
                         for (int b = 0; b < QSB_NVB; b++) if ((v >> b) & 1) gi |= hp.hdr.dst_vec[b];
@@ -174,6 +192,9 @@ static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st
                         }
                     }
                 }
+                /* the last store must be as coalesced as the first load (the lanes carry the low DESTINATION bits) */
+                rep.noncontig += lanes_not_contiguous(didx, f32, g_low_a > 0 ? g_low_a : (f32 ? 4 : 3));
+                for (int b = 0; b < QSB_NVB; b++) if (f32 && (hp.hdr.dst_vec[b] & 1)) rep.noncontig++;
             } else {
                 std::fill(written.begin(), written.end(), 0);
                 for (int tid = 0; tid < QSB_THREADS; tid++) {
@@ -212,6 +233,7 @@ extern "C" int qsb_hostcheck_run(int num_q, int prec, int low_bits, const qsb_ga
 {
     qsb_options_t opt; memset(&opt, 0, sizeof opt);
     opt.precision = prec; opt.low_bits = low_bits; opt.world_size = 1;
+    g_low_a = low_bits;
     const int T = tiled_min_local_bits(prec, &opt);
     const int nloc = std::max(num_q, T);
     std::vector<COp> cops; double gph[2];
@@ -236,7 +258,7 @@ extern "C" int qsb_hostcheck_run(int num_q, int prec, int low_bits, const qsb_ga
 /* ---- step-wise interface for sharded schedules (multi-rank tests) ------------------------------
  * The caller owns one local shard per rank (2^nloc complex doubles) and performs the exchanges
  * itself (numpy in one process, or torch.distributed/gloo across processes). */
-struct HcPlan { TiledPlan plan; int prec; int nloc; Report rep; };
+struct HcPlan { TiledPlan plan; int prec; int nloc; int low_bits; Report rep; };
 
 extern "C" void *qsb_hostcheck_plan(int num_q, int prec, int low_bits, int world, int rank, int swap_min_ops,
                                     const qsb_gate_t *gates, size_t n)
@@ -250,7 +272,7 @@ extern "C" void *qsb_hostcheck_plan(int num_q, int prec, int low_bits, int world
     if (qsb_canonicalise(gates, n, num_q, cops, gph)) return nullptr;
     BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
     HcPlan *h = new HcPlan();
-    h->prec = prec; h->nloc = nloc; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
+    h->prec = prec; h->nloc = nloc; h->low_bits = low_bits; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
     if (tiled_schedule(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan)) { delete h; return nullptr; }
     return h;
 }
@@ -268,7 +290,7 @@ extern "C" void *qsb_hostcheck_plan_fused(int num_q, int prec, int low_bits, int
     if (qsb_canonicalise(gates, n, num_q, cops, gph)) return nullptr;
     BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
     HcPlan *h = new HcPlan();
-    h->prec = prec; h->nloc = nloc; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
+    h->prec = prec; h->nloc = nloc; h->low_bits = low_bits; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
     if (tiled_schedule(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan)) { delete h; return nullptr; }
     return h;
 }
@@ -286,6 +308,7 @@ extern "C" int qsb_hostcheck_run_step_fused(void *hv, int i, const double *state
     if (!hp.fused_swap) return 1;
     std::vector<cd> st((size_t)1 << h->nloc);
     memcpy((void *)st.data(), state, sizeof(cd) * st.size());
+    g_low_a = h->low_bits;
     run_pass(hp, h->prec == QSB_F32, h->nloc, st, h->rep, (cd *const *)outs);
     return 0;
 }
@@ -312,6 +335,7 @@ extern "C" int qsb_hostcheck_run_step(void *hv, int i, double *state)
     if (hp.is_swap) return 1;
     std::vector<cd> st((size_t)1 << h->nloc);
     memcpy((void *)st.data(), state, sizeof(cd) * st.size());
+    g_low_a = h->low_bits;
     run_pass(hp, h->prec == QSB_F32, h->nloc, st, h->rep);
     memcpy(state, st.data(), sizeof(cd) * st.size());
     return 0;

@@ -55,12 +55,17 @@ def test_fusion_factor_on_headline_workload():
     circ = circuits.random_layered(30, 20, 12345)
     st = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32)
     assert st["source_gates"] == 900
-    assert st["passes"] <= 23                  # 2^12-amplitude tiles, hill-climbed tile choice (first come: 30)
+    assert st["passes"] <= 19 and st["rounds"] <= 120   # 2^12-amplitude tiles, hill-climbed tiles, lane relocation
     assert st["bytes_moved"] == st["passes"] * 2 * (1 << 30) * 8
     st64 = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=64)
-    assert st64["passes"] <= 23
+    assert st64["passes"] <= 21 and st64["rounds"] <= 122
     first_come = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 2])
-    assert first_come["passes"] >= st["passes"] + 5 and first_come["rounds"] >= st["rounds"]
+    assert first_come["passes"] >= st["passes"] + 5
+    # without the end-of-pass lane relocation (round 1 / start of round 2: 22 passes, 130 rounds, 11 of them empty)
+    no_reloc = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 3])
+    assert no_reloc["passes"] >= st["passes"] + 3 and no_reloc["rounds"] >= st["rounds"] + 10
+    conflict_only = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 4])
+    assert st["passes"] <= conflict_only["passes"] <= no_reloc["passes"]
 
 
 def test_multi_control_and_global_phase_gates():
