@@ -374,6 +374,8 @@ extern "C" int qsb_plan_dry_run(int num_qubits, const qsb_options_t *opt_in, con
     if (opt.world_size <= 0) opt.world_size = 1;
     if (opt.world_size & (opt.world_size - 1)) { qsb_set_error("world_size must be a power of two"); return QSB_ERR_ARG; }
     int g = ilog2(opt.world_size);
+    /* the exchange flavour qsb_comm_init chooses when the peer shards can be mapped (direct fused scatter) */
+    if (g > 0 && opt.reserved[5] == 0) opt.reserved[5] = 1;
     int nloc = std::max(num_qubits - g, tiled_min_local_bits(opt.precision, &opt));
     BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
     qsb_plan *p = nullptr;

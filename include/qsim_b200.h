@@ -91,7 +91,10 @@ typedef struct qsb_options {
      *       2 NCCL all-to-all, 3 pipelined copy-engine exchange, 4 round-1 fused scatter (victims moved to the top local
      *       positions first)   (0: chosen by qsb_comm_init -- 1, or 2 if the peer shards cannot be mapped)
      *       With [0] = 0 a sharded plan is built for a few exchange thresholds and the cheapest schedule kept.
-     *   [6] 1 = do not sink thread-level phases to later rounds; 2 = first-come tile choice (no hill climbing) */
+     *   [6] 1 = do not sink thread-level phases to later rounds; 2 = first-come tile choice (no hill climbing);
+     *       3 = no lane relocation at the end of a pass (an empty round turns the registers instead, as in round 1);
+     *       4 = lane relocation only for the qubits in conflict (default: every pass re-picks the qubits that live on
+     *       the lane positions).  With [6] = 0 a sharded plan also tries 4 and keeps the cheaper schedule. */
     int32_t reserved[7];
 } qsb_options_t;
 

@@ -99,7 +99,7 @@ def main():
             if len(gates) == 0: seed += 1; continue
             got, rep = helpers.hostcheck_run(gates, n, prec, low)
             err = float(np.max(np.abs(got - want)))
-            ok = err < (3e-6 if (blob and prec == 32) else 1e-11) and rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+            ok = err < (3e-6 if (blob and prec == 32) else 1e-11) and rep["bad_slots"] == 0 and rep["max_conflict"] == 1 and rep["noncontig"] == 0
         except Exception as e:
             ok, err, rep = False, repr(e), {}
         runs += 1

@@ -20,7 +20,7 @@ while time.time() < t_end:
     try:
         got, rep = helpers.hostcheck_run(q.gates_from_circuit(circ), n, prec)
         want = helpers.oracle_run_circuit(circ, n)
-        err = float(np.max(np.abs(got - want))); ok = err < (3e-6 if (blob and prec == 32) else 1e-11) and rep["bad_slots"] == 0 and rep["max_conflict"] == 1
+        err = float(np.max(np.abs(got - want))); ok = err < (3e-6 if (blob and prec == 32) else 1e-11) and rep["bad_slots"] == 0 and rep["max_conflict"] == 1 and rep["noncontig"] == 0
     except Exception as e:
         ok, err, rep = False, repr(e), {}
     runs += 1
