@@ -47,7 +47,7 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
          * of an exchange pass (NVLink-bound scatter of (1 - 2^-g) of the shard at ~700 GB/s, then the barrier): 1.25 with
          * one peer, 2.5 with three, 8 with seven.  Every rank plans the same circuit and picks the same schedule (the rank
          * only enters the descriptors, not the structure); ties go to the earlier candidate. */
-        static const int thresholds[] = {10, 8, 6, 14, 12, 7};
+        static const int thresholds[] = {10, 8, 14, 12};
         static const int lane_policies[] = {0, 4};
         struct Cand { qsb_options_t o; TiledPlan *plan; int rc; char err[512]; };
         std::vector<Cand> cand;
