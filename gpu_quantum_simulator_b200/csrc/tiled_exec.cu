@@ -43,10 +43,12 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
          *   - the lane relocation policy (every pass re-picks the qubits on the lane positions: fewer passes, but the
          *     schedule runs dry behind a global qubit sooner; or only on conflict), reserved[6].
          * Plan every combination -- each on its own host thread, ~10 ms -- and keep the cheapest schedule.  The cost model
-         * is the fit of DESIGN.md section 9, in ms at 2^30 local amplitudes: 1.5 per pass + 0.72 per round + the extra time
-         * of an exchange pass (NVLink-bound scatter of (1 - 2^-g) of the shard at ~700 GB/s, then the barrier): 1.25 with
-         * one peer, 2.5 with three, 8 with seven.  Every rank plans the same circuit and picks the same schedule (the rank
-         * only enters the descriptors, not the structure); ties go to the earlier candidate. */
+         * is a fit of the 30 q lines of round 2 ((passes, rounds) -> ms: (22, 130) 126.2, (54, 134)
+         * 177.7, (18, 117) 117.8, (20, 114) 119.1), in ms at 2^30 local amplitudes: 1.5 per pass + 0.25 per round, and the
+         * extra time of an exchange pass (NVLink-bound scatter of (1 - 2^-g) of the shard at ~700 GB/s, then the barrier;
+         * from the 34 q scaling lines): 1.25 with one peer, 2.5 with three, 8 with seven.  Every rank plans the same circuit
+         * and picks the same schedule (the rank only enters the descriptors, not the structure); ties go to the earlier
+         * candidate. */
         static const int thresholds[] = {10, 8, 14, 12};
         static const int lane_policies[] = {0, 4};
         struct Cand { qsb_options_t o; TiledPlan *plan; int rc; char err[512]; };
@@ -75,7 +77,7 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
             double c = 0;
             for (auto &hp : q->passes) {
                 if (hp.is_swap) { c += 1.5 + xcost; continue; }     /* the all-to-all costs about a pass on top */
-                c += 1.5 + 0.72 * (double)hp.rounds.size() + (hp.fused_swap ? xcost : 0.0);
+                c += 1.5 + 0.25 * (double)hp.rounds.size() + (hp.fused_swap ? xcost : 0.0);
             }
             return c;
         };
