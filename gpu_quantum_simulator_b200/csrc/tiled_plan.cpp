@@ -340,6 +340,76 @@ void fuse_same_qubit(std::vector<COp> &ops, int n, double gphase[2])
     ops.swap(res);
 }
 
+/* CX next to a Hadamard-like gate on its target.  If H.X.H^-1 = D is diagonal (H = the Hadamard gate, S.H, ...), then
+ * "CX, then H" is "H, then controlled-D", and "H, then CX" is "controlled-(H^-1.X.H), then H": the non-diagonal two-qubit
+ * gate becomes a controlled PHASE, which needs no residency, costs one entry of a thread-phase list instead of a
+ * multiplexed gate, and no longer separates H from the one-qubit gate on the other side of the CX -- the 2x2 products
+ * of fuse_same_qubit then see them as neighbours (h, cx, h -- the reference's spelling of CZ, SURVEY.md 8c -- is one
+ * phase gate and no matrix at all).  The moved gate commutes with everything it passes: nothing between the two ops
+ * touches the target, and the controlled phase stays at the CX's place, so it reads the controls when the CX did.
+ * Random layered workload (one of {h, rx, rz} per qubit and layer): 5 of 9 CX have an h next to their target. */
+void cx_through_h(std::vector<COp> &ops, double gphase[2])
+{
+    const int N = (int)ops.size();
+    std::vector<char> dead(N, 0);
+    std::vector<std::vector<COp>> repl(N);
+    auto touches = [](const COp &o, int t) { return o.target == t || ((o.ctrl >> t) & 1); };
+    /* D = H.X.H^-1 (forward) or H^-1.X.H (backward), H unitary; true if D is diagonal to rounding */
+    auto conj_x = [](const double *H, bool forward, double *D) {
+        auto mul = [](const double *A, const double *B, double *C) {       /* C = A.B, row-major complex 2x2 */
+            for (int r = 0; r < 2; r++) for (int c = 0; c < 2; c++) {
+                double pr = 0, pi = 0;
+                for (int k = 0; k < 2; k++) {
+                    const double ar = A[2 * (2 * r + k)], ai = A[2 * (2 * r + k) + 1], br = B[2 * (2 * k + c)], bi = B[2 * (2 * k + c) + 1];
+                    pr += ar * br - ai * bi; pi += ar * bi + ai * br;
+                }
+                C[2 * (2 * r + c)] = pr; C[2 * (2 * r + c) + 1] = pi;
+            }
+        };
+        double Hd[8];                                                       /* H^dagger */
+        for (int r = 0; r < 2; r++) for (int c = 0; c < 2; c++) { Hd[2 * (2 * r + c)] = H[2 * (2 * c + r)]; Hd[2 * (2 * r + c) + 1] = -H[2 * (2 * c + r) + 1]; }
+        static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+        double T[8], P[8];
+        if (forward) { mul(H, X, T); mul(T, Hd, P); } else { mul(Hd, X, T); mul(T, H, P); }
+        snap_mat(P, D);
+        if (D[2] != 0 || D[3] != 0 || D[4] != 0 || D[5] != 0) return false;
+        /* the diagonal of a conjugated X has modulus one: take the rounding out of exact values (+-1, +-i) */
+        for (int k : {0, 1, 6, 7}) if (fabs(D[k] - rint(D[k])) <= 8e-16) D[k] = rint(D[k]);
+        const double n0 = hypot(D[0], D[1]), n1 = hypot(D[6], D[7]);
+        return fabs(n0 - 1.0) <= 1e-12 && fabs(n1 - 1.0) <= 1e-12;       /* H was unitary */
+    };
+    auto plain_mat_on = [](const COp &o, int t) { return o.kind == C_MAT && o.ctrl == 0 && o.target == t; };
+    for (int i = 0; i < N; i++) {
+        const COp &cx = ops[i];
+        if (cx.kind != C_X || !cx.ctrl || dead[i] || !repl[i].empty()) continue;
+        const int t = cx.target;
+        double D[8];
+        int j = i + 1;
+        while (j < N && (dead[j] || !touches(ops[j], t))) j++;
+        if (j < N && repl[j].empty() && plain_mat_on(ops[j], t) && conj_x(ops[j].m, true, D)) {
+            std::vector<COp> seq; seq.push_back(ops[j]);
+            if (!canon_one(D, cx.ctrl, t, seq, gphase)) continue;
+            repl[i].swap(seq); dead[j] = 1;
+            continue;
+        }
+        int k = i - 1;
+        while (k >= 0 && (dead[k] || !touches(ops[k], t))) k--;
+        if (k >= 0 && repl[k].empty() && plain_mat_on(ops[k], t) && conj_x(ops[k].m, false, D)) {
+            std::vector<COp> seq;
+            if (!canon_one(D, cx.ctrl, t, seq, gphase)) continue;
+            seq.push_back(ops[k]);
+            repl[i].swap(seq); dead[k] = 1;
+        }
+    }
+    std::vector<COp> out; out.reserve(N + 8);
+    for (int i = 0; i < N; i++) {
+        if (dead[i]) continue;
+        if (repl[i].empty()) out.push_back(ops[i]);
+        else out.insert(out.end(), repl[i].begin(), repl[i].end());
+    }
+    ops.swap(out);
+}
+
 /* SWAP as a relabelling.  Three CX in a row on the same pair with alternating direction (what a front end
  * makes of `swap a, b`; SURVEY.md 8c lists SWAP = 3 CX) exchange the states of the two qubits: instead of
  * moving amplitudes, the two logical qubits trade wires -- every later op is rewritten onto the wire that
@@ -1517,6 +1587,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     int8_t wire[64];
     relabel_swaps(cops, n, wire);
     double gph[2] = {gphase[0], gphase[1]};
+    if (!(opt && (opt->reserved[4] == 2 || opt->reserved[4] == 5))) cx_through_h(cops, gph);   /* reserved[4] = 5: CX stays CX next to an h (A/B) */
     if (!(opt && opt->reserved[4] == 2)) fuse_same_qubit(cops, n, gph);      /* reserved[4] = 2: no 2x2 products (A/B, tests) */
     absorb_cx(cops, n);
     if (!(gph[0] == 1.0 && gph[1] == 0.0)) {

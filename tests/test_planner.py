@@ -55,17 +55,49 @@ def test_fusion_factor_on_headline_workload():
     circ = circuits.random_layered(30, 20, 12345)
     st = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32)
     assert st["source_gates"] == 900
-    assert st["passes"] <= 19 and st["rounds"] <= 120   # 2^12-amplitude tiles, hill-climbed tiles, lane relocation
+    assert st["passes"] <= 17 and st["rounds"] <= 95    # 2^12-amplitude tiles, hill-climbed tiles, lane relocation, CX -> CZ next to an h
     assert st["bytes_moved"] == st["passes"] * 2 * (1 << 30) * 8
     st64 = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=64)
-    assert st64["passes"] <= 21 and st64["rounds"] <= 122
+    assert st64["passes"] <= 18 and st64["rounds"] <= 100
     first_come = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 2])
-    assert first_come["passes"] >= st["passes"] + 5
-    # without the end-of-pass lane relocation (round 1 / start of round 2: 22 passes, 130 rounds, 11 of them empty)
+    assert first_come["passes"] >= st["passes"] + 4
+    # without the end-of-pass lane relocation: more passes, and empty rounds that only turn the registers
     no_reloc = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 3])
-    assert no_reloc["passes"] >= st["passes"] + 3 and no_reloc["rounds"] >= st["rounds"] + 10
+    assert no_reloc["passes"] >= st["passes"] + 2 and no_reloc["rounds"] >= st["rounds"] + 8
     conflict_only = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 4])
     assert st["passes"] <= conflict_only["passes"] <= no_reloc["passes"]
+    # CX kept as CX next to an h on its target (reserved[4] = 5): the schedule of call 32
+    cx_kept = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 5])
+    assert cx_kept["passes"] >= st["passes"] + 1 and cx_kept["rounds"] >= st["rounds"] + 20
+    # both off: the planner of round 1 / the start of round 2 (22 passes, 130 rounds, 11 of them empty)
+    old = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 5, 0, 3])
+    assert old["passes"] == 22 and old["rounds"] == 130
+
+
+def test_cx_next_to_a_hadamard_becomes_a_controlled_phase():
+    """h cx h on the target is the reference's spelling of CZ: no matrix op may be left of it, and every
+    variant (h before, h after, both, s.h, controls on several qubits) must reproduce the oracle."""
+    n = 6
+    base = [("h", (k,), ()) for k in range(n)] + [("rx", (k,), (0.3 + k,)) for k in range(n)]
+    cases = [
+        [("h", (1,), ()), ("cx", (0, 1), ()), ("h", (1,), ())],
+        [("cx", (0, 1), ()), ("h", (1,), ())],
+        [("h", (1,), ()), ("cx", (0, 1), ())],
+        [("rx", (1,), (0.7,)), ("cx", (0, 1), ()), ("h", (1,), ()), ("cx", (2, 1), ()), ("h", (1,), ()), ("cx", (1, 3), ())],
+        [("h", (2,), ()), ("ccx", (0, 1, 2), ()), ("h", (2,), ())],
+        [("h", (1,), ()), ("s", (1,), ()), ("cx", (0, 1), ()), ("sdg", (1,), ()), ("h", (1,), ())],
+        [("cx", (0, 1), ()), ("rz", (0,), (0.4,)), ("x", (0,), ()), ("h", (1,), ()), ("cx", (1, 0), ()), ("h", (0,), ())],
+    ]
+    for prec in (32, 64):
+        for tail in cases:
+            got, want, rep = run_both(base + tail + base, n, prec)
+            assert rep["bad_slots"] == 0 and rep["noncontig"] == 0
+            assert np.max(np.abs(got - want)) < 1e-12
+    cz = [("h", (1,), ()), ("cx", (0, 1), ()), ("h", (1,), ())]
+    st = q.plan_dry_run(4, q.gates_from_circuit(cz))
+    assert st["device_ops"] <= 2 and st["rounds"] == 1   # one controlled phase (+ the rounding of h.h as a global scalar)
+    kept = q.plan_dry_run(4, q.gates_from_circuit(cz), reserved=[0, 0, 0, 0, 5])
+    assert kept["device_ops"] == 3 and kept["rounds"] == 2
 
 
 def test_multi_control_and_global_phase_gates():
