@@ -353,4 +353,4 @@ void tiled_comm_destroy(qsb_sim *s);
 
 /* host-only planner entry (no CUDA): used by tiled_plan_build and by the test emulator */
 int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
-                   const std::vector<COp> &cops, const double gphase[2], TiledPlan *plan);
+                   const std::vector<COp> &cops, const double gphase[2], TiledPlan *plan, int climb_variant = 0);

@@ -1547,7 +1547,7 @@ struct PassBuilder {
 
 /* ----------------------------------------------------------------- scheduler */
 int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
-                   const std::vector<COp> &cops_in, const double gphase[2], TiledPlan *plan)
+                   const std::vector<COp> &cops_in, const double gphase[2], TiledPlan *plan, int climb_variant)
 {
     Machine M;
     M.n = n; M.prec = prec; M.g = g; M.nloc = nloc; M.rank = rank;
@@ -1658,18 +1658,27 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         return score;
     };
     /* hill climbing over the tile: trade one chosen qubit for one outside while the pass gets more ops */
+    /* climb_variant: the order in which the hill climbing tries its swaps (bit 0: qubits leaving the tile from the top,
+     * bit 1: qubits entering from the top, bit 2: best instead of first improvement).  The climb stops in a local optimum
+     * and the variants end in different ones, a pass more or less on the 30-34 q workloads: tiled_plan_build plans a few
+     * and keeps the cheapest schedule. */
+    const int xvar = climb_variant;
     auto improve_tile = [&](uint64_t lowS, uint64_t S) -> uint64_t {
         int best = count_fixed(S);
         for (int sweep = 0; sweep < 3; sweep++) {
             bool any = false;
-            for (int qo = 0; qo < n; qo++) {
+            for (int qo_ = 0; qo_ < n; qo_++) {
+                const int qo = (xvar & 1) ? n - 1 - qo_ : qo_;
                 if (!((S >> qo) & 1) || ((lowS >> qo) & 1)) continue;
-                for (int qi = 0; qi < n; qi++) {
+                uint64_t bestS = S; int bestc = best;
+                for (int qi_ = 0; qi_ < n; qi_++) {
+                    const int qi = (xvar & 2) ? n - 1 - qi_ : qi_;
                     if (((S >> qi) & 1) || perm.pos[qi] >= nloc) continue;
                     const uint64_t S2 = (S & ~(1ULL << qo)) | (1ULL << qi);
                     const int c = count_fixed(S2);
-                    if (c > best) { best = c; S = S2; any = true; break; }
+                    if (c > bestc) { bestc = c; bestS = S2; if (!(xvar & 4)) break; }
                 }
+                if (bestc > best) { best = bestc; S = bestS; any = true; }
             }
             if (!any) break;
         }

@@ -132,6 +132,13 @@ def hostcheck_use_blob(on):
     L.qsb_hostcheck_use_blob(1 if on else 0)
 
 
+def hostcheck_set_climb(variant):
+    """Order of the swaps the tile hill climbing tries (tiled_schedule's climb_variant, 0..7): the product plans the
+    variants 0, 2, 3, 4 on single-GPU runs and keeps the cheapest schedule; the double runs the one set here."""
+    L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
+    L.qsb_hostcheck_set_climb(int(variant))
+
+
 def hostcheck_blob_code_count(code, reset=False):
     """How many special ops with this code (tiled.h G_*) the blob double has interpreted since the last reset."""
     L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
