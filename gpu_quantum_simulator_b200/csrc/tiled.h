@@ -351,6 +351,7 @@ int tiled_execute(qsb_sim *s, TiledPlan *p);
 double tiled_last_exchange_ms(const TiledPlan *p);
 void tiled_comm_destroy(qsb_sim *s);
 
+void tiled_plan_trace_suppress(bool off);   /* QSB_PLAN_TRACE output of the calling thread's tiled_schedule calls on / off */
 /* host-only planner entry (no CUDA): used by tiled_plan_build and by the test emulator */
 int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
                    const std::vector<COp> &cops, const double gphase[2], TiledPlan *plan, int climb_variant = 0);

@@ -72,18 +72,24 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
                 }
             }
         }
+        const bool tracing = getenv("QSB_PLAN_TRACE") != nullptr;   /* candidates stay silent; the winner is planned once more, aloud */
         auto run = [&](Cand &c) {
+            tiled_plan_trace_suppress(true);
             c.plan = new TiledPlan();
             c.rc = tiled_schedule(n, prec, g, nloc, rank, &c.o, start, cops, gphase, c.plan, c.climb);
             if (c.rc) { snprintf(c.err, sizeof c.err, "%s", qsb_last_error()); delete c.plan; c.plan = nullptr; }   /* the message is thread-local */
+            tiled_plan_trace_suppress(false);
         };
         /* small circuits are planned faster than a thread starts */
         const bool threads = cops.size() >= 64;
         std::vector<std::thread> workers;
-        if (threads) for (size_t i = 1; i < cand.size(); i++) workers.emplace_back(run, std::ref(cand[i]));
+        for (size_t i = 1; i < cand.size(); i++) {
+            bool started = false;
+            if (threads) { try { workers.emplace_back(run, std::ref(cand[i])); started = true; } catch (...) {} }   /* no thread to be had: plan it here */
+            if (!started) run(cand[i]);
+        }
         run(cand[0]);
-        if (threads) for (std::thread &w : workers) w.join();
-        else for (size_t i = 1; i < cand.size(); i++) run(cand[i]);
+        for (std::thread &w : workers) w.join();
         const double xcost = g == 1 ? 1.25 : g == 2 ? 2.5 : 8.0;
         auto cost_of = [&](const TiledPlan *q) {
             double c = 0;
@@ -94,13 +100,20 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
             return c;
         };
         double best = 0;
+        const Cand *winner = nullptr;
         for (Cand &c : cand) {
             if (!c.plan) continue;
             const double cc = cost_of(c.plan);
-            if (!p || cc < best - 1e-9) { delete p; p = c.plan; best = cc; } else delete c.plan;
+            if (!p || cc < best - 1e-9) { delete p; p = c.plan; best = cc; winner = &c; } else delete c.plan;
             c.plan = nullptr;
         }
         if (!p) { qsb_set_error("%s", cand[0].err); return cand[0].rc ? cand[0].rc : QSB_ERR_ARG; }
+        if (tracing) {
+            TiledPlan again;
+            tiled_schedule(n, prec, g, nloc, rank, &winner->o, start, cops, gphase, &again, winner->climb);
+            fprintf(stderr, "qsb-plan: kept candidate %d of %zu (exchange threshold %d, lane policy %d, climb order %d), modelled cost %.1f\n",
+                    (int)(winner - cand.data()), cand.size(), winner->o.reserved[0], winner->o.reserved[6], winner->climb, best);
+        }
     }
     uint64_t n_ops = 0, n_rounds = 0, sweeps = 0, swaps = 0;
     for (auto &hp : p->passes) {

@@ -123,6 +123,12 @@ int qsb_canonicalise(const qsb_gate_t *gates, size_t n, int num_qubits, std::vec
     return QSB_OK;
 }
 
+/* QSB_PLAN_TRACE=1: the lowered op mix of every round on stderr.  tiled_plan_build plans several candidates and
+ * silences all but the schedule it keeps. */
+static thread_local bool t_trace_off = false;
+void tiled_plan_trace_suppress(bool off) { t_trace_off = off; }
+static bool plan_trace() { return !t_trace_off && getenv("QSB_PLAN_TRACE") != nullptr; }
+
 /* ------------------------------------------------------------------ helpers */
 int tiled_min_local_bits(int prec, const qsb_options_t *) { return prec == QSB_F64 ? QSB_T_F64 : QSB_T_F32; }
 
@@ -727,7 +733,7 @@ struct PassBuilder {
             if (!relocated && (Rl & F)) relocated = try_relocate(false);
         }
         if (roundR.back() & Flast) { roundR.push_back(0); round_ops.push_back({}); Flast = F; }
-        if (getenv("QSB_PLAN_TRACE")) {
+        if (plan_trace()) {
             for (size_t r = 0; r < roundR.size(); r++) {
                 int useful = 0, ph = 0; for (int i : round_ops[r]) (ops[i].kind != C_PHASE ? useful : ph)++;
                 fprintf(stderr, "qsb-plan: selected round %zu: vector bits %03x, gates %d, phases %d\n", r, roundR[r], useful, ph);
@@ -1500,7 +1506,7 @@ struct PassBuilder {
             close_segment();
             pad16(angstream[r]);
             G.n_tph = n_tph; G.n_ang = (uint32_t)(angstream[r].size() / 16); G.n_seg = (uint32_t)segrec[r].size();   /* n_ang: 16-byte units */
-            if (getenv("QSB_PLAN_TRACE")) {   /* host-side op mix of the lowered round (stderr); tools and DESIGN.md quote it */
+            if (plan_trace()) {   /* host-side op mix of the lowered round (stderr); tools and DESIGN.md quote it */
                 unsigned full = 0, dv = 0;
                 for (int b = 0; b < QSB_NVB; b++) { full += tr_code[G_FULL_G + b]; dv += tr_code[G_DIAG_V + b]; }
                 fprintf(stderr, "qsb-plan: round %d: segments %u, slots %u (+%u merged X), phase runs %u (%u gates), FULL_G %u, DIAG_V %u, "
