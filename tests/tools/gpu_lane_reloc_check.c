@@ -2,9 +2,11 @@
  * gpu_lane_reloc_check.c -- TEST TOOL (B200 box, no Python): hardware check and A/B of the end-of-pass lane
  * relocation (tiled_plan.cpp, build_rounds) through the C ABI.
  *   1. parity: a circuit file is run by the CPU oracle (oracle/_build/liboracle.so, oc_run_file) and on the GPU
- *      in f32 and f64, with the default planner and with reserved[6] = 3 / 4 (no relocation / conflicts only);
+ *      in f32 and f64, with the default planner, with the planner before the lane relocation and the CX -> controlled-phase
+ *      rewrite (reserved[6] = 3, reserved[4] = 5) and with reserved[6] = 4 (relocation of the qubits in conflict only);
  *      prints max |amplitude difference| per run and exits 1 above 1e-5 (f32) / 1e-12 (f64).
- *   2. timing: every further file is planned once per policy and executed `reps` times from |0...0>; prints the
+ *   2. timing: every further file is planned once per planner setting (old / lane relocation only / default) and executed
+ *      `reps` times from |0...0>; prints the
  *      CUDA-event time per execution (minimum and all), passes and rounds.
  * Usage: gpu_lane_reloc_check <parity.qasm> <reps> <bench.qasm[:64]>...
  * Build: tests/tools/Makefile.  The oracle is the checker here, never the thing measured.
@@ -37,10 +39,10 @@ int main(int argc, char **argv)
         if (oc_run_file(argv[1], &want, &nq2) || nq2 != nq) { printf("FAIL oracle on %s\n", argv[1]); return 2; }
         const uint64_t N = 1ULL << nq;
         double *got = (double *)malloc(sizeof(double) * 2 * N);
-        static const int pol[] = {0, 3, 4};
+        static const int pol[] = {0, 3, 4}, cxh[] = {0, 5, 0};
         for (int prec = 32; prec <= 64; prec += 32) for (int k = 0; k < 3; k++) {
             qsb_options_t o; qsb_options_default(&o);
-            o.precision = prec == 64 ? QSB_F64 : QSB_F32; o.reserved[6] = pol[k];
+            o.precision = prec == 64 ? QSB_F64 : QSB_F32; o.reserved[6] = pol[k]; o.reserved[4] = cxh[k];
             qsb_t *s = NULL;
             check(qsb_create(&s, nq, &o), "create");
             check(qsb_apply_gates(s, gates, n), "apply");
@@ -66,10 +68,10 @@ int main(int argc, char **argv)
         if (colon) { prec = atoi(colon + 1); *colon = 0; }
         int nq = 0; qsb_gate_t *gates = NULL; size_t n = 0;
         check(qsb_parse_qasm_file(path, &nq, &gates, &n), "parse");
-        static const int pol[] = {3, 0, 4};
+        static const int pol[] = {3, 0, 0}, cxh[] = {5, 5, 0};   /* the planner before both changes, lane relocation only, the default */
         for (int k = 0; k < 3; k++) {
             qsb_options_t o; qsb_options_default(&o);
-            o.precision = prec == 64 ? QSB_F64 : QSB_F32; o.reserved[6] = pol[k];
+            o.precision = prec == 64 ? QSB_F64 : QSB_F32; o.reserved[6] = pol[k]; o.reserved[4] = cxh[k];
             qsb_t *s = NULL;
             check(qsb_create(&s, nq, &o), "create");
             qsb_plan_t *p = NULL;
