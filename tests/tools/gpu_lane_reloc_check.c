@@ -51,8 +51,8 @@ int main(int argc, char **argv)
             double err = 0;
             for (uint64_t i = 0; i < 2 * N; i++) { const double d = fabs(got[i] - want[i]); if (d > err) err = d; }
             const double tol = prec == 64 ? 1e-12 : 1e-5;
-            printf("{\"parity\": \"%s\", \"qubits\": %d, \"gates\": %zu, \"precision\": %d, \"lane_policy\": %d, \"passes\": %u, \"rounds\": %u, "
-                   "\"max_abs_err\": %.3e, \"tol\": %.0e, \"ok\": %s}\n", argv[1], nq, n, prec, pol[k], st.passes, st.rounds, err, tol, err <= tol ? "true" : "false");
+            printf("{\"parity\": \"%s\", \"qubits\": %d, \"gates\": %zu, \"precision\": %d, \"lane_policy\": %d, \"cx_kept\": %d, \"passes\": %u, \"rounds\": %u, "
+                   "\"max_abs_err\": %.3e, \"tol\": %.0e, \"ok\": %s}\n", argv[1], nq, n, prec, pol[k], cxh[k] == 5, st.passes, st.rounds, err, tol, err <= tol ? "true" : "false");
             fflush(stdout);
             if (!(err <= tol)) bad = 1;
             qsb_destroy(s);
@@ -87,8 +87,8 @@ int main(int argc, char **argv)
             }
             double norm = 0, pmax = 0; uint64_t idx = 0;
             check(qsb_norm_argmax(s, &norm, &idx, &pmax), "norm");
-            printf("{\"bench\": \"%s\", \"qubits\": %d, \"gates\": %zu, \"precision\": %d, \"lane_policy\": %d, \"passes\": %u, \"rounds\": %u, "
-                   "\"ms_min\": %.3f, \"ms_all\": [%s], \"norm\": %.9f}\n", path, nq, n, prec, pol[k], st.passes, st.rounds, best, all, norm);
+            printf("{\"bench\": \"%s\", \"qubits\": %d, \"gates\": %zu, \"precision\": %d, \"lane_policy\": %d, \"cx_kept\": %d, \"passes\": %u, \"rounds\": %u, "
+                   "\"ms_min\": %.3f, \"ms_all\": [%s], \"norm\": %.9f}\n", path, nq, n, prec, pol[k], cxh[k] == 5, st.passes, st.rounds, best, all, norm);
             fflush(stdout);
             if (fabs(norm - 1.0) > (prec == 64 ? 1e-9 : 1e-3)) bad = 1;
             qsb_plan_destroy(p);
