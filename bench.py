@@ -511,7 +511,7 @@ def main():
     ap.add_argument("--no-sink", type=int, default=0, help="planner A/B (qsb_options_t.reserved[6]): 1 = do not sink thread-level phases to later rounds, 2 = first-come tile choice (no hill climbing), 3 = no end-of-pass lane relocation, 4 = lane relocation only on conflict")
     ap.add_argument("--fused", type=int, default=0, help="multi-GPU A/B: exchange flavour, 0 = default (fused peer scatter; pipelined at 2 GPUs), 1 = fused peer scatter (direct: victims anywhere), 2 = NCCL all-to-all, 3 = pipelined copy-engine exchange, 4 = round-1 fused flavour")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--res4", type=int, default=0, help="planner A/B: qsb_options_t.reserved[4] (1 = vector-bit phases not deferred, 2 = no 2x2 products, 3 = no Hadamard-like slot form, 4 = no merged phase runs, 5 = CX next to an h stays a CX)")
+    ap.add_argument("--res4", type=int, default=0, help="planner A/B: qsb_options_t.reserved[4] (1 = vector-bit phases not deferred, 2 = no 2x2 products, 3 = no Hadamard-like slot form, 4 = no merged phase runs, 5 = h cx h stays as it is, 6 = CX -> controlled phase with an h on one side too)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

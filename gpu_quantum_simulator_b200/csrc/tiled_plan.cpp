@@ -354,7 +354,7 @@ void fuse_same_qubit(std::vector<COp> &ops, int n, double gphase[2])
  * phase gate and no matrix at all).  The moved gate commutes with everything it passes: nothing between the two ops
  * touches the target, and the controlled phase stays at the CX's place, so it reads the controls when the CX did.
  * Random layered workload (one of {h, rx, rz} per qubit and layer): 5 of 9 CX have an h next to their target. */
-void cx_through_h(std::vector<COp> &ops, double gphase[2])
+void cx_through_h(std::vector<COp> &ops, double gphase[2], bool one_sided)
 {
     const int N = (int)ops.size();
     std::vector<char> dead(N, 0);
@@ -392,6 +392,20 @@ void cx_through_h(std::vector<COp> &ops, double gphase[2])
         double D[8];
         int j = i + 1;
         while (j < N && (dead[j] || !touches(ops[j], t))) j++;
+        if (!one_sided) {
+            /* Default: only when a Hadamard-like gate sits on BOTH sides of the CX, where the rewrite removes two matrix
+             * ops.  With one H the rewrite trades a multiplexed gate (the CX rides for free in the gate's slot) for a
+             * plain gate plus a controlled phase, and that phase costs a slot of its own whenever another gate on the
+             * target follows in the same round: on the 30 q layered circuit the one-sided rewrite saves 1-2 passes and
+             * 13 rounds but adds 100 diagonal slots (479 instead of 378 arithmetic slots), and the arithmetic slots are
+             * what the kernel's time follows (call 33: 25 rounds and 2 passes fewer were worth 2 ms of 118). */
+            int k2 = i - 1;
+            while (k2 >= 0 && (dead[k2] || !touches(ops[k2], t))) k2--;
+            double D2[8];
+            const bool fw = j < N && repl[j].empty() && plain_mat_on(ops[j], t) && conj_x(ops[j].m, true, D);
+            const bool bw = k2 >= 0 && repl[k2].empty() && plain_mat_on(ops[k2], t) && conj_x(ops[k2].m, false, D2);
+            if (!(fw && bw)) continue;
+        }
         if (j < N && repl[j].empty() && plain_mat_on(ops[j], t) && conj_x(ops[j].m, true, D)) {
             std::vector<COp> seq; seq.push_back(ops[j]);
             if (!canon_one(D, cx.ctrl, t, seq, gphase)) continue;
@@ -1593,7 +1607,8 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
     int8_t wire[64];
     relabel_swaps(cops, n, wire);
     double gph[2] = {gphase[0], gphase[1]};
-    if (!(opt && (opt->reserved[4] == 2 || opt->reserved[4] == 5))) cx_through_h(cops, gph);   /* reserved[4] = 5: CX stays CX next to an h (A/B) */
+    /* reserved[4] = 5: CX stays CX next to an h (A/B); 6: rewritten with an h on one side too (the build of GPU call 33) */
+    if (!(opt && (opt->reserved[4] == 2 || opt->reserved[4] == 5))) cx_through_h(cops, gph, opt && opt->reserved[4] == 6);
     if (!(opt && opt->reserved[4] == 2)) fuse_same_qubit(cops, n, gph);      /* reserved[4] = 2: no 2x2 products (A/B, tests) */
     absorb_cx(cops, n);
     if (!(gph[0] == 1.0 && gph[1] == 0.0)) {

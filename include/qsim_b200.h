@@ -86,8 +86,8 @@ typedef struct qsb_options {
      *   [2] k+1 = trim tail rounds of SM-bound passes that hold fewer than k gates (default k = 2; 1 = off)
      *   [3] fusion-depth cap: stop adding rounds to a pass at this estimated SM cost (unit-form gate units)
      *   [4] 1 = do not defer phase gates that touch a vector bit; 2 = no 2x2 products of consecutive one-qubit gates;
-     *       4 = no merged controlled-phase runs (G_DIAGA); 5 = a CX next to an h on its target stays a CX (default: it
-     *       becomes a controlled phase)
+     *       4 = no merged controlled-phase runs (G_DIAGA); 5 = a CX between two h on its target stays a CX (default: h cx h becomes one
+     *       controlled phase); 6 = the rewrite also with an h on one side only (fewer passes, more diagonal slots)
      *   [5] exchange flavour: 1 direct fused peer scatter (victims trade places with the rank bits wherever they are),
      *       2 NCCL all-to-all, 3 pipelined copy-engine exchange, 4 round-1 fused scatter (victims moved to the top local
      *       positions first)   (0: chosen by qsb_comm_init -- 1, or 2 if the peer shards cannot be mapped)

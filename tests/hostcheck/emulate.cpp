@@ -235,6 +235,8 @@ extern "C" int qsb_hostcheck_run(int num_q, int prec, int low_bits, const qsb_ga
 {
     qsb_options_t opt; memset(&opt, 0, sizeof opt);
     opt.precision = prec; opt.low_bits = low_bits; opt.world_size = 1;
+    if (getenv("QSB_HC_RES4")) opt.reserved[4] = atoi(getenv("QSB_HC_RES4"));   /* planner A/B knobs for the tests */
+    if (getenv("QSB_HC_RES6")) opt.reserved[6] = atoi(getenv("QSB_HC_RES6"));
     g_low_a = low_bits;
     const int T = tiled_min_local_bits(prec, &opt);
     const int nloc = std::max(num_q, T);
@@ -267,6 +269,8 @@ extern "C" void *qsb_hostcheck_plan(int num_q, int prec, int low_bits, int world
 {
     qsb_options_t opt; memset(&opt, 0, sizeof opt);
     opt.precision = prec; opt.low_bits = low_bits; opt.world_size = world; opt.rank = rank; opt.reserved[0] = swap_min_ops;
+    if (getenv("QSB_HC_RES4")) opt.reserved[4] = atoi(getenv("QSB_HC_RES4"));   /* planner A/B knobs for the tests */
+    if (getenv("QSB_HC_RES6")) opt.reserved[6] = atoi(getenv("QSB_HC_RES6"));
     int g = 0; while ((1 << g) < world) g++;
     const int T = tiled_min_local_bits(prec, &opt);
     const int nloc = std::max(num_q - g, T);
