@@ -55,7 +55,8 @@ def test_fusion_factor_on_headline_workload():
     circ = circuits.random_layered(30, 20, 12345)
     st = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32)
     assert st["source_gates"] == 900
-    assert st["passes"] <= 17 and st["rounds"] <= 105   # 2^12-amplitude tiles, hill-climbed tiles, lane relocation, h cx h -> cz
+    # 2^12-amplitude tiles, hill-climbed tiles, lane relocation, h cx h -> cz, rx cx rx -> rx cx
+    assert st["passes"] <= 18 and st["rounds"] <= 106 and st["device_ops"] <= 820
     assert st["bytes_moved"] == st["passes"] * 2 * (1 << 30) * 8
     st64 = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=64)
     assert st64["passes"] <= 19 and st64["rounds"] <= 110
@@ -63,12 +64,12 @@ def test_fusion_factor_on_headline_workload():
     assert first_come["passes"] >= st["passes"] + 4
     # without the end-of-pass lane relocation: more passes, and empty rounds that only turn the registers
     no_reloc = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 3])
-    assert no_reloc["passes"] >= st["passes"] + 2 and no_reloc["rounds"] >= st["rounds"] + 8
+    assert no_reloc["passes"] >= st["passes"] + 1 and no_reloc["rounds"] >= st["rounds"] + 8
     conflict_only = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 0, 0, 4])
     assert st["passes"] <= conflict_only["passes"] <= no_reloc["passes"]
     # CX kept as CX next to an h on its target (reserved[4] = 5): the schedule of call 32
     cx_kept = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 5])
-    assert cx_kept["passes"] >= st["passes"] + 1 and cx_kept["rounds"] >= st["rounds"] + 10 and cx_kept["device_ops"] >= st["device_ops"] + 30
+    assert cx_kept["passes"] >= st["passes"] and cx_kept["rounds"] >= st["rounds"] + 10 and cx_kept["device_ops"] >= st["device_ops"] + 50
     # rewritten with an h on ONE side of the CX too (reserved[4] = 6, the schedule of call 33): fewer passes and rounds, but every
     # such CX is now a gate plus a phase instead of one multiplexed gate
     one_sided = q.plan_dry_run(30, q.gates_from_circuit(circ), precision=32, reserved=[0, 0, 0, 0, 6])
@@ -91,6 +92,8 @@ def test_cx_next_to_a_hadamard_becomes_a_controlled_phase():
         [("h", (2,), ()), ("ccx", (0, 1, 2), ()), ("h", (2,), ())],
         [("h", (1,), ()), ("s", (1,), ()), ("cx", (0, 1), ()), ("sdg", (1,), ()), ("h", (1,), ())],
         [("cx", (0, 1), ()), ("rz", (0,), (0.4,)), ("x", (0,), ()), ("h", (1,), ()), ("cx", (1, 0), ()), ("h", (0,), ())],
+        # gates that commute with X hop over the CX and multiply (rx cx rx -> one multiplexed gate)
+        [("rx", (1,), (0.7,)), ("cx", (0, 1), ()), ("rx", (1,), (-1.9,)), ("cx", (2, 1), ()), ("x", (1,), ()), ("ccx", (0, 3, 1), ()), ("rx", (1,), (0.2,))],
     ]
     for prec in (32, 64):
         for tail in cases:
@@ -108,6 +111,8 @@ def test_cx_next_to_a_hadamard_becomes_a_controlled_phase():
     assert st["device_ops"] <= 2 and st["rounds"] == 1   # one controlled phase (+ the rounding of h.h as a global scalar)
     kept = q.plan_dry_run(4, q.gates_from_circuit(cz), reserved=[0, 0, 0, 0, 5])
     assert kept["device_ops"] == 3 and kept["rounds"] == 2
+    hop = [("rx", (1,), (0.7,)), ("cx", (0, 1), ()), ("rx", (1,), (0.4,))]
+    assert q.plan_dry_run(4, q.gates_from_circuit(hop))["device_ops"] < q.plan_dry_run(4, q.gates_from_circuit(hop), reserved=[0, 0, 0, 0, 5])["device_ops"]
 
 
 def test_multi_control_and_global_phase_gates():
