@@ -346,21 +346,25 @@ void fuse_same_qubit(std::vector<COp> &ops, int n, double gphase[2])
     ops.swap(res);
 }
 
-/* CX next to a Hadamard-like gate on its target.  If H.X.H^-1 = D is diagonal (H = the Hadamard gate, S.H, ...), then
- * "CX, then H" is "H, then controlled-D", and "H, then CX" is "controlled-(H^-1.X.H), then H": the non-diagonal two-qubit
- * gate becomes a controlled PHASE, which needs no residency, costs one entry of a thread-phase list instead of a
- * multiplexed gate, and no longer separates H from the one-qubit gate on the other side of the CX -- the 2x2 products
- * of fuse_same_qubit then see them as neighbours (h, cx, h -- the reference's spelling of CZ, SURVEY.md 8c -- is one
- * phase gate and no matrix at all).  The moved gate commutes with everything it passes: nothing between the two ops
- * touches the target, and the controlled phase stays at the CX's place, so it reads the controls when the CX did.
- * Random layered workload (one of {h, rx, rz} per qubit and layer): 5 of 9 CX have an h next to their target. */
+/* CX between one-qubit gates on its target: two algebraic rewrites that remove matrix ops before anything is scheduled.
+ *  (1) If H.X.H^-1 = D is diagonal (H = the Hadamard gate, S.H, ...), then "CX, then H" is "H, then controlled-D", and
+ *      "H, then CX" is "controlled-(H^-1.X.H), then H": the non-diagonal two-qubit gate becomes a controlled PHASE (no
+ *      residency, one entry of a thread-phase list) and no longer separates H from the one-qubit gate on the other side
+ *      of the CX -- the 2x2 products of fuse_same_qubit then see them as neighbours.  h, cx, h -- the reference's
+ *      spelling of CZ, SURVEY.md 8c -- is one phase gate and no matrix at all.  Applied when such a gate sits on both
+ *      sides (one_sided = false, the default) or on either side (one_sided: reserved[4] = 6, the build timed in GPU call 33).
+ *  (2) Gates that commute with X (rx, x) on both sides of the CX: the later one hops over the CX and the 2x2 products make
+ *      one gate of the two, which then absorbs the CX (absorb_cx).
+ * The moved gate commutes with everything it passes: nothing between the two ops touches the target, and the CX or the
+ * controlled phase stays at the CX's place, so it reads the controls when the CX did.
+ * Random layered workload (one of {h, rx, rz} per qubit and layer): 1 of 9 CX sits between two h, 1 of 9 between two rx. */
 void cx_through_h(std::vector<COp> &ops, double gphase[2], bool one_sided)
 {
     const int N = (int)ops.size();
     std::vector<char> dead(N, 0);
     std::vector<std::vector<COp>> repl(N);
     auto touches = [](const COp &o, int t) { return o.target == t || ((o.ctrl >> t) & 1); };
-    /* D = H.X.H^-1 (forward) or H^-1.X.H (backward), H unitary; true if D is diagonal to rounding */
+    /* D = H.X.H^-1 (forward) or H^-1.X.H (backward), H unitary; 1 if D is diagonal to rounding, 2 if D = X, else 0 */
     auto conj_x = [](const double *H, bool forward, double *D) -> int {
         auto mul = [](const double *A, const double *B, double *C) {       /* C = A.B, row-major complex 2x2 */
             for (int r = 0; r < 2; r++) for (int c = 0; c < 2; c++) {
