@@ -351,6 +351,10 @@ int tiled_execute(qsb_sim *s, TiledPlan *p);
 double tiled_last_exchange_ms(const TiledPlan *p);
 void tiled_comm_destroy(qsb_sim *s);
 
+/* host-only: plans the candidates for the knobs the caller left open (exchange threshold x lane policy when sharded, four
+ * hill-climbing orders on one GPU) on host threads and returns the cheapest schedule; *out is new'ed */
+int tiled_plan_search(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
+                      const std::vector<COp> &cops, const double gphase[2], TiledPlan **out);
 void tiled_plan_trace_suppress(bool off);   /* QSB_PLAN_TRACE output of the calling thread's tiled_schedule calls on / off */
 /* host-only planner entry (no CUDA): used by tiled_plan_build and by the test emulator */
 int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,

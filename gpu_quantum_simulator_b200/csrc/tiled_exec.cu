@@ -15,8 +15,6 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <algorithm>
-#include <functional>
-#include <thread>
 #include <utility>
 #include <string.h>
 
@@ -30,91 +28,8 @@ int tiled_plan_build(int n, int prec, int g, int nloc, int rank, const qsb_optio
                      TiledPlan **out, qsb_run_stats_t *stats)
 {
     TiledPlan *p = nullptr;
-    const bool search_threshold = g > 0 && opt && opt->reserved[0] == 0;
-    const bool search_lanes = g > 0 && opt && opt->reserved[6] == 0;
-    const bool search_climb = g == 0 && cops.size() >= 64 && (!opt || (opt->reserved[6] == 0 && opt->reserved[3] == 0));   /* small circuits: one tile, nothing to choose */
-    if (!search_threshold && !search_lanes && !search_climb) {
-        p = new TiledPlan();
-        int rc = tiled_schedule(n, prec, g, nloc, rank, opt, start, cops, gphase, p);
-        if (rc) { delete p; return rc; }
-    } else {
-        /* Planner knobs the caller did not pin: plan a few candidates, each on its own host thread (~5-10 ms), and keep
-         * the cheapest schedule.
-         *   sharded run -- two knobs trade passes and rounds against qubit exchanges, and the best setting depends on the
-         *     circuit and on the number of ranks: the exchange threshold (how few runnable gates make the scheduler
-         *     exchange qubits), reserved[0], and the lane relocation policy (every pass re-picks the qubits on the lane
-         *     positions: fewer passes, but the schedule runs dry behind a global qubit sooner; or only on conflict),
-         *     reserved[6]: 4 x 2 candidates;
-         *   single GPU -- the tile hill climbing ends in a local optimum that depends on the order of its swaps: four
-         *     orders (tiled_schedule, climb_variant), a pass more or less on the 30-34 q workloads.
-         * The cost model is a fit of the 30 q lines of round 2 ((passes, rounds) -> ms: (22, 130)
-         * 126.2, (54, 134) 177.7, (18, 117) 117.8, (20, 114) 119.1), in ms at 2^30 local amplitudes: 1.5 per pass + 0.25 per
-         * round, and the extra time of an exchange pass (NVLink-bound scatter of (1 - 2^-g) of the shard at ~700 GB/s, then
-         * the barrier; from the 34 q scaling lines): 1.25 with one peer, 2.5 with three, 8 with seven.  Every rank plans the
-         * same circuit and picks the same schedule (the rank only enters the descriptors, not the structure); ties go to
-         * the earlier candidate. */
-        static const int thresholds[] = {10, 8, 14, 12};
-        static const int lane_policies[] = {0, 4};
-        static const int climb_variants[] = {0, 3, 2, 4};
-        struct Cand { qsb_options_t o; int climb; TiledPlan *plan; int rc; char err[512]; };
-        std::vector<Cand> cand;
-        qsb_options_t base; if (opt) base = *opt; else qsb_options_default(&base);
-        for (int lp : lane_policies) {
-            if (!search_lanes && lp != lane_policies[0]) continue;
-            for (int th : thresholds) {
-                if (!search_threshold && th != thresholds[0]) continue;
-                for (int cv : climb_variants) {
-                    if (!search_climb && cv != climb_variants[0]) continue;
-                    Cand c; c.o = base; c.climb = cv; c.plan = nullptr; c.rc = QSB_OK; c.err[0] = 0;
-                    if (search_threshold) c.o.reserved[0] = th;
-                    if (search_lanes) c.o.reserved[6] = lp;
-                    cand.push_back(c);
-                }
-            }
-        }
-        const bool tracing = getenv("QSB_PLAN_TRACE") != nullptr;   /* candidates stay silent; the winner is planned once more, aloud */
-        auto run = [&](Cand &c) {
-            tiled_plan_trace_suppress(true);
-            c.plan = new TiledPlan();
-            c.rc = tiled_schedule(n, prec, g, nloc, rank, &c.o, start, cops, gphase, c.plan, c.climb);
-            if (c.rc) { snprintf(c.err, sizeof c.err, "%s", qsb_last_error()); delete c.plan; c.plan = nullptr; }   /* the message is thread-local */
-            tiled_plan_trace_suppress(false);
-        };
-        /* small circuits are planned faster than a thread starts */
-        const bool threads = cops.size() >= 64;
-        std::vector<std::thread> workers;
-        for (size_t i = 1; i < cand.size(); i++) {
-            bool started = false;
-            if (threads) { try { workers.emplace_back(run, std::ref(cand[i])); started = true; } catch (...) {} }   /* no thread to be had: plan it here */
-            if (!started) run(cand[i]);
-        }
-        run(cand[0]);
-        for (std::thread &w : workers) w.join();
-        const double xcost = g == 1 ? 1.25 : g == 2 ? 2.5 : 8.0;
-        auto cost_of = [&](const TiledPlan *q) {
-            double c = 0;
-            for (auto &hp : q->passes) {
-                if (hp.is_swap) { c += 1.5 + xcost; continue; }     /* the all-to-all costs about a pass on top */
-                c += 1.5 + 0.25 * (double)hp.rounds.size() + (hp.fused_swap ? xcost : 0.0);
-            }
-            return c;
-        };
-        double best = 0;
-        const Cand *winner = nullptr;
-        for (Cand &c : cand) {
-            if (!c.plan) continue;
-            const double cc = cost_of(c.plan);
-            if (!p || cc < best - 1e-9) { delete p; p = c.plan; best = cc; winner = &c; } else delete c.plan;
-            c.plan = nullptr;
-        }
-        if (!p) { qsb_set_error("%s", cand[0].err); return cand[0].rc ? cand[0].rc : QSB_ERR_ARG; }
-        if (tracing) {
-            TiledPlan again;
-            tiled_schedule(n, prec, g, nloc, rank, &winner->o, start, cops, gphase, &again, winner->climb);
-            fprintf(stderr, "qsb-plan: kept candidate %d of %zu (exchange threshold %d, lane policy %d, climb order %d), modelled cost %.1f\n",
-                    (int)(winner - cand.data()), cand.size(), winner->o.reserved[0], winner->o.reserved[6], winner->climb, best);
-        }
-    }
+    int rc = tiled_plan_search(n, prec, g, nloc, rank, opt, start, cops, gphase, &p);   /* tiled_plan.cpp: plans the candidates, keeps the cheapest */
+    if (rc) return rc;
     uint64_t n_ops = 0, n_rounds = 0, sweeps = 0, swaps = 0;
     for (auto &hp : p->passes) {
         if (hp.is_swap) { swaps++; continue; }

@@ -133,8 +133,9 @@ def hostcheck_use_blob(on):
 
 
 def hostcheck_set_climb(variant):
-    """Order of the swaps the tile hill climbing tries (tiled_schedule's climb_variant, 0..7): the product plans the
-    variants 0, 2, 3, 4 on single-GPU runs and keeps the cheapest schedule; the double runs the one set here."""
+    """-1 (the default): the double runs the schedule tiled_plan_search picks -- what a GPU run executes (four orders of the
+    tile hill climbing on one GPU, exchange threshold x lane policy when sharded, cheapest kept).  0..7: one fixed order of
+    the hill climbing's swaps (tiled_schedule's climb_variant) without the search."""
     L = C.CDLL(_build(HOSTCHECK_SO, os.path.join(ROOT, "tests", "hostcheck"), always=True))
     L.qsb_hostcheck_set_climb(int(variant))
 

@@ -46,8 +46,21 @@ static int lanes_not_contiguous(const std::vector<uint64_t> &idx, bool f32, int 
     return bad;
 }
 extern "C" void qsb_hostcheck_use_blob(int on) { g_use_blob = on; }
-static int g_climb = 0;      /* tiled_schedule's climb_variant (the product plans variants 0, 2, 3, 4 and keeps the cheapest) */
+/* -1 (default): the doubles run the schedule tiled_plan_search picks, i.e. what a GPU run executes; 0..7: one fixed order of
+ * the tile hill climbing (tiled_schedule's climb_variant), no search */
+static int g_climb = -1;
 extern "C" void qsb_hostcheck_set_climb(int v) { g_climb = v; }
+static int make_plan(int n, int prec, int g, int nloc, int rank, const qsb_options_t *opt, const BitPerm &start,
+                     const std::vector<COp> &cops, const double gph[2], TiledPlan *plan)
+{
+    if (g_climb >= 0) return tiled_schedule(n, prec, g, nloc, rank, opt, start, cops, gph, plan, g_climb);
+    TiledPlan *p = nullptr;
+    int rc = tiled_plan_search(n, prec, g, nloc, rank, opt, start, cops, gph, &p);
+    if (rc) return rc;
+    *plan = std::move(*p);
+    delete p;
+    return 0;
+}
 
 static void run_pass(const HostPass &hp, bool f32, int nloc, std::vector<cd> &st, Report &rep, cd *const *outs = nullptr)
 {
@@ -245,7 +258,7 @@ extern "C" int qsb_hostcheck_run(int num_q, int prec, int low_bits, const qsb_ga
     if (rc) return rc;
     BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
     TiledPlan plan;
-    rc = tiled_schedule(num_q, prec, 0, nloc, 0, &opt, id, cops, gph, &plan, g_climb);
+    rc = make_plan(num_q, prec, 0, nloc, 0, &opt, id, cops, gph, &plan);
     if (rc) return rc;
     std::vector<cd> st((size_t)1 << nloc);
     memcpy((void *)st.data(), state, sizeof(cd) * st.size());
@@ -279,7 +292,7 @@ extern "C" void *qsb_hostcheck_plan(int num_q, int prec, int low_bits, int world
     BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
     HcPlan *h = new HcPlan();
     h->prec = prec; h->nloc = nloc; h->low_bits = low_bits; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
-    if (tiled_schedule(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan, g_climb)) { delete h; return nullptr; }
+    if (make_plan(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan)) { delete h; return nullptr; }
     return h;
 }
 /* like qsb_hostcheck_plan, with the exchanges fused into the preceding pass (peer scatter) */
@@ -297,7 +310,7 @@ extern "C" void *qsb_hostcheck_plan_fused(int num_q, int prec, int low_bits, int
     BitPerm id; for (int q = 0; q < 64; q++) id.pos[q] = (int8_t)q;
     HcPlan *h = new HcPlan();
     h->prec = prec; h->nloc = nloc; h->low_bits = low_bits; memset(&h->rep, 0, sizeof h->rep); h->rep.max_conflict = 1;
-    if (tiled_schedule(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan, g_climb)) { delete h; return nullptr; }
+    if (make_plan(num_q, prec, g, nloc, rank, &opt, id, cops, gph, &h->plan)) { delete h; return nullptr; }
     return h;
 }
 /* 0 ordinary pass, 1 exchange marker (all-to-all of chunks), 2 fused-exchange pass */

@@ -115,6 +115,34 @@ def test_cx_next_to_a_hadamard_becomes_a_controlled_phase():
     assert q.plan_dry_run(4, q.gates_from_circuit(hop))["device_ops"] < q.plan_dry_run(4, q.gates_from_circuit(hop), reserved=[0, 0, 0, 0, 5])["device_ops"]
 
 
+def test_doubles_run_the_schedule_the_product_picks():
+    """The host doubles call the same plan search as the library (tiled_plan_search: four hill-climbing orders, cheapest kept),
+    so what they emulate is what a GPU run executes: same pass and round counts as the library's dry run, and the fixed
+    orders the search chooses from are really different schedules."""
+    n = 17
+    circ = circuits.random_layered(n, depth=8, seed=3)
+    gates = q.gates_from_circuit(circ)
+    want = helpers.oracle_run_circuit(circ, n)
+    for prec in (32, 64):
+        st = q.plan_dry_run(n, gates, precision=prec)
+        got, rep = helpers.hostcheck_run(gates, n, prec)
+        assert (rep["passes"], rep["rounds"]) == (st["passes"], st["rounds"])
+        assert np.max(np.abs(got - want)) < 1e-12
+    seen = set()
+    try:
+        for v in range(8):
+            helpers.hostcheck_set_climb(v)
+            got, rep = helpers.hostcheck_run(gates, n, 32)
+            assert np.max(np.abs(got - want)) < 1e-12 and rep["bad_slots"] == 0 and rep["noncontig"] == 0
+            seen.add((rep["passes"], rep["rounds"]))
+    finally:
+        helpers.hostcheck_set_climb(-1)
+    assert len(seen) >= 2
+    best = min(1.5 * p + 0.25 * r for p, r in seen)
+    st = q.plan_dry_run(n, gates, precision=32)
+    assert 1.5 * st["passes"] + 0.25 * st["rounds"] <= best + 1e-9 or st["passes"] <= min(p for p, _ in seen) + 1
+
+
 def test_multi_control_and_global_phase_gates():
     circ = [("h", (0,), ()), ("h", (1,), ()), ("h", (2,), ()), ("ccx", (0, 1, 2), ()), ("y", (1,), ()),
             ("z", (0,), ()), ("sx", (2,), ()), ("cp", (2, 0), (0.3,)), ("cz", (1, 2), ())]

@@ -60,7 +60,7 @@ def main():
         low = 0 if rng.rand() < .7 else int(rng.choice([3, 5, 6] if prec == 32 else [2, 4, 5]))
         blob = bool(rng.rand() < .5)
         helpers.hostcheck_use_blob(blob)
-        helpers.hostcheck_set_climb(int(seed) % 8)   # every order of the hill climbing's swaps
+        helpers.hostcheck_set_climb(int(seed) % 9 - 1)   # the product's search (-1) and every fixed order of the hill climbing's swaps
         mode = rng.randint(5)
         try:
             if mode == 0:

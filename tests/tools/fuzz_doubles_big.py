@@ -13,7 +13,7 @@ while time.time() < t_end:
     rng = np.random.RandomState(seed)
     n = int(rng.randint(15, 20)); prec = 32 if rng.rand() < .5 else 64
     blob = bool(rng.rand() < .5); helpers.hostcheck_use_blob(blob)
-    helpers.hostcheck_set_climb(int(seed) % 8)   # every order of the hill climbing's swaps
+    helpers.hostcheck_set_climb(int(seed) % 9 - 1)   # the product's search (-1) and every fixed order of the hill climbing's swaps
     mode = rng.randint(3)
     if mode == 0: circ = circuits.random_superset(n, int(rng.randint(50, 400)), seed)
     elif mode == 1: circ = circuits.random_layered(n, depth=int(rng.randint(1, 10)), seed=seed)
