@@ -301,7 +301,11 @@ def run_ours(args):
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": "k_tile_pass", "bytes_per_launch": bytes_per_launch,
-                    "avg_launch_ms": pass_ms, "peak_source": peak_src}
+                    "avg_launch_ms": pass_ms, "peak_source": peak_src,
+                    "launches_per_circuit": pst["passes"], "rounds_per_launch": pst["rounds"] / max(pst["passes"], 1),
+                    "note": "one launch fuses ~45 gates in ~6 register/shared-memory rounds, so it runs longer than a stream of its 2*N*B bytes; "
+                            "the planner minimises circuit time (fewer, deeper launches lower this fraction while gates/s rise); "
+                            "at_30q.shallow_fusion is the same kernel with the fusion depth capped (HBM-bound regime)"}
         # second limit of the same kernel: every round but the first of a pass moves the whole tile
         # through shared memory once in each direction; peak = SMs x 128 B/clk x SM clock
         try:
