@@ -1758,7 +1758,15 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
         return QSB_OK;
     };
 
+    /* Termination.  An ordinary pass always consumes ops; an exchange need not (its permutation pass runs "whatever
+     * fits" with the victims' positions forced into the tile).  With a high exchange threshold on a circuit whose tail
+     * never offers that many runnable gates, the scheduler could exchange for ever: a second exchange without an op
+     * consumed since the first one is refused while this pass has anything to run, and a pass count that no schedule
+     * can reach ends the planning with an error instead of a hang (a candidate of tiled_plan_search is then dropped). */
+    size_t left_at_last_exchange = (size_t)-1;
+    const size_t max_plan_steps = 4 * N + 1024;
     while (left) {
+        if (plan->passes.size() > max_plan_steps) { qsb_set_error("internal: the scheduler does not terminate (%zu passes for %zu ops)", plan->passes.size(), N); return QSB_ERR_ARG; }
         uint64_t lowS = 0;
         for (int q = 0; q < n; q++) if (perm.pos[q] < M.a) lowS |= 1ULL << q;
         std::vector<COp> mine; std::vector<size_t> mine_idx; uint64_t S = 0;
@@ -1783,13 +1791,15 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             return blocked_global && nd < SWAP_MIN_OPS;
         };
         bool want_swap = g > 0 && starving(mine);
+        const bool exchanged_in_vain = left == left_at_last_exchange && !mine.empty();
+        if (exchanged_in_vain) want_swap = false;
         if (M.fused_direct) {
             /* Direct fused exchange (round 2): victims trade places with the rank bits wherever they are, so the
              * exchange needs no tile slot and ANY pass can carry it.  Take the last pass that still has a full load of
              * gates: if the schedule would starve once this pass is through, this pass scatters into the peers. */
             bool fuse_now = want_swap;
             for (size_t k : mine_idx) done[k] = 1;            /* look past this pass */
-            if (!fuse_now && !mine.empty()) {
+            if (!fuse_now && !mine.empty() && !exchanged_in_vain) {
                 std::vector<COp> m2; std::vector<size_t> i2; uint64_t S2 = 0;
                 collect(lowS, M.a, m2, i2, S2);
                 fuse_now = starving(m2);
@@ -1819,6 +1829,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
                     rc = emit_pass(S, 0, nullptr, mine, mine_idx, true, true, victim_pos);
                 }
                 if (rc) return rc == QSB_PLAN_OVERFLOW ? QSB_ERR_ARG : rc;
+                left_at_last_exchange = left;
                 for (int qq = 0; qq < n; qq++) {          /* position victim_pos[k] <-> rank bit k */
                     const int pp = perm.pos[qq];
                     for (int k = 0; k < g; k++) {
@@ -1900,6 +1911,7 @@ int tiled_schedule(int n, int prec, int g, int nloc, int rank, const qsb_options
             if (p >= nloc) perm.pos[q] = (int8_t)(p - g);
             else if (p >= nloc - g) perm.pos[q] = (int8_t)(p + g);
         }
+        left_at_last_exchange = left;
     }
     /* logical qubit q ended on wire[q] (relabel_swaps) */
     for (int q = 0; q < 64; q++) plan->end_perm.pos[q] = q < n ? perm.pos[wire[q]] : perm.pos[q];

@@ -63,6 +63,22 @@ def test_single_round_permutation_passes_synchronise_before_the_scatter():
     assert seen > 0, "no single-round permutation pass in the sample: the test checks nothing"
 
 
+@pytest.mark.timeout(300)
+def test_high_exchange_threshold_terminates():
+    """Found by the sharded fuzzer once the doubles ran the library's own plan search: with an exchange threshold the tail
+    of a circuit never reaches (14 runnable gates, one of the search's candidates) the NCCL-style schedule exchanged
+    qubits for ever -- each exchange's permutation pass consumed nothing.  A second exchange without an op consumed since
+    the first is now refused while the pass has anything to run; every threshold must plan, and reproduce the oracle."""
+    n, world, prec = 18, 4, 32            # fuzz seed 23600015: the 18-qubit QFT on four ranks
+    circ = circuits.qft(n)
+    want = helpers.oracle_run_circuit(circ, n)
+    for fused in (False, True):
+        for smo in (14, 20, 40, 0):
+            got, rep = helpers.sharded_host_run(q.gates_from_circuit(circ), n, world, prec, swap_min_ops=smo, fused=fused)
+            assert rep["bad_slots"] == 0 and np.max(np.abs(got - want)) < 1e-12, (fused, smo)
+            assert rep["swaps"] <= 6, (fused, smo, rep)
+
+
 def test_exchange_count_on_the_34_qubit_workload():
     circ = circuits.random_layered(34, 20, 12345)
     g = q.gates_from_circuit(circ)

@@ -18,7 +18,7 @@ while time.time() < t_end:
     T = 13 if prec == 32 else 12
     n = int(rng.randint(T + 2 * g, T + 2 * g + 4))
     fused = bool(rng.rand() < .5)
-    smo = int(rng.choice([0, 2, 4, 10]))
+    smo = int(rng.choice([0, 2, 4, 10, 14, 20]))   # 0: the product's search over thresholds and lane policies
     mode = rng.randint(3)
     if mode == 0: circ = circuits.random_superset(n, int(rng.randint(20, 200)), seed)
     elif mode == 1: circ = circuits.random_layered(n, depth=int(rng.randint(1, 6)), seed=seed)
