@@ -69,7 +69,10 @@ def gates_from_circuit(circ):
 
 def _options(precision, mode, low_bits, rank, world_size, device, reserved=None, use_graph=False, dense_k=0):
     """reserved: planner tuning knobs (qsb_options_t.reserved): [0] min gates before a qubit exchange,
-    [1] 2 = lazy diagonals on, [2] k+1 = trim tail rounds with < k gates (1 = off), [3] fusion-depth cost cap."""
+    [1] 2 = lazy diagonals on, [2] k+1 = trim tail rounds with < k gates (1 = off), [3] fusion-depth cost cap,
+    [4] gate rewrites (5 = CX between two h / two rx left alone, 6 = CX -> controlled phase with an h on one side too),
+    [5] exchange flavour, [6] 2 = first-come tiles, 3 / 4 = no / conflicts-only lane relocation; the full list is in
+    include/qsim_b200.h.  Knobs left at 0 are searched by the library where it plans several candidates."""
     o = Options()
     lib.qsb_options_default(C.byref(o))
     for k, v in enumerate(reserved or ()):
